@@ -1,0 +1,412 @@
+/* oracle/ref_driver.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Drives the reference's own hot-path functions (compiled unmodified from
+ * /root/reference by oracle/Makefile into oracle/_ref/libref_oracle.so):
+ *     fft1_b -> fft1_c -> fft1_waterfall -> fft1_mix1_fixed
+ * on a synthetic timf1 ring, the way wideband_dsp()/narrowband_dsp() do
+ * (wcw.c:1036-1085, wcw.c:1706-1716).  This file restates only the SIZING and
+ * table-initialisation glue of buf.c (which cannot be linked, it pulls in the
+ * GUI): get_wideband_sizes buf.c:139-332, timf3 sizes buf.c:645-657, table
+ * init buf.c:1297-1300,1403-1456, prepare_mixer buf.c:55-111, and
+ * make_wg_yfac wide_graph.c:956-1001.  All arithmetic on samples is done by
+ * the reference functions themselves.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include "osnum.h"
+#include "globdef.h"
+#include "uidef.h"
+#include "fft1def.h"
+#include "fft2def.h"
+#include "fft3def.h"
+#include "screendef.h"
+#include "seldef.h"
+#include "sigdef.h"
+#include "thrdef.h"
+#include "graphcal.h"
+
+#define REF_MAX_SEL 64
+
+typedef struct {
+  int input_mode;        /* ui.rx_input_mode bits: DWORD_INPUT=1 TWO_CHANNELS=2 IQ_DATA=4 */
+  int rf_channels;       /* ui.rx_rf_channels */
+  int ad_speed;          /* ui.rx_ad_speed */
+  int fft1_n;            /* log2(fft1_size) */
+  int fft1_version;      /* index into fft_cntrl[] (6, 7, 2, 1, 10 ...) */
+  int sinpow;            /* genparm[FIRST_FFT_SINPOW] */
+  int fft1_gain;         /* genparm[FIRST_FFT_GAIN] */
+  int mix1_red_n;        /* genparm[MIX1_BANDWIDTH_REDUCTION_N] */
+  int avg1num;           /* wg.fft_avg1num */
+  int avg2num;           /* wg_fft_avg2num */
+  int waterfall_avgnum;  /* wg.waterfall_avgnum */
+  int direction;         /* fft1_direction (+1/-1) */
+  int n_sel;             /* number of mix1 selections driven by this harness */
+  int first_xpoint;      /* wg.first_xpoint */
+  int xpoints;           /* wg.xpoints */
+  int xpoints_per_pixel; /* wg.xpoints_per_pixel */
+  int pixels_per_xpoint; /* wg.pixels_per_xpoint */
+  int wf_lines;          /* waterfall ring lines */
+  int sample_shift;      /* ui.sample_shift */
+} ref_cfg;
+
+typedef struct {
+  float phase, phase_step, phase_rot, old_phase;
+  int point, old_point;
+  double selfreq;
+} sel_state;
+
+static ref_cfg C;
+static sel_state SEL[REF_MAX_SEL];
+static float *timf3_all;        /* n_sel regions of 2*timf3_size floats */
+static int frame_bytes;
+static int inited = 0;
+extern int ref_last_lirerr;
+
+/* a few globals live in reference files that cannot be linked */
+/* (everything else comes from the reference's own *var.c objects) */
+
+static void *zalloc(size_t n) { void *p = calloc(n + 64, 1); if (!p) { fprintf(stderr, "oom\n"); exit(3);} return p; }
+
+int ref_fft1_size(void) { return fft1_size; }
+int ref_fft1_block(void) { return fft1_block; }
+int ref_interleave_points(void) { return fft1_interleave_points; }
+int ref_new_points(void) { return fft1_new_points; }
+int ref_timf1_blockbytes(void) { return timf1_blockbytes; }
+int ref_mix1_size(void) { return (int)mix1.size; }
+int ref_mix1_interleave(void) { return (int)mix1.interleave_points; }
+int ref_mix1_new_points(void) { return (int)mix1.new_points; }
+int ref_mix1_crossover(void) { return (int)mix1.crossover_points; }
+int ref_timf3_block(void) { return timf3_block; }
+int ref_timf3_size(void) { return timf3_size; }
+int ref_wg_xpixels(void) { return wg_xpixels; }
+int ref_sumsq_bufsize(void) { return fft1_sumsq_bufsize; }
+int ref_sumsq_pa(void) { return fft1_sumsq_pa; }
+int ref_sumsq_counter(void) { return fft1_sumsq_counter; }
+int ref_waterf_ptr(void) { return wg_waterf_ptr; }
+int ref_waterf_size(void) { return wg_waterf_size; }
+int ref_first_point(void) { return fft1_first_point; }
+int ref_last_point(void) { return fft1_last_point; }
+int ref_lirerr(void) { return ref_last_lirerr; }
+float ref_points_per_hz(void) { return fftx_points_per_hz; }
+float ref_filtercorr_start(void) { return fft1_filtercorr_start; }
+const float *ref_window(void) { return fft1_window; }
+const float *ref_filtercorr(void) { return fft1_filtercorr; }
+const float *ref_desired(void) { return fft1_desired; }
+const float *ref_sumsq(void) { return fft1_sumsq; }
+const float *ref_slowsum(void) { return fft1_slowsum; }
+const short *ref_waterf(void) { return wg_waterf; }
+const float *ref_waterf_yfac(void) { return wg_waterf_yfac; }
+const float *ref_waterf_sum(void) { return wg_waterf_sum; }
+const float *ref_mix1_fqwin(void) { return mix1_fqwin; }
+const float *ref_mix1_window(void) { return mix1.window; }
+const float *ref_mix1_cos2win(void) { return mix1.cos2win; }
+const float *ref_mix1_sin2win(void) { return mix1.sin2win; }
+const float *ref_timf3(int ss) { return timf3_all + (size_t)ss * 2 * timf3_size; }
+int ref_timf3_pa(void) { return timf3_pa; }
+void ref_sel_state(int ss, float *f4, int *i2)
+{
+  f4[0] = SEL[ss].phase; f4[1] = SEL[ss].phase_step; f4[2] = SEL[ss].phase_rot; f4[3] = SEL[ss].old_phase;
+  i2[0] = SEL[ss].point; i2[1] = SEL[ss].old_point;
+}
+
+/* the reference's own table builders, exposed for oracle-port validation */
+void ref_make_window(int mo, int sz, int n, float *win) { make_window(mo, sz, n, win); }
+void ref_fftback(int size, int n, float *x)
+{
+  COSIN_TABLE *tab = zalloc(sizeof(COSIN_TABLE) * size);
+  unsigned short *perm = zalloc(sizeof(unsigned short) * size * 2);
+  init_fft(0, n, size, tab, perm);
+  fftback(size, n, x, tab, perm, 0);
+  free(tab); free(perm);
+}
+
+static void free_all(void)
+{
+  /* buffers are intentionally leaked between re-inits of this test harness
+     except the big ones */
+  free(timf1_char); timf1_char = NULL;
+  free(fft1_char); fft1_char = NULL;
+  free(fft1_sumsq); fft1_sumsq = NULL;
+  free(timf3_all); timf3_all = NULL;
+  free(wg_waterf); wg_waterf = NULL;
+}
+
+void ref_set_selfreq(int ss, double hz)
+{
+  SEL[ss].selfreq = hz;
+  SEL[ss].point = -1;         /* wide_graph.c:174 */
+}
+
+int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
+{
+  int i, j, k, v, mode_row;
+  unsigned int ui_, uj, uk;
+  float t1;
+  if (inited) free_all();
+  C = *cfg;
+  ref_last_lirerr = 0;
+  memset(&ui, 0, sizeof(ui));
+  memset(genparm, 0, sizeof(int) * (MAX_GENPARM + 2));
+  memset(&wg, 0, sizeof(wg));
+  ui.rx_input_mode = C.input_mode;
+  ui.rx_rf_channels = C.rf_channels;
+  ui.rx_ad_channels = (C.input_mode & IQ_DATA) ? 2 * C.rf_channels : C.rf_channels;
+  ui.rx_ad_speed = C.ad_speed;
+  ui.sample_shift = C.sample_shift;
+  ui.network_flag = 0;
+  ui.operator_skil = OPERATOR_SKIL_NEWCOMER;
+  rx_mode = 0;
+  kill_all_flag = 0;
+  internal_generator_flag = 0;
+  genparm[FIRST_FFT_SINPOW] = C.sinpow;
+  genparm[FIRST_FFT_GAIN] = C.fft1_gain;
+  genparm[MIX1_BANDWIDTH_REDUCTION_N] = C.mix1_red_n;
+  genparm[MIX1_NO_OF_CHANNELS] = 1;      /* harness loops selections itself, see ref_process */
+  genparm[SECOND_FFT_ENABLE] = 0;
+  genparm[MAX_NO_OF_SPURS] = 0;
+  genparm[FIRST_FFT_BANDWIDTH] = 100;
+  /* buf.c:149 + fft1var.c:74-79: find the VERNR column that maps to the wanted fft_cntrl row */
+  fft1mode = (ui.rx_input_mode & (TWO_CHANNELS + IQ_DATA)) / 2;
+  mode_row = fft1mode;
+  v = -1;
+  for (i = 0; i < MAX_FFT1_VERNR; i++) if (fft1_version[mode_row][i] == C.fft1_version) v = i;
+  if (v < 0) { fprintf(stderr, "[ref oracle] version %d not legal for fft1mode %d\n", C.fft1_version, fft1mode); return -1; }
+  genparm[FIRST_FFT_VERNR] = v;
+
+  /* ---- sizes, buf.c:165-332 with fft1_n given directly ---- */
+  twice_rxchan = 2 * ui.rx_rf_channels;
+  sw_onechan = (ui.rx_rf_channels == 1);
+  fft1_n = C.fft1_n;
+  fft1_size = 1 << fft1_n;
+  fft1_block = twice_rxchan * fft1_size;
+  fft1_use_gpu = 0;
+  fft1_muln = (fft_cntrl[FFT1_CURMODE].real2complex + 1) * fft_cntrl[FFT1_CURMODE].parall_fft;
+  fft1_mulblock = fft1_block * fft1_muln;
+  j = fft1_size * (fft_cntrl[FFT1_CURMODE].real2complex + 1);
+  fft1_permute_size = j; fft1_window_size = j; fft1_costab_size = j / 2;
+  if (fft_cntrl[FFT1_CURMODE].permute == 2) { fft1_costab_size *= 2; fft1_permute_size *= 2; fft1_window_size += 16; }
+  if (fft_cntrl[FFT1_CURMODE].doub == 0 && fft1_permute_size > 0x10000) { fprintf(stderr, "[ref oracle] N too big for float path\n"); return -2; }
+  fft1_blockbytes = fft1_block * (int)sizeof(float);
+  frame_bytes = 2 * ui.rx_ad_channels;
+  if (ui.rx_input_mode & DWORD_INPUT) frame_bytes *= 2;
+  /* buf.c:113-136 make_interleave_ratio (stored in a float) */
+  if (C.sinpow == 0) fft1_interleave_ratio = 0;
+  else if (C.sinpow == 9) fft1_interleave_ratio = 0.625;
+  else if (C.sinpow == 8) fft1_interleave_ratio = 0.8;
+  else fft1_interleave_ratio = 2 * asin(pow(0.5, 1.0 / C.sinpow)) / PI_L;
+  mix1.n = fft1_n - C.mix1_red_n;
+  if (mix1.n < 3) mix1.n = 3;
+  mix1.size = 1 << mix1.n;
+  mix1.interleave_points = fft1_interleave_ratio * mix1.size;
+  mix1.interleave_points &= 0xfffffffe;
+  fft1_interleave_points = mix1.interleave_points * (fft1_size / mix1.size);
+  fft1_new_points = fft1_size - fft1_interleave_points;
+  mix1.new_points = mix1.size - mix1.interleave_points;
+  timf1_blockbytes = fft1_new_points * frame_bytes;
+  if ((ui.rx_input_mode & IQ_DATA) == 0) timf1_blockbytes *= 2;
+  timf1_blockbytes *= fft1_muln;                 /* buf.c:616-617 */
+  timf1_sampling_speed = ui.rx_ad_speed;
+  if ((ui.rx_input_mode & IQ_DATA) == 0) timf1_sampling_speed *= 0.5;   /* buf.c:48-51 */
+  fft1_hz_per_point = (float)ui.rx_ad_speed / fft1_size;
+  if ((ui.rx_input_mode & IQ_DATA) == 0) fft1_hz_per_point /= 2;
+  fftx_points_per_hz = 1 / fft1_hz_per_point;
+  timf3_sampling_speed = timf1_sampling_speed / fft1_size * mix1.size;
+  timf3_block = twice_rxchan * mix1.new_points;
+  timf3_size = 16 * mix1.size * twice_rxchan;            /* pow2, includes the 2C factor (buf.c:645-655) */
+  timf3_mask = timf3_size - 1;
+  timf3_totsiz = timf3_size;
+  yieldflag_wdsp_fft1 = 0; yieldflag_ndsp_mix1 = 0;
+  fft1_calibrate_flag = 0;
+  fft1_direction = C.direction;
+  pg_ch2_c1 = 1; pg_ch2_c2 = 0;
+  fft1afc_flag = 0; fft1_correlation_flag = 0; no_of_spurs = 0;
+
+  /* ---- rings ---- */
+  timf1_bytes = timf1_bytes_req;
+  timf1_bytemask = timf1_bytes - 1;
+  timf1_char = zalloc(timf1_bytes);
+  timf1_short_int = (short int *)timf1_char; timf1_int = (int *)timf1_char; timf1_float = (float *)timf1_char;
+  timf1p_pa = timf1p_pb = timf1p_px = 0;
+  max_fft1n = max_fft1n_req;
+  fft1n_mask = max_fft1n - 1;
+  fft1_bytes = max_fft1n * fft1_blockbytes;
+  fft1_mask = max_fft1n * fft1_block - 1;
+  fft1_char = zalloc(2 * (size_t)fft1_bytes);
+  fft1_float = (float *)fft1_char;
+  fft1_pa = fft1_pb = fft1_px = 0; fft1_na = fft1_nb = fft1_nx = fft1_nm = 0;
+  fft1_tmp_bytes = fft1_blockbytes * (fft_cntrl[FFT1_CURMODE].real2complex + 1) * fft_cntrl[FFT1_CURMODE].parall_fft;
+  if (fft_cntrl[FFT1_CURMODE].doub) fft1_tmp_bytes *= 2;
+  fftw_tmp = zalloc(fft1_tmp_bytes + 64);
+  fft1_sumsq_bufsize = 16 * fft1_size; if (C.avg2num + 2 > 16) { k = C.avg2num + 2; make_power_of_two(&k); fft1_sumsq_bufsize = k * fft1_size; }
+  fft1_sumsq_mask = fft1_sumsq_bufsize - 1;
+  fft1_sumsq = zalloc(sizeof(float) * fft1_sumsq_bufsize);
+  fft1_slowsum = zalloc(sizeof(float) * fft1_size);
+  fft1_sumsq_pa = 0; fft1_sumsq_counter = 0; fft1_sumsq_pwg = 0;
+  ag_pa = 0; ag_mask = 255;
+
+  /* ---- tables, buf.c:1403-1456 ---- */
+  i = (fft_cntrl[FFT1_CURMODE].permute == 2) ? 2 : 1;
+  k = fft_cntrl[FFT1_CURMODE].real2complex ? 2 * fft1_size : fft1_size;
+  fft1tab = zalloc(sizeof(COSIN_TABLE) * (fft1_costab_size + 16));
+  d_fft1tab = zalloc(sizeof(D_COSIN_TABLE) * (fft1_costab_size + 16));
+  fft1_permute = zalloc(sizeof(unsigned short) * (fft1_permute_size + 16));
+  fft1_bigpermute = zalloc(sizeof(unsigned int) * (fft1_permute_size + 16));
+  fft1_window = zalloc(sizeof(float) * (fft1_window_size + 32));
+  d_fft1_window = zalloc(sizeof(double) * (fft1_window_size + 32));
+  make_sincos(i, k, fft1tab);
+  if (fft_cntrl[FFT1_CURMODE].doub) {
+    make_d_sincos(i, k, d_fft1tab);
+    make_bigpermute(fft_cntrl[FFT1_CURMODE].permute, fft_cntrl[FFT1_CURMODE].real2complex ? fft1_n + 1 : fft1_n, k, fft1_bigpermute);
+    make_d_window(fft_cntrl[FFT1_CURMODE].window, k, C.sinpow, d_fft1_window);
+  } else {
+    make_permute(fft_cntrl[FFT1_CURMODE].permute, fft_cntrl[FFT1_CURMODE].real2complex ? fft1_n + 1 : fft1_n, k, fft1_permute);
+  }
+  make_window(fft_cntrl[FFT1_CURMODE].window, k, C.sinpow, fft1_window);
+
+  /* ---- wide graph range + endpoints (fft1.c:4607) ---- */
+  wg.first_xpoint = C.first_xpoint;
+  wg.xpoints = C.xpoints;
+  wg.fft_avg1num = C.avg1num;
+  wg.waterfall_avgnum = C.waterfall_avgnum;
+  wg.xpoints_per_pixel = C.xpoints_per_pixel;
+  wg.pixels_per_xpoint = C.pixels_per_xpoint;
+  wg_fft_avg2num = C.avg2num;
+  change_fft1_flag = 0;
+  lir_status = 0;
+  fft1_filtercorr = zalloc(sizeof(float) * twice_rxchan * fft1_size + 64);
+  fft1_desired = zalloc(sizeof(float) * fft1_size);
+  fft1_foldcorr = zalloc(sizeof(float) * twice_rxchan * fft1_size);
+  clear_fft1_filtercorr();                       /* fft1.c:4673, uncalibrated defaults */
+  set_fft1_endpoints();                          /* fft1.c:4607 */
+
+  /* ---- waterfall (wide_graph.c:956-1001, 1374-1389) ---- */
+  if (wg.xpoints_per_pixel > 1) wg_xpixels = wg.xpoints / wg.xpoints_per_pixel;
+  else if (wg.pixels_per_xpoint > 1) wg_xpixels = wg.xpoints * wg.pixels_per_xpoint;
+  else wg_xpixels = wg.xpoints;
+  if (wg.xpoints_per_pixel == 1 || wg.pixels_per_xpoint == 1) { if (wg_xpixels + wg.first_xpoint > fft1_size) wg_xpixels = fft1_size - wg.first_xpoint; }
+  wg_waterf_size = wg_xpixels * C.wf_lines;
+  wg_waterf = zalloc(sizeof(short) * (wg_waterf_size + wg_xpixels + 64));
+  for (i = 0; i < wg_waterf_size; i++) wg_waterf[i] = (short int)0x8000;
+  wg_waterf_ptr = 0;
+  wg_waterf_sum = zalloc(sizeof(float) * (fft1_size + 16));
+  for (i = 0; i < fft1_size; i++) wg_waterf_sum[i] = 0.00001F;
+  wg_waterf_sum_counter = 0;
+  wg_waterf_yfac = zalloc(sizeof(float) * (fft1_size + 16));
+  t1 = (float)FFT1_WATERFALL_ZERO / (float)wg.waterfall_avgnum;
+  if (wg.xpoints_per_pixel > 1) t1 *= (float)ui.rx_rf_channels;
+  for (i = 0; i < fft1_size; i++) {
+    if (fft1_desired[i] > 0.3162278) wg_waterf_yfac[i] = t1 / (float)pow(fft1_desired[i], 2.0);
+    else wg_waterf_yfac[i] = t1 * 10;
+  }
+  wg_waterf_yfac[0] = t1; wg_waterf_yfac[fft1_size - 1] = t1;
+  audio_dump_flag = 0;
+
+  /* ---- mix1 (buf.c:982,1297-1300; prepare_mixer buf.c:55-111) ---- */
+  mix1_fqwin = zalloc(sizeof(float) * (mix1.size / 2 + 16));
+  make_window(5, mix1.size, 4, mix1_fqwin);
+  mix1.window = zalloc(sizeof(float) * (mix1.size + 16));
+  mix1.cos2win = zalloc(sizeof(float) * (mix1.size + 16));
+  mix1.sin2win = zalloc(sizeof(float) * (mix1.size + 16));
+  mix1.permute = zalloc(sizeof(unsigned short) * (mix1.size + 16));
+  mix1.table = zalloc(sizeof(COSIN_TABLE) * (mix1.size + 16));
+  if (C.sinpow != 0 && C.sinpow != 2) make_window(3, mix1.size, C.sinpow, mix1.window);
+  init_fft(0, mix1.n, mix1.size, mix1.table, mix1.permute);
+  mix1.crossover_points = 0;
+  if (C.sinpow != 0 && C.sinpow != 2) {
+    if (C.sinpow == 9) mix1.crossover_points = mix1.size / 8;
+    else if (C.sinpow == 8) mix1.crossover_points = mix1.size / 16;
+    else {
+      ui_ = mix1.interleave_points / 2;
+      t1 = mix1.window[ui_];
+      while (mix1.window[ui_] < 30 * t1 && ui_ > 0) { ui_--; mix1.crossover_points++; }
+      if (mix1.crossover_points > 0.75 * mix1.new_points) mix1.crossover_points = 0.75 * mix1.new_points;
+      if (mix1.crossover_points > mix1.interleave_points / 2) mix1.crossover_points = mix1.interleave_points / 2;
+    }
+    t1 = 0.25 * PI_L / mix1.crossover_points;
+    uj = (mix1.size - mix1.new_points) / 2;
+    uk = uj + mix1.crossover_points / 2;
+    uj -= mix1.crossover_points / 2;
+    for (ui_ = 0; ui_ < mix1.crossover_points; ui_++) {
+      mix1.cos2win[ui_] = mix1.window[uk] * pow(cos(t1), 2.0);
+      mix1.sin2win[ui_] = mix1.window[uj] * pow(sin(t1), 2.0);
+      uk--; uj++;
+      t1 += 0.5 * PI_L / mix1.crossover_points;
+    }
+  }
+  fftn_tmp = zalloc(sizeof(float) * (4 * mix1.size * ui.rx_rf_channels + 64));
+  timf3_all = zalloc(sizeof(float) * 2 * (size_t)timf3_size * (C.n_sel > 0 ? C.n_sel : 1));
+  timf3_float = timf3_all;
+  timf3_pa = 0;
+  mix1_lowest_fq = (fft1_first_point + 1) * fft1_hz_per_point;      /* wide_graph.c:1336-1341 */
+  mix1_highest_fq = (fft1_last_point - 1) * fft1_hz_per_point;
+  old_mix1_selfreq = -1;
+  for (i = 0; i < REF_MAX_SEL; i++) {
+    memset(&SEL[i], 0, sizeof(sel_state));
+    SEL[i].selfreq = -1; SEL[i].point = -1;
+  }
+  inited = 1;
+  return ref_last_lirerr;
+}
+
+/* append nblocks*timf1_blockbytes bytes of raw samples to the timf1 ring and
+ * run the path once per block.  Outputs (any may be NULL):
+ *   fft1_out : nblocks * fft1_block floats  (post-fft1_c contents of fft1_float)
+ *   raw_out  : nblocks * fft1_block floats  (fft1_b output BEFORE fft1_c)
+ *   timf3_out: nblocks * n_sel * timf3_block floats (the block at timf3_pa after each call)
+ */
+int ref_process(const void *data, int nblocks, float *fft1_out, float *raw_out, float *timf3_out)
+{
+  int b, ss, i, sub;
+  const char *src = (const char *)data;
+  for (b = 0; b < nblocks; b++) {
+    for (i = 0; i < timf1_blockbytes; i++) timf1_char[(timf1p_pa + i) & timf1_bytemask] = src[(size_t)b * timf1_blockbytes + i];
+    timf1p_pa = (timf1p_pa + timf1_blockbytes) & timf1_bytemask;
+    timf1p_pb = timf1p_pa;
+    /* wcw.c:1036-1047 */
+    fft1_b(timf1p_px, &fft1_float[fft1_pa], fftw_tmp, 0);
+    timf1p_px = (timf1p_px + timf1_blockbytes) & timf1_bytemask;
+    if (raw_out) memcpy(raw_out + (size_t)b * fft1_mulblock, &fft1_float[fft1_pa], sizeof(float) * fft1_mulblock);
+    fft1_pa = (fft1_pa + fft1_mulblock) & fft1_mask;
+    fft1_na = fft1_pa / fft1_block;
+    /* wcw.c:1067-1072 */
+    sub = 0;
+    while (fft1_na != fft1_nb) {
+      int at = fft1_nb * fft1_block;
+      size_t tno = (size_t)b * fft1_muln + sub;      /* running transform number */
+      fft1_c();
+      fft1_waterfall();
+      if (fft1_out) memcpy(fft1_out + tno * fft1_block, &fft1_float[at], sizeof(float) * fft1_block);
+      /* wcw.c:1706-1716, one fft1_mix1_fixed per transform; selections looped here (MAX_MIX1==1) */
+      if (C.n_sel > 0) {
+        int pa0 = timf3_pa, nx0 = fft1_nx, px0 = fft1_px;
+        for (ss = 0; ss < C.n_sel; ss++) {
+          timf3_pa = pa0; fft1_nx = nx0; fft1_px = px0;
+          timf3_float = timf3_all + (size_t)ss * 2 * timf3_size;
+          mix1_selfreq[0] = SEL[ss].selfreq;
+          mix1_phase[0] = SEL[ss].phase; mix1_phase_step[0] = SEL[ss].phase_step;
+          mix1_phase_rot[0] = SEL[ss].phase_rot; mix1_old_phase[0] = SEL[ss].old_phase;
+          mix1_point[0] = SEL[ss].point; mix1_old_point[0] = SEL[ss].old_point;
+          fft1_mix1_fixed();
+          SEL[ss].phase = mix1_phase[0]; SEL[ss].phase_step = mix1_phase_step[0];
+          SEL[ss].phase_rot = mix1_phase_rot[0]; SEL[ss].old_phase = mix1_old_phase[0];
+          SEL[ss].point = mix1_point[0]; SEL[ss].old_point = mix1_old_point[0];
+          if (timf3_out) {
+            float *dst = timf3_out + (tno * C.n_sel + ss) * timf3_block;
+            for (i = 0; i < timf3_block; i++) dst[i] = timf3_float[(pa0 + i) & timf3_mask];
+          }
+        }
+      } else {
+        fft1_nx = (fft1_nx + 1) & fft1n_mask;
+        fft1_px = (fft1_px + fft1_block) & fft1_mask;
+      }
+      sub++;
+    }
+    if (ref_last_lirerr) return ref_last_lirerr;
+  }
+  return 0;
+}
+
+/* timing leg for bench.py --impl reference / cpu_baseline: same loop, no copies */
+int ref_process_timed(const void *data, int nblocks) { return ref_process(data, nblocks, NULL, NULL, NULL); }

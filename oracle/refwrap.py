@@ -1,0 +1,186 @@
+"""oracle/refwrap.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes wrapper around oracle/_ref/libref_oracle.so: the reference's own C files
+(fft0.c fft1.c fft1_re.c mix1.c + *var.c) compiled unmodified by oracle/Makefile
+and driven by oracle/ref_driver.c.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "_ref", "libref_oracle.so")
+
+DWORD_INPUT, TWO_CHANNELS, IQ_DATA = 1, 2, 4
+
+
+class RefCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "input_mode", "rf_channels", "ad_speed", "fft1_n", "fft1_version", "sinpow",
+        "fft1_gain", "mix1_red_n", "avg1num", "avg2num", "waterfall_avgnum", "direction",
+        "n_sel", "first_xpoint", "xpoints", "xpoints_per_pixel", "pixels_per_xpoint",
+        "wf_lines", "sample_shift")]
+
+
+def available():
+    return os.path.exists(REF_SO)
+
+
+class RefOracle:
+    """One instance at a time (the reference keeps its state in globals)."""
+
+    def __init__(self, *, input_mode, rf_channels, ad_speed, fft1_n, fft1_version, sinpow=2,
+                 fft1_gain=2000, mix1_red_n=4, avg1num=5, avg2num=4, waterfall_avgnum=10,
+                 direction=1, n_sel=0, first_xpoint=0, xpoints=None, xpoints_per_pixel=1,
+                 pixels_per_xpoint=1, wf_lines=8, sample_shift=0, timf1_bytes=None, max_fft1n=8):
+        self.lib = C.CDLL(REF_SO)
+        L = self.lib
+        L.ref_init.argtypes = [C.POINTER(RefCfg), C.c_int, C.c_int]
+        L.ref_process.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_set_selfreq.argtypes = [C.c_int, C.c_double]
+        L.ref_sel_state.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_make_window.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_fftback.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        for f in ("ref_points_per_hz", "ref_filtercorr_start"):
+            getattr(L, f).restype = C.c_float
+        for f in ("ref_window", "ref_filtercorr", "ref_desired", "ref_sumsq", "ref_slowsum",
+                  "ref_waterf", "ref_waterf_yfac", "ref_waterf_sum", "ref_mix1_fqwin",
+                  "ref_mix1_window", "ref_mix1_cos2win", "ref_mix1_sin2win"):
+            getattr(L, f).restype = C.c_void_p
+        L.ref_timf3.restype = C.c_void_p
+        L.ref_timf3.argtypes = [C.c_int]
+        n = 1 << fft1_n
+        if xpoints is None:
+            xpoints = n
+        self.cfg = RefCfg(input_mode, rf_channels, ad_speed, fft1_n, fft1_version, sinpow,
+                          fft1_gain, mix1_red_n, avg1num, avg2num, waterfall_avgnum, direction,
+                          n_sel, first_xpoint, xpoints, xpoints_per_pixel, pixels_per_xpoint,
+                          wf_lines, sample_shift)
+        frame = (4 if input_mode & IQ_DATA else 2) * rf_channels
+        if input_mode & DWORD_INPUT:
+            frame *= 2
+        if timf1_bytes is None:
+            timf1_bytes = 1
+            while timf1_bytes < 8 * n * frame:
+                timf1_bytes *= 2
+        rc = L.ref_init(C.byref(self.cfg), timf1_bytes, max_fft1n)
+        if rc != 0:
+            raise RuntimeError(f"ref_init failed rc={rc}")
+        self.n_sel = n_sel
+        self.fft1_size = L.ref_fft1_size()
+        self.fft1_block = L.ref_fft1_block()
+        self.interleave_points = L.ref_interleave_points()
+        self.new_points = L.ref_new_points()
+        self.timf1_blockbytes = L.ref_timf1_blockbytes()
+        self.mix1_size = L.ref_mix1_size()
+        self.mix1_interleave = L.ref_mix1_interleave()
+        self.mix1_new_points = L.ref_mix1_new_points()
+        self.mix1_crossover = L.ref_mix1_crossover()
+        self.timf3_block = L.ref_timf3_block()
+        self.timf3_size = L.ref_timf3_size()
+        self.wg_xpixels = L.ref_wg_xpixels()
+        self.sumsq_bufsize = L.ref_sumsq_bufsize()
+        self.points_per_hz = L.ref_points_per_hz()
+        self.first_point = L.ref_first_point()
+        self.last_point = L.ref_last_point()
+        self.muln = 1
+
+    def _arr(self, fn, count, dtype=np.float32):
+        ptr = getattr(self.lib, fn)()
+        buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).copy()
+
+    def set_selfreq(self, ss, hz):
+        self.lib.ref_set_selfreq(ss, float(hz))
+
+    def sel_state(self, ss):
+        f = np.zeros(4, np.float32)
+        i = np.zeros(2, np.int32)
+        self.lib.ref_sel_state(ss, f.ctypes.data, i.ctypes.data)
+        return dict(phase=f[0], phase_step=f[1], phase_rot=f[2], old_phase=f[3],
+                    point=int(i[0]), old_point=int(i[1]))
+
+    def process(self, raw, want_raw=False):
+        """raw: contiguous array of whole blocks in timf1 memory format."""
+        raw = np.ascontiguousarray(raw)
+        nbytes = raw.nbytes
+        assert nbytes % self.timf1_blockbytes == 0, (nbytes, self.timf1_blockbytes)
+        nb = nbytes // self.timf1_blockbytes
+        fft1 = np.zeros((nb, self.fft1_block), np.float32)
+        rawout = np.zeros((nb, self.fft1_block), np.float32) if want_raw else None
+        t3 = np.zeros((nb, max(self.n_sel, 1), self.timf3_block), np.float32) if self.n_sel else None
+        rc = self.lib.ref_process(raw.ctypes.data, nb, fft1.ctypes.data,
+                                  rawout.ctypes.data if want_raw else None,
+                                  t3.ctypes.data if t3 is not None else None)
+        if rc != 0:
+            raise RuntimeError(f"reference raised lirerr({rc})")
+        return dict(fft1=fft1, raw=rawout, timf3=t3)
+
+    def process_timed(self, raw, nblocks):
+        return self.lib.ref_process_timed(raw.ctypes.data, nblocks)
+
+    # snapshots of reference state
+    def window(self, count=None):
+        return self._arr("ref_window", count or self.fft1_size)
+
+    def filtercorr(self):
+        return self._arr("ref_filtercorr", self.fft1_block)
+
+    def desired(self):
+        return self._arr("ref_desired", self.fft1_size)
+
+    def sumsq(self):
+        return self._arr("ref_sumsq", self.sumsq_bufsize)
+
+    def sumsq_pa(self):
+        return self.lib.ref_sumsq_pa()
+
+    def sumsq_counter(self):
+        return self.lib.ref_sumsq_counter()
+
+    def slowsum(self):
+        return self._arr("ref_slowsum", self.fft1_size)
+
+    def waterf(self):
+        return self._arr("ref_waterf", self.lib.ref_waterf_size(), np.int16)
+
+    def waterf_ptr(self):
+        return self.lib.ref_waterf_ptr()
+
+    def waterf_yfac(self):
+        return self._arr("ref_waterf_yfac", self.fft1_size)
+
+    def waterf_sum(self):
+        return self._arr("ref_waterf_sum", self.fft1_size)
+
+    def mix1_fqwin(self):
+        return self._arr("ref_mix1_fqwin", self.mix1_size // 2 + 1)
+
+    def mix1_window(self):
+        return self._arr("ref_mix1_window", self.mix1_size)
+
+    def mix1_cos2win(self):
+        return self._arr("ref_mix1_cos2win", max(self.mix1_crossover, 1))
+
+    def mix1_sin2win(self):
+        return self._arr("ref_mix1_sin2win", max(self.mix1_crossover, 1))
+
+    def timf3_ring(self, ss):
+        ptr = self.lib.ref_timf3(ss)
+        buf = (C.c_char * (self.timf3_size * 4)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.float32).copy()
+
+    def timf3_pa(self):
+        return self.lib.ref_timf3_pa()
+
+    def make_window(self, mo, sz, n, count=None):
+        w = np.zeros((count or sz) + 32, np.float32)
+        self.lib.ref_make_window(mo, sz, n, w.ctypes.data)
+        return w[:count or sz]
+
+    def fftback(self, x):
+        x = np.ascontiguousarray(x, np.complex64).copy()
+        n = int(np.log2(len(x)))
+        self.lib.ref_fftback(len(x), n, x.ctypes.data)
+        return x
