@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- fft1 + power + mix1 throughput on B200 (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic timf1 input:
+    lb200_fft1_dev (fused unpack/window/fft1/filtercorr/|z|^2/fft1_sumsq) + lb200_mix1_dev.
+value  : new input samples per second (Msamples/s), whole job, inputs resident in HBM.
+e2e    : same metric through the host-buffer C-ABI calls (lb200_fft1 + lb200_mix1) with
+         host<->device copies inside the timed region.
+roofline: algorithmic bytes of the fft1 kernel / its CUDA-event duration.
+cpu_baseline / --impl reference: the reference's own C path (oracle/_ref) on the host cores.
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 under torchrun (one rank per
+GPU, independent receiver streams per rank = weak scaling; the only collective is the
+all-reduce of the averaged power spectrum).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from linrad_b200 import sizing  # noqa: E402
+from linrad_b200.synth import make_timf1  # noqa: E402
+
+IQ, DW, TWO = sizing.IQ_DATA, sizing.DWORD_INPUT, sizing.TWO_CHANNELS
+
+WORKLOADS = {
+    # name: (PathSetup kwargs, reference fft_cntrl row, selections (bins), batch per step)
+    "cfg1": (dict(input_mode=IQ, rf_channels=1, ad_speed=96000, fft1_n=13, mix1_red_n=4), 6, [3000.37], 5920),
+    "cfg2": (dict(input_mode=IQ | DW | TWO, rf_channels=2, ad_speed=192000, fft1_n=14, mix1_red_n=4), 7, [6000.74], 740),
+}
+WORKLOAD_TEXT = {
+    "cfg1": "configs[0]: 1-ch complex IQ 96 kS/s int16, fft1 N=8192 sin^2 window, mix1 M=512 one signal",
+    "cfg2": "configs[1]: 2-ch complex IQ 192 kS/s 24-bit (int32), fft1 N=16384 sin^2 window, mix1 M=1024 one signal",
+}
+
+
+def pow2_at_least(x):
+    p = 1
+    while p < x:
+        p *= 2
+    return p
+
+
+def alg_bytes(s, nsel):
+    """algorithmic bytes per transform, split by kernel."""
+    N, C = s.fft1_size, s.rf_channels
+    b_in = s.fft1_new_points * s.frame_bytes
+    b_fft1 = 8 * C * N
+    b_pow = 4.0 * N / s.avg1num
+    M, Mi, Mn = s.mix1_size, s.mix1_interleave_points, s.mix1_new_points
+    b_mix = nsel * (8 * C * M + 8 * C * Mn + (8 * C * Mi if Mi == Mn else 0))
+    return dict(fft1=b_in + b_fft1 + b_pow, mix1=b_mix, total=b_in + b_fft1 + b_pow + b_mix)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.th = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref) on the host cores.
+    One process per core, each an independent Linrad-style pipeline on its own block range
+    (the reference's own parallel model is independent time blocks per fft1b thread,
+    wcw.c:974-1000)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    kw, version, selbins, _ = WORKLOADS[args.workload]
+    s = sizing.PathSetup(**kw)
+    cores = args.cpu_procs or max(1, (os.cpu_count() or 2))
+    blocks = args.cpu_blocks or max(8, int(48 * 8192 * 13 / (s.fft1_size * s.fft1_n * s.rf_channels)))
+    ctx = mp.get_context("fork")
+
+    def worker(q_in, q_out, seed):
+        from oracle.refwrap import RefOracle
+        r = RefOracle(fft1_version=version, n_sel=len(selbins), **kw)
+        for i, fb in enumerate(selbins):
+            r.set_selfreq(i, s.selfreq_for_bin(fb))
+        raw = make_timf1(s.input_mode, s.rf_channels, s.fft1_size, blocks, s.fft1_new_points, seed=seed)
+        q_out.put("ready")
+        while True:
+            cmd = q_in.get()
+            if cmd is None:
+                return
+            t0 = time.perf_counter()
+            r.process_timed(raw, blocks)
+            q_out.put(time.perf_counter() - t0)
+
+    procs = []
+    for i in range(cores):
+        qi, qo = ctx.Queue(), ctx.Queue()
+        p = ctx.Process(target=worker, args=(qi, qo, 100 + i), daemon=True)
+        p.start()
+        procs.append((p, qi, qo))
+    for _, _, qo in procs:
+        qo.get()
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        for _, qi, _ in procs:
+            qi.put(1)
+        for _, _, qo in procs:
+            qo.get()
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    for p, qi, _ in procs:
+        qi.put(None)
+    tot = sum(times)
+    samples = blocks * s.fft1_new_points * cores * len(times)
+    value = samples / tot / 1e6
+    line = {
+        "impl": "reference", "metric": "fft1+mix1 IQ Msamples/s", "value": value, "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.workload], "blocks_per_step_per_core": blocks,
+                   "reference_fft1_version": version},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                         "sample": f"{blocks} transforms per core per step, {cores} independent pipelines, "
+                                   f"fft1_b(v{version})+fft1_c+fft1_waterfall+fft1_mix1_fixed compiled from the reference C files (-O2 -ffast-math)"},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_quick(workload, seconds=12.0):
+    """Bounded single-core sample of the compiled reference for the default run."""
+    try:
+        from oracle import refwrap
+        if not refwrap.available():
+            return None
+        kw, version, selbins, _ = WORKLOADS[workload]
+        s = sizing.PathSetup(**kw)
+        r = refwrap.RefOracle(fft1_version=version, n_sel=len(selbins), **kw)
+        for i, fb in enumerate(selbins):
+            r.set_selfreq(i, s.selfreq_for_bin(fb))
+        blocks = 16
+        raw = make_timf1(s.input_mode, s.rf_channels, s.fft1_size, blocks, s.fft1_new_points, seed=9)
+        r.process_timed(raw, blocks)
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < seconds:
+            r.process_timed(raw, blocks)
+            n += blocks
+        dt = time.perf_counter() - t0
+        return {"value": n * s.fft1_new_points / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "reference",
+                "sample": f"{n} transforms in {dt:.1f} s, one thread: fft1_b(v{version})+fft1_c+fft1_waterfall+"
+                          f"fft1_mix1_fixed from the reference C files (-O2 -ffast-math); nproc={os.cpu_count()}"}
+    except Exception as e:  # the baseline must never take the GPU line down
+        return {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="transforms per step per GPU (0 = workload default)")
+    ap.add_argument("--e2e-batch", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-procs", type=int, default=0)
+    ap.add_argument("--cpu-blocks", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from linrad_b200 import api
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    kw, version, selbins, default_batch = WORKLOADS[args.workload]
+    s = sizing.PathSetup(**kw)
+    B = args.batch or default_batch
+    N, C = s.fft1_size, s.rf_channels
+    plan = api.Plan(s, device=local_rank)
+    stream = torch.cuda.ExternalStream(plan.stream, device=dev)
+
+    # ---- device-resident rings (same layouts as Linrad's host rings) -------------------------
+    raw = make_timf1(s.input_mode, C, N, 64, s.fft1_new_points, seed=100 + rank)
+    raw_bytes = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+    timf1_bytes = pow2_at_least((B + 2) * s.timf1_blockbytes)
+    reps = (B * s.timf1_blockbytes + raw_bytes.size - 1) // raw_bytes.size
+    host_in = np.tile(raw_bytes, reps)[: B * s.timf1_blockbytes]
+    d_timf1 = torch.zeros(timf1_bytes, dtype=torch.uint8, device=dev)
+    d_timf1[: host_in.size].copy_(torch.from_numpy(host_in))
+    fft1_floats = pow2_at_least(B * s.fft1_block)
+    d_fft1 = torch.empty(fft1_floats, dtype=torch.float32, device=dev)
+    rows = (B + s.avg1num - 1) // s.avg1num
+    sumsq_floats = pow2_at_least((rows + 1) * N)
+    d_sumsq = torch.zeros(sumsq_floats, dtype=torch.float32, device=dev)
+    timf3_size = pow2_at_least((B + 2) * s.timf3_block + 2 * C * s.mix1_size)
+    nsel = len(selbins)
+    d_timf3 = torch.zeros(nsel * 2 * timf3_size, dtype=torch.float32, device=dev)
+    states = api.new_states([s.selfreq_for_bin(b) for b in selbins])
+    torch.cuda.synchronize()
+
+    ev_pairs = []
+
+    def step(record=False):
+        # block 0 of the batch starts at byte 0; its overlap half is the ring's tail (zeros/old data)
+        if record:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        plan.fft1_dev(timf1=d_timf1.data_ptr(), timf1_bytes=timf1_bytes, ref=0, nblocks=B, fft1=d_fft1.data_ptr(),
+                      fft1_floats=fft1_floats, fft1_pa=0, apply_fc=True, sumsq=d_sumsq.data_ptr(),
+                      sumsq_floats=sumsq_floats, sumsq_pa=0, counter=0)
+        if record:
+            e1.record(stream)
+            ev_pairs.append((e0, e1))
+        plan.mix1_dev(fft1=d_fft1.data_ptr(), fft1_floats=fft1_floats, fft1_px=0, nblocks=B, states=states,
+                      timf3=d_timf3.data_ptr(), timf3_floats=timf3_size, timf3_pa=0)
+        if world > 1:
+            # the averaged power spectrum is the only thing that crosses GPUs
+            with torch.cuda.stream(stream):
+                dist.all_reduce(d_sumsq[: rows * N])
+
+    for _ in range(args.warmup):
+        step()
+    plan.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = plan.launches()
+    with ClockSampler(local_rank) as clk:
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        t_start.record(stream)
+        for _ in range(args.steps):
+            step(record=True)
+        t_end.record(stream)
+        plan.synchronize()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = t_start.elapsed_time(t_end)
+    launches = plan.launches() - launches0
+    fft1_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs]))
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    samples = B * s.fft1_new_points * args.steps * world
+    value = samples / (ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (fft1_small_kernel) -----------------------------------
+    ab = alg_bytes(s, nsel)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = ab["fft1"] * B / (fft1_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "fft1_small_kernel", "kernel_ms": fft1_ms,
+                "algorithmic_bytes_per_launch": ab["fft1"] * B, "peak_source": peak_src,
+                "whole_step_frac": ab["total"] * B * args.steps / (ms * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the host-buffer C ABI ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        Be = args.e2e_batch
+        h_timf1 = torch.zeros(pow2_at_least((Be + 2) * s.timf1_blockbytes), dtype=torch.uint8).pin_memory()
+        h_timf1[: Be * s.timf1_blockbytes].copy_(torch.from_numpy(host_in[: Be * s.timf1_blockbytes]))
+        h_fft1 = torch.zeros(pow2_at_least(Be * s.fft1_block), dtype=torch.float32).pin_memory()
+        h_sumsq = torch.zeros(pow2_at_least((Be // s.avg1num + 2) * N), dtype=torch.float32).pin_memory()
+        t3s = pow2_at_least((Be + 2) * s.timf3_block + 2 * C * s.mix1_size)
+        h_timf3 = torch.zeros(nsel * 2 * t3s, dtype=torch.float32).pin_memory()
+        plan2 = api.Plan(s, device=local_rank)
+        st2 = api.new_states([s.selfreq_for_bin(b) for b in selbins])
+        os.environ["LB200_NO_HOSTREGISTER"] = "1"      # buffers are already pinned
+        os.environ["LB200_MIX1_TRUST_MIRROR"] = "1"    # mix1 runs on the plan that produced fft1_float
+
+        def e2e_step():
+            plan2.fft1_host(timf1=h_timf1.numpy(), ref=0, nblocks=Be, fft1=h_fft1.numpy(), fft1_pa=0, apply_fc=True,
+                            sumsq=h_sumsq.numpy(), sumsq_pa=0, counter=0)
+            plan2.mix1_host(fft1=h_fft1.numpy(), fft1_px=0, nblocks=Be, states=st2, timf3=h_timf3.numpy(),
+                            timf3_floats=t3s, timf3_pa=0)
+
+        for _ in range(3):
+            e2e_step()
+        h0, d0 = plan2.h2d_bytes(), plan2.d2h_bytes()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        nrep = max(3, args.steps // 2)
+        for _ in range(nrep):
+            e2e_step()
+        plan2.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": Be * s.fft1_new_points * nrep * world / dt / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": (plan2.h2d_bytes() - h0) // nrep, "d2h_bytes_per_step": (plan2.d2h_bytes() - d0) // nrep,
+               "batch": Be, "api": "lb200_fft1 + lb200_mix1 on pinned host rings"}
+        plan2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_quick(args.workload)
+
+    if rank == 0:
+        line = {
+            "metric": "fft1+mix1 IQ Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_TEXT[args.workload], "transforms_per_step_per_gpu": B,
+                       "l2": f"working set per step {(B * (s.timf1_blockbytes + 4 * s.fft1_block)) >> 20} MiB > 126 MiB L2, no flush needed",
+                       "mix1_selections": nsel, "fft_avg1num": s.avg1num,
+                       "parallelism": f"{world} independent receiver streams, one per GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clk.summary(),
+        }
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

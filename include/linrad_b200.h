@@ -1,0 +1,169 @@
+/* linrad_b200.h -- C ABI of liblinrad_b200.so, the B200 (sm_100a) replacement for Linrad's
+ * wideband DSP hot path:  timf1 -> (unpack, window) -> fft1 -> fft1_float -> |X|^2 ->
+ * fft1_sumsq -> mix1 -> timf3.
+ *
+ * The reference (fventuri/linrad) has no FFI for this path: its boundary is a set of C
+ * functions working on global ring buffers.  Every entry point
+ * below names the reference function it replaces; argument names are the reference's own
+ * global names so that the host-side shim (linrad_b200/host/lb200_shim.c)
+ * is a one-line forward per function.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Two flavours of every compute call:
+ *   *_dev : all buffers are DEVICE pointers (bulk processing, several streams per GPU)
+ *   plain : buffers are HOST pointers exactly as Linrad owns them (buf.c mem() list); the
+ *           library stages them through its own device mirrors (H2D/D2H inside the call).
+ * All calls on one plan are serialised on the plan's CUDA stream; different plans are
+ * independent (one plan per fft1b worker thread, like the cuFFT handles of wcw.c:552-576).
+ *
+ * Return value: 0 on success, else an LB200_ERR_* code.  The shim forwards non-zero codes
+ * to lirerr() (lxsys.c:495); texts for errors.lir are listed in INTEGRATION.md.
+ */
+#ifndef LINRAD_B200_H
+#define LINRAD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB200_ABI_VERSION 1
+
+/* ui.rx_input_mode bits used by the path (globdef.h:277-279) */
+#define LB200_DWORD_INPUT 1
+#define LB200_TWO_CHANNELS 2
+#define LB200_IQ_DATA 4
+
+/* error codes (new lirerr numbers; 3100-3119 are unused in errors.lir) */
+#define LB200_OK 0
+#define LB200_ERR_NO_DEVICE 3100      /* no CUDA device / driver */
+#define LB200_ERR_CUDA 3101           /* a CUDA runtime call or kernel launch failed */
+#define LB200_ERR_BAD_CONFIG 3102     /* inconsistent sizes in lb200_config */
+#define LB200_ERR_UNSUPPORTED 3103    /* size / mode outside what the kernels cover */
+#define LB200_ERR_BAD_ARG 3104        /* null pointer, misaligned offset, ring too small */
+#define LB200_ERR_MIX1_RANGE_LOW 1211 /* same codes set_mix1_phases raises (mix1.c:787-796) */
+#define LB200_ERR_MIX1_RANGE_HIGH 1212
+
+#define LB200_MAX_MIX1 64             /* selections per plan (reference MAX_MIX1 is 1, globdef.h:169) */
+
+typedef struct lb200_plan lb200_plan; /* opaque */
+
+/* Everything the path reads from Linrad's setup (sizes from get_wideband_sizes buf.c:139,
+ * tables from get_buffers buf.c:1297-1456).  Tables are HOST pointers copied at create. */
+typedef struct lb200_config {
+  int abi_version;              /* LB200_ABI_VERSION */
+  int device;                   /* CUDA device ordinal */
+  /* --- input format ------------------------------------------------------------- */
+  int rx_input_mode;            /* ui.rx_input_mode (DWORD_INPUT|TWO_CHANNELS|IQ_DATA) */
+  int rx_rf_channels;           /* ui.rx_rf_channels: 1 or 2 */
+  int sample_shift;             /* ui.sample_shift (Q delay in samples, fft1.c:778-787) */
+  /* --- fft1 geometry -------------------------------------------------------------- */
+  int fft1_n;                   /* fft1_n;  fft1_size = 1 << fft1_n (bins) */
+  int fft1_interleave_points;   /* fft1_interleave_points (buf.c:303,327) */
+  int fft1_direction;           /* fft1_direction: +1 or -1 (fft1.c:3660-3680) */
+  int fft1_first_point;         /* fft1_first_point (fft1.c:4607-4651) */
+  int fft1_last_point;          /* fft1_last_point */
+  /* --- tables ----------------------------------------------------------------------- */
+  const float *fft1_window;     /* NATURAL-order window w[0..fft1_size) (2*fft1_size for real
+                                   input); NULL when genparm[FIRST_FFT_SINPOW]==0.  Use
+                                   lb200_window_to_natural() to convert a make_window() table. */
+  const float *fft1_filtercorr; /* twice_rxchan*fft1_size floats, layout of fft1.c:4691-4692 */
+  const float *fft1_foldcorr;   /* twice_rxchan*fft1_size floats or NULL (CALIQ off) */
+  /* --- power spectra --------------------------------------------------------------- */
+  int fft_avg1num;              /* wg.fft_avg1num */
+  /* --- mix1 ------------------------------------------------------------------------- */
+  int mix1_n;                   /* mix1.n ; mix1.size = 1 << mix1_n ; 0 = mix1 not used */
+  int mix1_interleave_points;   /* mix1.interleave_points */
+  int mix1_crossover_points;    /* mix1.crossover_points */
+  const float *mix1_fqwin;      /* mix1.size/2+1 floats, make_window(5,...) buf.c:1297 */
+  const float *mix1_window;     /* mix1.size floats or NULL (sinpow 0 or 2) */
+  const float *mix1_cos2win;    /* crossover_points floats or NULL */
+  const float *mix1_sin2win;    /* crossover_points floats or NULL */
+  float fftx_points_per_hz;     /* fftx_points_per_hz */
+  float mix1_lowest_fq;         /* mix1_lowest_fq  (wide_graph.c:1336-1341) */
+  float mix1_highest_fq;        /* mix1_highest_fq */
+  /* --- bulk-mode capacity ------------------------------------------------------------ */
+  int max_batch;                /* largest nblocks per call (sizes staging buffers) */
+} lb200_config;
+
+/* Ring-buffer descriptor: base pointer + power-of-two size (the reference's xxx_mask+1). */
+typedef struct lb200_ring {
+  void *base;
+  size_t size;                  /* bytes for timf1, floats for fft1_float/fft1_sumsq/timf3_float */
+} lb200_ring;
+
+/* One call of the fused fft1_b + fft1_c over `nblocks` consecutive transforms. */
+typedef struct lb200_fft1_args {
+  lb200_ring timf1;             /* timf1_char, timf1_bytemask+1 */
+  uint32_t timf1p_ref;          /* byte offset of the first NEW sample of the first transform
+                                   (fft1_b's timf1p_ref == timf1p_px, wcw.c:1036) */
+  int nblocks;
+  lb200_ring fft1_float;        /* fft1_float, fft1_mask+1 (floats) */
+  uint32_t fft1_pa;             /* float index where the first transform goes (wcw.c:1036) */
+  int apply_filtercorr;         /* 0: raw fft1_b output; 1: fft1_c's filtercorr applied too */
+  lb200_ring fft1_sumsq;        /* fft1_sumsq ring or base==NULL to skip power */
+  uint32_t fft1_sumsq_pa;       /* fft1_sumsq_pa (floats) */
+  int fft1_sumsq_counter;       /* fft1_sumsq_counter on entry (fft1.c:4115,4507) */
+  float *power_rows;            /* optional: nblocks rows of fft1_size floats = per-transform
+                                   |z|^2 (lets a host fft1_c keep the reference's own
+                                   accumulation order); NULL to skip */
+} lb200_fft1_args;
+
+/* per-selection mix1 state, the reference's per-ss globals (selvar.c:213-220) */
+typedef struct lb200_mix1_state {
+  double mix1_selfreq;          /* mix1_selfreq[ss], <0 = not selected */
+  float mix1_phase;             /* mix1_phase[ss] */
+  float mix1_phase_step;        /* mix1_phase_step[ss] */
+  float mix1_phase_rot;         /* mix1_phase_rot[ss] */
+  float mix1_old_phase;         /* mix1_old_phase[ss] */
+  int mix1_point;               /* mix1_point[ss], -1 right after selection */
+  int mix1_old_point;           /* mix1_old_point[ss] */
+} lb200_mix1_state;
+
+typedef struct lb200_mix1_args {
+  lb200_ring fft1_float;        /* source spectra (post fft1_c) */
+  uint32_t fft1_px;             /* float index of the first transform to mix (mix1.c:1019) */
+  int nblocks;
+  int no_of_channels;           /* genparm[MIX1_NO_OF_CHANNELS] */
+  lb200_mix1_state *state;      /* HOST array[no_of_channels], updated like set_mix1_phases/do_mix1 do */
+  lb200_ring timf3_float;       /* per-selection ring: selection ss lives at base + ss*2*size
+                                   (mix1.c:109 poffs=ss*timf3_size; see DESIGN.md on ss>0) */
+  uint32_t timf3_pa;            /* timf3_pa on entry */
+} lb200_mix1_args;
+
+/* ---------------------------------------------------------------------------------------- */
+int lb200_create(const lb200_config *cfg, lb200_plan **plan); /* ~ cufftPlanMany site wcw.c:552-576 */
+void lb200_destroy(lb200_plan *plan);                         /* ~ wcw.c:1174-1184 */
+const char *lb200_strerror(int code);
+int lb200_abi_version(void);
+/* plan-owned CUDA stream (cudaStream_t) so callers can order their own copies against it */
+void *lb200_stream(lb200_plan *plan);
+int lb200_synchronize(lb200_plan *plan);
+/* counters for bench.py: kernels launched / bytes copied by this plan since creation */
+uint64_t lb200_launch_count(const lb200_plan *plan);
+uint64_t lb200_h2d_bytes(const lb200_plan *plan);
+uint64_t lb200_d2h_bytes(const lb200_plan *plan);
+
+/* fft1_b (fft1.c:3302) fused with fft1_c's arithmetic (fft1.c:4085-4200): device buffers */
+int lb200_fft1_dev(lb200_plan *plan, const lb200_fft1_args *a);
+/* same on Linrad's host buffers: copies the needed timf1 span H2D, runs, copies the new
+ * fft1_float blocks (and sumsq rows / power rows) back D2H */
+int lb200_fft1(lb200_plan *plan, const lb200_fft1_args *a);
+
+/* fft1_mix1_fixed (mix1.c:995) incl. set_mix1_phases (mix1.c:781) and do_mix1 (mix1.c:55) */
+int lb200_mix1_dev(lb200_plan *plan, const lb200_mix1_args *a);
+int lb200_mix1(lb200_plan *plan, const lb200_mix1_args *a);
+
+/* Host helpers shared by the shim and the tests (pure integer / scalar logic) */
+/* set_mix1_phases (mix1.c:781-861) for one selection and one transform; returns 0 or 1211/1212 */
+int lb200_set_mix1_phases(const lb200_config *cfg, lb200_mix1_state *s, float fq);
+/* value of mix1_phase[ss] after do_mix1's running sum of `count` float additions of `rot`
+ * (mix1.c:146-153,172-186), computed without iterating when the exponent does not change */
+float lb200_phase_advance(float phase, float rot, int count);
+/* convert a reference window table (make_window mo=1 interleaved / mo=4 natural / mo=2 half,
+ * fft0.c:812-921) to natural order */
+void lb200_window_to_natural(int mo, int size, const float *win, float *natural);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,265 @@
+"""ctypes binding of liblinrad_b200.so (include/linrad_b200.h) for the test and bench harness.
+
+The product is the C-ABI library; this module only marshals arguments.  It never computes
+samples itself and there is no fallback: if the CUDA library is missing the import fails.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblinrad_b200.so")
+
+LB200_ABI_VERSION = 1
+ERR = {0: "OK", 3100: "NO_DEVICE", 3101: "CUDA", 3102: "BAD_CONFIG", 3103: "UNSUPPORTED", 3104: "BAD_ARG",
+       1211: "MIX1_RANGE_LOW", 1212: "MIX1_RANGE_HIGH"}
+
+# every symbol include/linrad_b200.h declares
+EXPORTS = ["lb200_create", "lb200_destroy", "lb200_strerror", "lb200_abi_version", "lb200_stream",
+           "lb200_synchronize", "lb200_launch_count", "lb200_h2d_bytes", "lb200_d2h_bytes",
+           "lb200_fft1_dev", "lb200_fft1", "lb200_mix1_dev", "lb200_mix1", "lb200_set_mix1_phases",
+           "lb200_phase_advance", "lb200_window_to_natural"]
+
+
+class Lb200Error(RuntimeError):
+    def __init__(self, code, what=""):
+        self.code = code
+        super().__init__(f"lb200 error {code} ({ERR.get(code, '?')}) {what}")
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int), ("device", C.c_int),
+        ("rx_input_mode", C.c_int), ("rx_rf_channels", C.c_int), ("sample_shift", C.c_int),
+        ("fft1_n", C.c_int), ("fft1_interleave_points", C.c_int), ("fft1_direction", C.c_int),
+        ("fft1_first_point", C.c_int), ("fft1_last_point", C.c_int),
+        ("fft1_window", C.c_void_p), ("fft1_filtercorr", C.c_void_p), ("fft1_foldcorr", C.c_void_p),
+        ("fft_avg1num", C.c_int),
+        ("mix1_n", C.c_int), ("mix1_interleave_points", C.c_int), ("mix1_crossover_points", C.c_int),
+        ("mix1_fqwin", C.c_void_p), ("mix1_window", C.c_void_p), ("mix1_cos2win", C.c_void_p),
+        ("mix1_sin2win", C.c_void_p),
+        ("fftx_points_per_hz", C.c_float), ("mix1_lowest_fq", C.c_float), ("mix1_highest_fq", C.c_float),
+        ("max_batch", C.c_int),
+    ]
+
+
+class Ring(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("size", C.c_size_t)]
+
+
+class Fft1Args(C.Structure):
+    _fields_ = [
+        ("timf1", Ring), ("timf1p_ref", C.c_uint32), ("nblocks", C.c_int),
+        ("fft1_float", Ring), ("fft1_pa", C.c_uint32), ("apply_filtercorr", C.c_int),
+        ("fft1_sumsq", Ring), ("fft1_sumsq_pa", C.c_uint32), ("fft1_sumsq_counter", C.c_int),
+        ("power_rows", C.c_void_p),
+    ]
+
+
+class Mix1State(C.Structure):
+    _fields_ = [
+        ("mix1_selfreq", C.c_double), ("mix1_phase", C.c_float), ("mix1_phase_step", C.c_float),
+        ("mix1_phase_rot", C.c_float), ("mix1_old_phase", C.c_float),
+        ("mix1_point", C.c_int), ("mix1_old_point", C.c_int),
+    ]
+
+
+class Mix1Args(C.Structure):
+    _fields_ = [
+        ("fft1_float", Ring), ("fft1_px", C.c_uint32), ("nblocks", C.c_int), ("no_of_channels", C.c_int),
+        ("state", C.POINTER(Mix1State)), ("timf3_float", Ring), ("timf3_pa", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads liblinrad_b200.so; raises if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the CUDA library is the only implementation of this path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.lb200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.lb200_destroy.argtypes = [C.c_void_p]
+    lib.lb200_destroy.restype = None
+    lib.lb200_strerror.argtypes = [C.c_int]
+    lib.lb200_strerror.restype = C.c_char_p
+    lib.lb200_stream.argtypes = [C.c_void_p]
+    lib.lb200_stream.restype = C.c_void_p
+    lib.lb200_synchronize.argtypes = [C.c_void_p]
+    for f in ("lb200_launch_count", "lb200_h2d_bytes", "lb200_d2h_bytes"):
+        getattr(lib, f).argtypes = [C.c_void_p]
+        getattr(lib, f).restype = C.c_uint64
+    for f in ("lb200_fft1_dev", "lb200_fft1"):
+        getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(Fft1Args)]
+    for f in ("lb200_mix1_dev", "lb200_mix1"):
+        getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(Mix1Args)]
+    lib.lb200_set_mix1_phases.argtypes = [C.POINTER(Config), C.POINTER(Mix1State), C.c_float]
+    lib.lb200_phase_advance.argtypes = [C.c_float, C.c_float, C.c_int]
+    lib.lb200_phase_advance.restype = C.c_float
+    lib.lb200_window_to_natural.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.lb200_window_to_natural.restype = None
+    _lib = lib
+    return lib
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, np.float32)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def make_config(setup, device=0, window=None, filtercorr=None, max_batch=0):
+    """Build an lb200_config from a sizing.PathSetup.  `window`/`filtercorr` override the tables
+    (e.g. with the reference's own, taken from the oracle in the parity tests).  Returns
+    (Config, keepalive) -- keepalive holds the numpy tables until lb200_create has copied them."""
+    keep = dict(
+        window=_f32(window if window is not None else setup.window),
+        filtercorr=_f32(filtercorr if filtercorr is not None else setup.filtercorr),
+        fqwin=_f32(setup.mix1_fqwin), mwin=_f32(setup.mix1_window),
+        cos2=_f32(setup.mix1_cos2win), sin2=_f32(setup.mix1_sin2win))
+    cfg = Config()
+    cfg.abi_version = LB200_ABI_VERSION
+    cfg.device = device
+    cfg.rx_input_mode = setup.input_mode
+    cfg.rx_rf_channels = setup.rf_channels
+    cfg.sample_shift = 0
+    cfg.fft1_n = setup.fft1_n
+    cfg.fft1_interleave_points = setup.fft1_interleave_points
+    cfg.fft1_direction = setup.direction
+    cfg.fft1_first_point = setup.fft1_first_point
+    cfg.fft1_last_point = setup.fft1_last_point
+    cfg.fft1_window = _ptr(keep["window"])
+    cfg.fft1_filtercorr = _ptr(keep["filtercorr"])
+    cfg.fft1_foldcorr = None
+    cfg.fft_avg1num = setup.avg1num
+    cfg.mix1_n = setup.mix1_n
+    cfg.mix1_interleave_points = setup.mix1_interleave_points
+    cfg.mix1_crossover_points = setup.mix1_crossover_points
+    cfg.mix1_fqwin = _ptr(keep["fqwin"])
+    cfg.mix1_window = _ptr(keep["mwin"])
+    cfg.mix1_cos2win = _ptr(keep["cos2"])
+    cfg.mix1_sin2win = _ptr(keep["sin2"])
+    cfg.fftx_points_per_hz = setup.fftx_points_per_hz
+    cfg.mix1_lowest_fq = setup.mix1_lowest_fq
+    cfg.mix1_highest_fq = setup.mix1_highest_fq
+    cfg.max_batch = max_batch
+    return cfg, keep
+
+
+class Plan:
+    """Thin handle around lb200_plan."""
+
+    def __init__(self, setup, device=0, window=None, filtercorr=None, max_batch=0):
+        self.lib = load_library()
+        self.setup = setup
+        self.cfg, keep = make_config(setup, device, window, filtercorr, max_batch)
+        h = C.c_void_p()
+        rc = self.lib.lb200_create(C.byref(self.cfg), C.byref(h))
+        if rc:
+            raise Lb200Error(rc, "lb200_create")
+        self.h = h
+        del keep
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return self.lib.lb200_stream(self.h)
+
+    def synchronize(self):
+        rc = self.lib.lb200_synchronize(self.h)
+        if rc:
+            raise Lb200Error(rc, "synchronize")
+
+    def launches(self):
+        return int(self.lib.lb200_launch_count(self.h))
+
+    def h2d_bytes(self):
+        return int(self.lib.lb200_h2d_bytes(self.h))
+
+    def d2h_bytes(self):
+        return int(self.lib.lb200_d2h_bytes(self.h))
+
+    def _fft1_args(self, timf1_ptr, timf1_bytes, ref, nblocks, fft1_ptr, fft1_floats, fft1_pa,
+                   apply_fc, sumsq_ptr, sumsq_floats, sumsq_pa, counter, power_ptr):
+        a = Fft1Args()
+        a.timf1 = Ring(timf1_ptr, timf1_bytes)
+        a.timf1p_ref = ref
+        a.nblocks = nblocks
+        a.fft1_float = Ring(fft1_ptr, fft1_floats)
+        a.fft1_pa = fft1_pa
+        a.apply_filtercorr = 1 if apply_fc else 0
+        a.fft1_sumsq = Ring(sumsq_ptr, sumsq_floats)
+        a.fft1_sumsq_pa = sumsq_pa
+        a.fft1_sumsq_counter = counter
+        a.power_rows = power_ptr
+        return a
+
+    def fft1_dev(self, *, timf1, timf1_bytes, ref, nblocks, fft1, fft1_floats, fft1_pa=0, apply_fc=True,
+                 sumsq=None, sumsq_floats=0, sumsq_pa=0, counter=0, power=None):
+        """All pointers are raw device addresses (ints)."""
+        a = self._fft1_args(timf1, timf1_bytes, ref, nblocks, fft1, fft1_floats, fft1_pa, apply_fc,
+                            sumsq, sumsq_floats, sumsq_pa, counter, power)
+        rc = self.lib.lb200_fft1_dev(self.h, C.byref(a))
+        if rc:
+            raise Lb200Error(rc, "lb200_fft1_dev")
+
+    def fft1_host(self, *, timf1, ref, nblocks, fft1, fft1_pa=0, apply_fc=True, sumsq=None, sumsq_pa=0,
+                  counter=0, power=None):
+        """numpy arrays standing in for Linrad's host rings (sizes must be powers of two)."""
+        a = self._fft1_args(timf1.ctypes.data, timf1.nbytes, ref, nblocks, fft1.ctypes.data, fft1.size, fft1_pa,
+                            apply_fc, _ptr(sumsq), 0 if sumsq is None else sumsq.size, sumsq_pa, counter,
+                            _ptr(power))
+        rc = self.lib.lb200_fft1(self.h, C.byref(a))
+        if rc:
+            raise Lb200Error(rc, "lb200_fft1")
+
+    def _mix1_args(self, fft1_ptr, fft1_floats, fft1_px, nblocks, states, timf3_ptr, timf3_floats, timf3_pa):
+        a = Mix1Args()
+        a.fft1_float = Ring(fft1_ptr, fft1_floats)
+        a.fft1_px = fft1_px
+        a.nblocks = nblocks
+        a.no_of_channels = len(states)
+        a.state = states
+        a.timf3_float = Ring(timf3_ptr, timf3_floats)
+        a.timf3_pa = timf3_pa
+        return a
+
+    def mix1_dev(self, *, fft1, fft1_floats, fft1_px, nblocks, states, timf3, timf3_floats, timf3_pa):
+        a = self._mix1_args(fft1, fft1_floats, fft1_px, nblocks, states, timf3, timf3_floats, timf3_pa)
+        rc = self.lib.lb200_mix1_dev(self.h, C.byref(a))
+        if rc:
+            raise Lb200Error(rc, "lb200_mix1_dev")
+
+    def mix1_host(self, *, fft1, fft1_px, nblocks, states, timf3, timf3_floats, timf3_pa):
+        a = self._mix1_args(fft1.ctypes.data, fft1.size, fft1_px, nblocks, states, timf3.ctypes.data,
+                            timf3_floats, timf3_pa)
+        rc = self.lib.lb200_mix1(self.h, C.byref(a))
+        if rc:
+            raise Lb200Error(rc, "lb200_mix1")
+
+
+def new_states(selfreqs):
+    """Mix1 state array as buf.c:1259-1263 / wide_graph.c:174 initialise it."""
+    arr = (Mix1State * len(selfreqs))()
+    for i, f in enumerate(selfreqs):
+        arr[i].mix1_selfreq = f
+        arr[i].mix1_point = -1
+    return arr

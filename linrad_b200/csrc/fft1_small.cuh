@@ -1,0 +1,165 @@
+// fft1_small.cuh -- fused fft1 kernel for transforms that fit one CTA (N <= 2^14 per channel).
+//
+// One launch replaces, for a batch of consecutive time blocks,
+//   fft1win_dit_one / fft1win_dif_chan   (fft1.c:684-1028, 2041-2247: ring gather, int->float, window)
+//   bulk_of_dit / bulk_of_dif + permute  (fft0.c:1590-1769, 161-195; fft1.c:637-682)
+//   the direction flip of fft1_b         (fft1.c:3660-3680, 4029-4060)
+//   fft1_c                               (fft1.c:4115-4200: filtercorr multiply, |z|^2, fft1_sumsq)
+// Output convention (probed from the compiled reference):
+//   fft1_float[k] = conj( sum_n w[n] x[n] exp(-2 pi i n ((k+N/2) mod N)/N) ) * filtercorr[k]
+// The (k+N/2) rotation is obtained for free by negating odd-numbered input samples.
+//
+// Work decomposition: one CTA owns one *averaging group* (the wg.fft_avg1num consecutive
+// transforms that are summed into one fft1_sumsq row, fft1.c:4507-4520) and walks through its
+// transforms and channels in time order, so the row is accumulated on chip in the reference's
+// own order and written exactly once.
+#pragma once
+#include "fft_core.cuh"
+
+namespace lb {
+
+enum InFmt { FMT_I16_1CH = 0, FMT_I16_2CH = 1, FMT_I32_1CH = 2, FMT_I32_2CH = 3 };
+template <int FMT> struct FmtInfo;
+template <> struct FmtInfo<FMT_I16_1CH> { static constexpr int FRAME = 4, NCH = 1; };
+template <> struct FmtInfo<FMT_I16_2CH> { static constexpr int FRAME = 8, NCH = 2; };
+template <> struct FmtInfo<FMT_I32_1CH> { static constexpr int FRAME = 8, NCH = 1; };
+template <> struct FmtInfo<FMT_I32_2CH> { static constexpr int FRAME = 16, NCH = 2; };
+
+struct Fft1K {
+  const uint8_t* timf1;     // device ring
+  uint32_t ring_mask;       // bytes
+  uint32_t ref0;            // byte offset of first new sample of transform 0
+  uint32_t blockbytes;      // timf1_blockbytes
+  uint32_t pre_bytes;       // fft1_interleave_points * frame bytes
+  int nblocks;
+  const float* window;      // natural order, nullptr = rectangular
+  const float2* Wn;         // exp(-2 pi i m / N)
+  const float* filtercorr;  // mm*N floats
+  int fc_mode;              // 0 none (raw fft1_b), 1 uniform real gain except edges, 2 full table
+  float fc_gain;            // the uniform gain for fc_mode 1
+  int fc_edge;              // bins [0,fc_edge) and [N-fc_edge,N) always read the table
+  float* out;               // fft1_float ring
+  uint32_t out_mask;        // floats
+  uint32_t out_pa;          // floats
+  float* sumsq;             // fft1_sumsq ring or nullptr
+  uint32_t sumsq_mask;
+  uint32_t sumsq_pa;
+  int counter0;             // fft1_sumsq_counter on entry
+  int avg1num;
+  float* power_rows;        // per-transform |z|^2 rows or nullptr
+  int first_point, last_point;
+  int direction;
+};
+
+template <int FMT>
+LB_D float2 load_iq(const uint8_t* ring, uint32_t off, int c)
+{
+  if (FMT == FMT_I16_1CH) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(ring + off);
+    return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+  } else if (FMT == FMT_I16_2CH) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(ring + off + 4 * c);
+    return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+  } else if (FMT == FMT_I32_1CH) {
+    const int2 w = *reinterpret_cast<const int2*>(ring + off);
+    return make_float2((float)w.x, (float)w.y);
+  } else {
+    const int2 w = *reinterpret_cast<const int2*>(ring + off + 8 * c);
+    return make_float2((float)w.x, (float)w.y);
+  }
+}
+
+template <int LOG2N, int LOG2E, int FMT>
+__global__ void __launch_bounds__(1 << (LOG2N - LOG2E))
+fft1_small_kernel(const Fft1K p)
+{
+  using P = Plan<LOG2N, LOG2E>;
+  constexpr int N = P::N, E = P::E, T = P::T;
+  constexpr int FRAME = FmtInfo<FMT>::FRAME, NCH = FmtInfo<FMT>::NCH, MM = 2 * NCH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* xch = reinterpret_cast<float2*>(smem_raw);
+  float* acc = reinterpret_cast<float*>(smem_raw + sizeof(float2) * (N + N / 32 + 32));
+  const int t = threadIdx.x;
+
+  Twiddles<P> tw;
+  load_twiddles<P>(tw, p.Wn, t);
+  const float sgn = (t & 1) ? -1.0f : 1.0f;          // (-1)^n: rotates the spectrum by N/2
+  const float qs = p.direction < 0 ? -sgn : sgn;     // conj(input) reverses the frequency axis
+
+  const int group_size = p.power_rows ? 1 : p.avg1num;
+  const int c0 = p.power_rows ? 0 : p.counter0;
+  const int ngroups = (c0 + p.nblocks + group_size - 1) / group_size;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    int b0 = g * group_size - c0;
+    int b1 = b0 + group_size;
+    if (b0 < 0) b0 = 0;
+    if (b1 > p.nblocks) b1 = p.nblocks;
+    for (int b = b0; b < b1; b++) {
+      const uint32_t start = p.ref0 + (uint32_t)b * p.blockbytes - p.pre_bytes;
+      float* outb = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c++) {
+        float2 v[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const int idx = t + T * e;
+          const uint32_t off = (start + (uint32_t)idx * FRAME) & p.ring_mask;
+          const float2 s = load_iq<FMT>(p.timf1, off, c);
+          const float w = p.window ? p.window[idx] : 1.0f;
+          v[e] = make_float2(s.x * (w * sgn), s.y * (w * qs));
+        }
+        fft_forward<P>(v, xch, t, tw);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const int k = t + T * e;
+          // direction>0: conj(Y).  direction<0: j*conj(Y') with Y' from the conjugated input.
+          float2 o = p.direction < 0 ? make_float2(v[e].y, v[e].x) : make_float2(v[e].x, -v[e].y);
+          const bool inr = (k >= p.first_point) && (k <= p.last_point);
+          if (p.fc_mode != 0 && inr) {
+            float2 f;
+            if (p.fc_mode == 2 || k < p.fc_edge || k >= N - p.fc_edge)
+              f = *reinterpret_cast<const float2*>(p.filtercorr + (size_t)k * MM + 2 * c);
+            else
+              f = make_float2(p.fc_gain, 0.0f);
+            const float re = o.x * f.x - o.y * f.y;       // fft1.c:4121-4125
+            const float im = o.y * f.x + o.x * f.y;
+            o = make_float2(re, im);
+            const float pw = re * re + im * im;
+            if (b == b0 && c == 0) acc[k] = pw;
+            else acc[k] += pw;
+          }
+          *reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c) = o;
+        }
+      }
+      if (p.power_rows && p.fc_mode != 0) {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const int k = t + T * e;
+          const bool inr = (k >= p.first_point) && (k <= p.last_point);
+          p.power_rows[(size_t)b * N + k] = inr ? acc[k] : 0.0f;
+        }
+      }
+    }
+    if (p.sumsq && !p.power_rows && p.fc_mode != 0 && b1 > b0) {
+      float* row = p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask);
+      const bool continuing = (g == 0 && p.counter0 > 0);
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const int k = t + T * e;
+        if (k >= p.first_point && k <= p.last_point) {
+          float val = acc[k];
+          if (continuing) val = row[k] + val;
+          row[k] = val;
+        }
+      }
+    }
+  }
+}
+
+template <int LOG2N, int LOG2E>
+constexpr size_t fft1_small_smem()
+{
+  return sizeof(float2) * ((1 << LOG2N) + (1 << LOG2N) / 32 + 32) + sizeof(float) * (1 << LOG2N);
+}
+
+}  // namespace lb

@@ -1,0 +1,250 @@
+// fft_core.cuh -- register-resident Stockham FFT building blocks for sm_100a.
+//
+// One transform of N = E*T points is spread over T threads, each holding E points in
+// registers as float2 v[E] with the invariant
+//        v[e] == data[t + T*e]                       (t = thread index within the transform)
+// both before the first pass (natural-order input) and after the last pass (natural-order
+// output), so global loads and stores are unit-stride across threads with no shuffle step.
+// A pass of radix R (R | E) does E/R butterflies per thread; between passes the points are
+// re-distributed through shared memory (the Stockham auto-sort scatter).  This replaces the
+// reference's table-driven in-place CPU kernels: bulk_of_dit (fft0.c:1590-1769, radix-4 DIT
+// + fft1_permute gather), bulk_of_dif (fft0.c:161-195) and fftback (fft0.c:481-533).
+// Sign convention: forward, X[k] = sum_n x[n] exp(-2*pi*i*n*k/N), unnormalised (what the
+// probed reference kernels compute).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef LB_HD
+#define LB_HD __host__ __device__ __forceinline__
+#endif
+#ifndef LB_D
+#define LB_D __device__ __forceinline__
+#endif
+
+namespace lb {
+
+// ---------------------------------------------------------------- small complex helpers
+LB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+LB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+LB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// cos(2*pi*k/32), k = 0..31 (folds to a literal once k is a compile-time constant)
+LB_HD constexpr float cos32(int k)
+{
+  k &= 31;
+  if (k > 16) k = 32 - k;
+  switch (k) {
+    case 0: return 1.0f;
+    case 1: return 0.98078528040323044913f;
+    case 2: return 0.92387953251128675613f;
+    case 3: return 0.83146961230254523708f;
+    case 4: return 0.70710678118654752440f;
+    case 5: return 0.55557023301960222474f;
+    case 6: return 0.38268343236508977173f;
+    case 7: return 0.19509032201612826785f;
+    case 8: return 0.0f;
+    case 9: return -0.19509032201612826785f;
+    case 10: return -0.38268343236508977173f;
+    case 11: return -0.55557023301960222474f;
+    case 12: return -0.70710678118654752440f;
+    case 13: return -0.83146961230254523708f;
+    case 14: return -0.92387953251128675613f;
+    case 15: return -0.98078528040323044913f;
+    default: return -1.0f;
+  }
+}
+LB_HD constexpr float sin32(int k) { return cos32(k - 8); }
+
+// a * exp(-2*pi*i*k32/32) with the trivial rotations done without multiplies
+LB_HD float2 rot32(float2 a, int k32)
+{
+  k32 &= 31;
+  switch (k32) {
+    case 0: return a;
+    case 8: return make_float2(a.y, -a.x);
+    case 16: return make_float2(-a.x, -a.y);
+    case 24: return make_float2(-a.y, a.x);
+    case 4: return make_float2((a.x + a.y) * 0.70710678118654752440f, (a.y - a.x) * 0.70710678118654752440f);
+    case 12: return make_float2((a.y - a.x) * 0.70710678118654752440f, -(a.x + a.y) * 0.70710678118654752440f);
+    case 20: return make_float2(-(a.x + a.y) * 0.70710678118654752440f, (a.x - a.y) * 0.70710678118654752440f);
+    case 28: return make_float2((a.x - a.y) * 0.70710678118654752440f, (a.x + a.y) * 0.70710678118654752440f);
+    default: {
+      const float c = cos32(k32), s = sin32(k32);      // exp(-i th) = c - i s
+      return make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- DFT_R on registers
+// In-place forward DFT of the R points x[0], x[S], ..., x[(R-1)S]; natural order in and out.
+// Radix-2 decimation in time; every index is a compile-time constant after unrolling so the
+// "temporary" arrays are pure register renaming.
+template <int R, int S>
+struct DftS {
+  static LB_HD void run(float2* x)
+  {
+    DftS<R / 2, 2 * S>::run(x);
+    DftS<R / 2, 2 * S>::run(x + S);
+    float2 lo[R / 2], hi[R / 2];
+#pragma unroll
+    for (int k = 0; k < R / 2; k++) {
+      const float2 e = x[2 * S * k];
+      const float2 o = rot32(x[S + 2 * S * k], k * (32 / R));
+      lo[k] = cadd(e, o);
+      hi[k] = csub(e, o);
+    }
+#pragma unroll
+    for (int k = 0; k < R / 2; k++) {
+      x[S * k] = lo[k];
+      x[S * (k + R / 2)] = hi[k];
+    }
+  }
+};
+template <int S>
+struct DftS<1, S> {
+  static LB_HD void run(float2*) {}
+};
+
+// ---------------------------------------------------------------- one Stockham pass
+// Geometry of a pass: N points, T threads, E = N/T points per thread, radix R, Ns = product
+// of the radices of the earlier passes.  Butterfly q of thread t is Stockham butterfly
+// j = t + T*q; it consumes v[q + r*(E/R)], r = 0..R-1 (== data[j + r*N/R]) and its r-th
+// output belongs at index (j-k)*R + k + r*Ns with k = j mod Ns.
+//
+// Twiddles: input r is multiplied by w1^r, w1 = exp(-2*pi*i*k/(Ns*R)).  Only w1 is fetched
+// (tw1[q], hoisted by the caller); the powers are built with four interleaved chains
+// w[r] = w[r-4]*w[4] to keep both latency and live registers low.
+template <int E, int R, int T>
+LB_HD void pass_butterflies(float2 (&v)[E], const float2* tw1, bool twiddled)
+{
+  constexpr int Q = E / R;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    float2 x[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) x[r] = v[q + r * Q];
+    if (twiddled) {
+      const float2 w1 = tw1[q];
+      if (R >= 2) x[1] = cmul(x[1], w1);
+      if (R > 2) {
+        float2 w[R > 4 ? R : 5];
+        w[1] = w1;
+        w[2] = cmul(w1, w1);
+        w[3] = cmul(w[2], w1);
+        x[2] = cmul(x[2], w[2]);
+        x[3] = cmul(x[3], w[3]);
+        if (R > 4) {
+          w[4] = cmul(w[2], w[2]);
+          x[4] = cmul(x[4], w[4]);
+#pragma unroll
+          for (int r = 5; r < R; r++) {
+            w[r] = cmul(w[r - 4], w[4]);
+            x[r] = cmul(x[r], w[r]);
+          }
+        }
+      }
+    }
+    DftS<R, 1>::run(x);
+#pragma unroll
+    for (int r = 0; r < R; r++) v[q + r * Q] = x[r];
+  }
+}
+
+// index of the twiddle base w1 for butterfly q of thread t inside a table
+// W[m] = exp(-2*pi*i*m/N): m = k * N/(Ns*R)
+template <int E, int R, int T>
+LB_HD int tw1_index(int t, int q, int Ns)
+{
+  constexpr int N = E * T;
+  const int j = t + T * q;
+  const int k = j & (Ns - 1);
+  return k * (N / (Ns * R));
+}
+
+// shared-memory slot for logical index i; one pad slot every 32 keeps the strided scatter of
+// the first exchange spread over the banks.
+template <int LOG2PAD>
+LB_HD int padded(int i) { return LOG2PAD > 0 ? i + (i >> LOG2PAD) : i; }
+
+template <int E, int R, int T, int LOG2PAD>
+LB_HD void exchange_store(const float2 (&v)[E], float2* sm, int t, int Ns)
+{
+  constexpr int Q = E / R;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int j = t + T * q;
+    const int k = j & (Ns - 1);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; r++) sm[padded<LOG2PAD>(base + r * Ns)] = v[q + r * Q];
+  }
+}
+
+template <int E, int T, int LOG2PAD>
+LB_HD void exchange_load(float2 (&v)[E], const float2* sm, int t)
+{
+#pragma unroll
+  for (int e = 0; e < E; e++) v[e] = sm[padded<LOG2PAD>(t + T * e)];
+}
+
+// ---------------------------------------------------------------- radix plans
+// Radix sequence for N = 2^LOG2N with E points per thread: as many radix-E passes as fit,
+// preceded by one smaller pass for the remainder (the first pass needs no twiddles, so the
+// odd-sized one goes first).
+template <int LOG2N, int LOG2E>
+struct Plan {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int E = 1 << LOG2E;
+  static constexpr int T = N / E;
+  static constexpr int REM = LOG2N % LOG2E;                 // log2 of the leading small radix
+  static constexpr int NPASS = LOG2N / LOG2E + (REM ? 1 : 0);
+  static constexpr int R0 = REM ? (1 << REM) : E;           // radix of pass 0
+  // radix of pass p, and Ns before pass p
+  static LB_HD constexpr int radix(int p) { return p == 0 ? R0 : E; }
+  static LB_HD constexpr int ns(int p) { return p == 0 ? 1 : (R0 << (LOG2E * (p - 1))); }
+  static constexpr int MAXQ = E / R0;                       // butterflies per thread in pass 0
+  static constexpr int NTW = NPASS - 1;                     // twiddled passes (each has Q = 1 ... or E/R)
+};
+
+// Per-thread hoisted twiddle bases: tw[p-1][q] for pass p >= 1 (all later passes have R == E,
+// hence exactly one butterfly per thread).
+template <class P>
+struct Twiddles {
+  float2 w[P::NTW > 0 ? P::NTW : 1];
+};
+
+template <class P>
+LB_D void load_twiddles(Twiddles<P>& tw, const float2* __restrict__ Wn, int t)
+{
+#pragma unroll
+  for (int p = 1; p < P::NPASS; p++) {
+    const int Ns = P::ns(p);
+    tw.w[p - 1] = Wn[tw1_index<P::E, P::E, P::T>(t, 0, Ns)];
+  }
+}
+
+#ifdef __CUDACC__
+// The whole transform.  On entry v[e] = x[t + T*e]; on exit v[e] = X[t + T*e].
+// `sm` must hold N + N/32 float2; every thread of the CTA must call this (it contains
+// __syncthreads), but several independent transforms may run side by side in one CTA as
+// long as each gets its own `sm` slice and its own t in [0,T).
+template <class P>
+LB_D void fft_forward(float2 (&v)[P::E], float2* sm, int t, const Twiddles<P>& tw)
+{
+  constexpr int E = P::E, T = P::T;
+  pass_butterflies<E, P::R0, T>(v, nullptr, false);
+#pragma unroll
+  for (int p = 1; p < P::NPASS; p++) {
+    const int NsPrev = P::ns(p - 1);
+    if (p == 1) exchange_store<E, P::R0, T, 5>(v, sm, t, NsPrev);
+    else exchange_store<E, E, T, 5>(v, sm, t, NsPrev);
+    __syncthreads();
+    exchange_load<E, T, 5>(v, sm, t);
+    __syncthreads();
+    pass_butterflies<E, E, T>(v, &tw.w[p - 1], true);
+  }
+}
+#endif
+
+}  // namespace lb

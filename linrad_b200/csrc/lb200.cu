@@ -1,0 +1,491 @@
+// lb200.cu -- plan object, kernel dispatch and the extern "C" entry points of
+// include/linrad_b200.h.  Host logic here mirrors what the reference's wideband and
+// narrowband threads do around their compute calls (wcw.c:1036-1047, fft1.c:4507-4523,
+// mix1.c:995-1041); all sample arithmetic runs in the sm_100a kernels.  There is no CPU
+// fallback: without a CUDA device lb200_create fails with LB200_ERR_NO_DEVICE.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include "plan.h"
+#include "fft1_small.cuh"
+#include "fft1_large.cuh"
+#include "mix1.cuh"
+
+using namespace lb;
+
+#define LB_PI 3.1415926535897932
+
+// ------------------------------------------------------------------------------------------
+// kernel launchers (explicit instantiation lives in kernels_*.cu so they compile in parallel)
+typedef cudaError_t (*fft1_small_launch_t)(const Fft1K&, int grid, cudaStream_t);
+typedef cudaError_t (*mix1_launch_t)(const Mix1K&, int grid, cudaStream_t);
+fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* threads, size_t* smem);
+mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem);
+cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k);
+bool lb_fft1_large_supported(int log2n);
+
+static int env_int(const char* name, int dflt)
+{
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------
+static int upload(lb200_plan* plan, void** dst, const void* src, size_t bytes)
+{
+  LB_CUDA(cudaMalloc(dst, bytes));
+  LB_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static void make_twiddles(std::vector<float2>& w, int n)
+{
+  w.resize(n);
+  for (int i = 0; i < n; i++) {
+    const double a = -2.0 * LB_PI * (double)i / (double)n;
+    w[i] = make_float2((float)cos(a), (float)sin(a));
+  }
+}
+
+extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
+{
+  if (!cfg || !out) return LB200_ERR_BAD_ARG;
+  *out = nullptr;
+  if (cfg->abi_version != LB200_ABI_VERSION) return LB200_ERR_BAD_CONFIG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) return LB200_ERR_NO_DEVICE;
+  lb200_plan* plan = new lb200_plan();
+  plan->cfg = *cfg;
+  plan->device = cfg->device;
+  int rc = 0;
+  auto fail = [&](int code) { lb200_destroy(plan); return code; };
+  if (cudaSetDevice(plan->device) != cudaSuccess) return fail(LB200_ERR_NO_DEVICE);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, plan->device) != cudaSuccess) return fail(LB200_ERR_NO_DEVICE);
+  plan->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(LB200_ERR_CUDA);
+
+  // ---- geometry (buf.c:165-332)
+  if (cfg->fft1_n < 3 || cfg->fft1_n > 22) return fail(LB200_ERR_BAD_CONFIG);
+  if (cfg->rx_rf_channels < 1 || cfg->rx_rf_channels > 2) return fail(LB200_ERR_BAD_CONFIG);
+  plan->N = 1 << cfg->fft1_n;
+  plan->nch = cfg->rx_rf_channels;
+  plan->mm = 2 * plan->nch;
+  plan->iq = (cfg->rx_input_mode & LB200_IQ_DATA) != 0;
+  const bool dword = (cfg->rx_input_mode & LB200_DWORD_INPUT) != 0;
+  if (((cfg->rx_input_mode & LB200_TWO_CHANNELS) != 0) != (plan->nch == 2)) return fail(LB200_ERR_BAD_CONFIG);
+  plan->frame = (plan->iq ? 2 : 1) * plan->nch * (dword ? 4 : 2);
+  plan->fmt = (dword ? 2 : 0) + (plan->nch == 2 ? 1 : 0);
+  plan->fft1_block = plan->mm * plan->N;
+  if (cfg->fft1_interleave_points < 0 || cfg->fft1_interleave_points >= plan->N) return fail(LB200_ERR_BAD_CONFIG);
+  plan->new_points = plan->N - cfg->fft1_interleave_points;
+  plan->blockbytes = (uint32_t)plan->new_points * plan->frame * (plan->iq ? 1 : 2);
+  if (cfg->fft1_first_point < 0 || cfg->fft1_last_point >= plan->N || cfg->fft1_first_point > cfg->fft1_last_point)
+    return fail(LB200_ERR_BAD_CONFIG);
+  if (cfg->fft_avg1num < 1) return fail(LB200_ERR_BAD_CONFIG);
+  if (cfg->sample_shift != 0) return fail(LB200_ERR_UNSUPPORTED);
+  if (cfg->fft1_foldcorr != nullptr) return fail(LB200_ERR_UNSUPPORTED);
+  if (!plan->iq) return fail(LB200_ERR_UNSUPPORTED);   // real input: fft1_re path, see DESIGN.md
+  if (cfg->fft1_n > 14 && !lb_fft1_large_supported(cfg->fft1_n)) return fail(LB200_ERR_UNSUPPORTED);
+  if (cfg->fft1_n < 7) return fail(LB200_ERR_UNSUPPORTED);
+
+  // ---- tables
+  {
+    std::vector<float2> w;
+    make_twiddles(w, plan->N);
+    if ((rc = upload(plan, (void**)&plan->d_Wn, w.data(), sizeof(float2) * w.size()))) return fail(rc);
+  }
+  if (cfg->fft1_window)
+    if ((rc = upload(plan, (void**)&plan->d_window, cfg->fft1_window, sizeof(float) * plan->N))) return fail(rc);
+  if (cfg->fft1_filtercorr) {
+    const float* fc = cfg->fft1_filtercorr;
+    if ((rc = upload(plan, (void**)&plan->d_filtercorr, fc, sizeof(float) * plan->fft1_block))) return fail(rc);
+    // uncalibrated tables (clear_fft1_filtercorr, fft1.c:4673-4724) are one real gain except for
+    // the sin^2 taper on the outermost bins: detect that and spare the kernel the table read
+    const int edge = 16;
+    plan->fc_mode = 1;
+    plan->fc_edge = edge;
+    plan->fc_gain = fc[(size_t)plan->mm * (plan->N / 2)];
+    for (int k = edge; k < plan->N - edge && plan->fc_mode == 1; k++)
+      for (int c = 0; c < plan->nch; c++)
+        if (fc[(size_t)k * plan->mm + 2 * c] != plan->fc_gain || fc[(size_t)k * plan->mm + 2 * c + 1] != 0.0f) plan->fc_mode = 2;
+    if (env_int("LB200_FC_TABLE", 0)) plan->fc_mode = 2;
+  } else {
+    plan->fc_mode = 0;
+  }
+
+  // ---- mix1 (buf.c:1297-1300, prepare_mixer buf.c:55-111)
+  if (cfg->mix1_n > 0) {
+    if (cfg->mix1_n < 3 || cfg->mix1_n > 13 || cfg->mix1_n > cfg->fft1_n) return fail(LB200_ERR_UNSUPPORTED);
+    plan->M = 1 << cfg->mix1_n;
+    if (!cfg->mix1_fqwin) return fail(LB200_ERR_BAD_CONFIG);
+    std::vector<float2> w;
+    make_twiddles(w, plan->M);
+    if ((rc = upload(plan, (void**)&plan->d_Wm, w.data(), sizeof(float2) * w.size()))) return fail(rc);
+    if ((rc = upload(plan, (void**)&plan->d_fqwin, cfg->mix1_fqwin, sizeof(float) * (plan->M / 2 + 1)))) return fail(rc);
+    const int Mi = cfg->mix1_interleave_points, Mn = plan->M - Mi;
+    if (Mi != 0 && Mi != Mn) {
+      if (!cfg->mix1_window || !cfg->mix1_cos2win || !cfg->mix1_sin2win || cfg->mix1_crossover_points <= 0)
+        return fail(LB200_ERR_BAD_CONFIG);
+      if ((rc = upload(plan, (void**)&plan->d_mixwin, cfg->mix1_window, sizeof(float) * (plan->M / 2 + 1)))) return fail(rc);
+      if ((rc = upload(plan, (void**)&plan->d_cos2win, cfg->mix1_cos2win, sizeof(float) * cfg->mix1_crossover_points))) return fail(rc);
+      if ((rc = upload(plan, (void**)&plan->d_sin2win, cfg->mix1_sin2win, sizeof(float) * cfg->mix1_crossover_points))) return fail(rc);
+    }
+  }
+  // the plan keeps its own copies; never dereference the caller's table pointers again
+  plan->cfg.fft1_window = nullptr; plan->cfg.fft1_filtercorr = nullptr; plan->cfg.fft1_foldcorr = nullptr;
+  plan->cfg.mix1_fqwin = nullptr; plan->cfg.mix1_window = nullptr; plan->cfg.mix1_cos2win = nullptr; plan->cfg.mix1_sin2win = nullptr;
+  *out = plan;
+  return LB200_OK;
+}
+
+static void free_mirror(HostMirror& m)
+{
+  if (m.d) cudaFree(m.d);
+  m = HostMirror();
+}
+
+extern "C" void lb200_destroy(lb200_plan* plan)
+{
+  if (!plan) return;
+  cudaSetDevice(plan->device);
+  if (plan->stream) cudaStreamSynchronize(plan->stream);
+  for (auto& kv : plan->registered) cudaHostUnregister(const_cast<void*>(kv.first));
+  void* ptrs[] = {plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
+                  plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wbig, plan->d_mixjobs};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (plan->h_mixjobs) cudaFreeHost(plan->h_mixjobs);
+  free_mirror(plan->m_timf1); free_mirror(plan->m_fft1); free_mirror(plan->m_sumsq);
+  free_mirror(plan->m_timf3); free_mirror(plan->m_power);
+  if (plan->stream) cudaStreamDestroy(plan->stream);
+  delete plan;
+}
+
+extern "C" void* lb200_stream(lb200_plan* plan) { return plan ? (void*)plan->stream : nullptr; }
+extern "C" int lb200_synchronize(lb200_plan* plan)
+{
+  if (!plan) return LB200_ERR_BAD_ARG;
+  LB_CUDA(cudaStreamSynchronize(plan->stream));
+  return LB200_OK;
+}
+extern "C" uint64_t lb200_launch_count(const lb200_plan* plan) { return plan ? plan->launches : 0; }
+extern "C" uint64_t lb200_h2d_bytes(const lb200_plan* plan) { return plan ? plan->h2d : 0; }
+extern "C" uint64_t lb200_d2h_bytes(const lb200_plan* plan) { return plan ? plan->d2h : 0; }
+
+static bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
+
+// ------------------------------------------------------------------------------------------
+// fft1
+extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
+{
+  if (!plan || !a || !a->timf1.base || !a->fft1_float.base) return LB200_ERR_BAD_ARG;
+  if (a->nblocks <= 0) return LB200_OK;
+  if (!is_pow2(a->timf1.size) || !is_pow2(a->fft1_float.size)) return LB200_ERR_BAD_ARG;
+  if (a->timf1p_ref % plan->frame) return LB200_ERR_BAD_ARG;
+  if ((size_t)plan->fft1_block * a->nblocks > a->fft1_float.size) return LB200_ERR_BAD_ARG;
+  if ((size_t)plan->blockbytes * a->nblocks + (size_t)plan->cfg.fft1_interleave_points * plan->frame > a->timf1.size) return LB200_ERR_BAD_ARG;
+  if (a->fft1_pa % plan->fft1_block) return LB200_ERR_BAD_ARG;
+  if (a->apply_filtercorr && plan->fc_mode == 0) return LB200_ERR_BAD_CONFIG;
+  cudaSetDevice(plan->device);
+  Fft1K k;
+  memset(&k, 0, sizeof(k));
+  k.timf1 = (const uint8_t*)a->timf1.base;
+  k.ring_mask = (uint32_t)(a->timf1.size - 1);
+  k.ref0 = a->timf1p_ref;
+  k.blockbytes = plan->blockbytes;
+  k.pre_bytes = (uint32_t)plan->cfg.fft1_interleave_points * plan->frame;
+  k.nblocks = a->nblocks;
+  k.window = plan->d_window;
+  k.Wn = plan->d_Wn;
+  k.filtercorr = plan->d_filtercorr;
+  k.fc_mode = a->apply_filtercorr ? plan->fc_mode : 0;
+  k.fc_gain = plan->fc_gain;
+  k.fc_edge = plan->fc_edge;
+  k.out = (float*)a->fft1_float.base;
+  k.out_mask = (uint32_t)(a->fft1_float.size - 1);
+  k.out_pa = a->fft1_pa;
+  k.sumsq = nullptr;
+  k.power_rows = nullptr;
+  k.avg1num = plan->cfg.fft_avg1num;
+  k.counter0 = 0;
+  if (a->apply_filtercorr) {
+    if (a->power_rows) {
+      k.power_rows = a->power_rows;
+    } else if (a->fft1_sumsq.base) {
+      if (!is_pow2(a->fft1_sumsq.size) || a->fft1_sumsq_pa % plan->N) return LB200_ERR_BAD_ARG;
+      if (a->fft1_sumsq_counter < 0 || a->fft1_sumsq_counter >= plan->cfg.fft_avg1num) return LB200_ERR_BAD_ARG;
+      const size_t rows = ((size_t)a->fft1_sumsq_counter + a->nblocks + plan->cfg.fft_avg1num - 1) / plan->cfg.fft_avg1num;
+      if (rows * plan->N > a->fft1_sumsq.size) return LB200_ERR_BAD_ARG;
+      k.sumsq = (float*)a->fft1_sumsq.base;
+      k.sumsq_mask = (uint32_t)(a->fft1_sumsq.size - 1);
+      k.sumsq_pa = a->fft1_sumsq_pa;
+      k.counter0 = a->fft1_sumsq_counter;
+    }
+  }
+  k.first_point = plan->cfg.fft1_first_point;
+  k.last_point = plan->cfg.fft1_last_point;
+  k.direction = plan->cfg.fft1_direction;
+
+  if (plan->cfg.fft1_n > 14) {
+    LB_CUDA(lb_launch_fft1_large(plan, k));
+    return LB200_OK;
+  }
+  int threads = 0;
+  size_t smem = 0;
+  fft1_small_launch_t fn = lb_get_fft1_small(plan->cfg.fft1_n, plan->fmt, env_int("LB200_FFT1_VARIANT", 0), &threads, &smem);
+  if (!fn) return LB200_ERR_UNSUPPORTED;
+  const int group = k.power_rows ? 1 : k.avg1num;
+  const int ngroups = (k.counter0 + k.nblocks + group - 1) / group;
+  int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int by_threads = 2048 / threads;
+  if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
+  int grid = ngroups;
+  const int cap = plan->sm_count * ctas_per_sm * env_int("LB200_GRID_WAVES", 1);
+  if (grid > cap) grid = cap;
+  LB_CUDA(fn(k, grid, plan->stream));
+  plan->launches++;
+  return LB200_OK;
+}
+
+// ---- host-ring staging helpers -----------------------------------------------------------
+static int ensure_mirror(lb200_plan* plan, HostMirror& m, const void* host, size_t bytes)
+{
+  if (m.d && m.bytes == bytes && m.host == host) return 0;
+  if (m.d) { cudaFree(m.d); m.d = nullptr; }
+  LB_CUDA(cudaMalloc(&m.d, bytes));
+  LB_CUDA(cudaMemsetAsync(m.d, 0, bytes, plan->stream));
+  m.bytes = bytes;
+  m.host = host;
+  // page-lock Linrad's malloc'ed ring once so the copies run at full PCIe rate
+  if (host && !plan->registered.count(host) && !env_int("LB200_NO_HOSTREGISTER", 0)) {
+    if (cudaHostRegister(const_cast<void*>(host), bytes, cudaHostRegisterDefault) == cudaSuccess) plan->registered[host] = bytes;
+    else cudaGetLastError();
+  }
+  return 0;
+}
+
+// copy [off, off+len) of a power-of-two ring of `size` bytes, wrapping, H2D or D2H
+static int ring_copy(lb200_plan* plan, void* dev, void* host, size_t size, size_t off, size_t len, bool h2d)
+{
+  off &= size - 1;
+  while (len > 0) {
+    size_t n = size - off;
+    if (n > len) n = len;
+    if (h2d) {
+      LB_CUDA(cudaMemcpyAsync((char*)dev + off, (const char*)host + off, n, cudaMemcpyHostToDevice, plan->stream));
+      plan->h2d += n;
+    } else {
+      LB_CUDA(cudaMemcpyAsync((char*)host + off, (const char*)dev + off, n, cudaMemcpyDeviceToHost, plan->stream));
+      plan->d2h += n;
+    }
+    len -= n;
+    off = (off + n) & (size - 1);
+  }
+  return 0;
+}
+
+extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
+{
+  if (!plan || !a || !a->timf1.base || !a->fft1_float.base) return LB200_ERR_BAD_ARG;
+  if (a->nblocks <= 0) return LB200_OK;
+  if (!is_pow2(a->timf1.size) || !is_pow2(a->fft1_float.size)) return LB200_ERR_BAD_ARG;
+  cudaSetDevice(plan->device);
+  int rc;
+  lb200_fft1_args d = *a;
+  const size_t pre = (size_t)plan->cfg.fft1_interleave_points * plan->frame;
+  const size_t span = pre + (size_t)plan->blockbytes * a->nblocks;
+  if (span > a->timf1.size) return LB200_ERR_BAD_ARG;
+  if ((rc = ensure_mirror(plan, plan->m_timf1, a->timf1.base, a->timf1.size))) return rc;
+  if ((rc = ensure_mirror(plan, plan->m_fft1, a->fft1_float.base, a->fft1_float.size * sizeof(float)))) return rc;
+  if ((rc = ring_copy(plan, plan->m_timf1.d, a->timf1.base, a->timf1.size, (size_t)a->timf1p_ref - pre + a->timf1.size, span, true))) return rc;
+  d.timf1.base = plan->m_timf1.d;
+  d.fft1_float.base = plan->m_fft1.d;
+  size_t rows = 0;
+  if (a->apply_filtercorr && a->power_rows) {
+    const size_t bytes = sizeof(float) * (size_t)plan->N * a->nblocks;
+    if (!plan->m_power.d || plan->m_power.bytes < bytes) {
+      if (plan->m_power.d) cudaFree(plan->m_power.d);
+      LB_CUDA(cudaMalloc(&plan->m_power.d, bytes));
+      plan->m_power.bytes = bytes;
+    }
+    d.power_rows = (float*)plan->m_power.d;
+  } else if (a->apply_filtercorr && a->fft1_sumsq.base) {
+    if (!is_pow2(a->fft1_sumsq.size)) return LB200_ERR_BAD_ARG;
+    if ((rc = ensure_mirror(plan, plan->m_sumsq, a->fft1_sumsq.base, a->fft1_sumsq.size * sizeof(float)))) return rc;
+    d.fft1_sumsq.base = plan->m_sumsq.d;
+    rows = ((size_t)a->fft1_sumsq_counter + a->nblocks + plan->cfg.fft_avg1num - 1) / plan->cfg.fft_avg1num;
+    if (a->fft1_sumsq_counter > 0)   // a row in progress: bring the host's partial sums over
+      if ((rc = ring_copy(plan, plan->m_sumsq.d, a->fft1_sumsq.base, a->fft1_sumsq.size * 4, (size_t)a->fft1_sumsq_pa * 4, (size_t)plan->N * 4, true))) return rc;
+  }
+  if ((rc = lb200_fft1_dev(plan, &d))) return rc;
+  if ((rc = ring_copy(plan, plan->m_fft1.d, a->fft1_float.base, a->fft1_float.size * 4, (size_t)a->fft1_pa * 4,
+                      (size_t)plan->fft1_block * a->nblocks * 4, false))) return rc;
+  if (d.power_rows && a->power_rows) {
+    const size_t bytes = sizeof(float) * (size_t)plan->N * a->nblocks;
+    LB_CUDA(cudaMemcpyAsync(a->power_rows, d.power_rows, bytes, cudaMemcpyDeviceToHost, plan->stream));
+    plan->d2h += bytes;
+  } else if (rows) {
+    if ((rc = ring_copy(plan, plan->m_sumsq.d, a->fft1_sumsq.base, a->fft1_sumsq.size * 4, (size_t)a->fft1_sumsq_pa * 4,
+                        rows * plan->N * 4, false))) return rc;
+  }
+  LB_CUDA(cudaStreamSynchronize(plan->stream));
+  return LB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// mix1
+static int mix1_mode(const lb200_plan* plan)
+{
+  const int Mi = plan->cfg.mix1_interleave_points, Mn = plan->M - Mi;
+  return Mi == 0 ? 0 : (Mi == Mn ? 1 : 2);
+}
+
+// Build the job table for one call: the sequential part of fft1_mix1_fixed
+// (mix1.c:1005-1040) -- set_mix1_phases per transform and selection, then the float phase that
+// do_mix1 leaves behind after its Mn running additions (mix1.c:154,187,260).
+static int build_mix1_jobs(lb200_plan* plan, const lb200_mix1_args* a, std::vector<Mix1Job>& jobs)
+{
+  const int K = a->no_of_channels, B = a->nblocks;
+  const int Mn = plan->M - plan->cfg.mix1_interleave_points;
+  const uint32_t t3block = (uint32_t)(plan->mm * Mn);
+  jobs.resize((size_t)K * B);
+  for (int ss = 0; ss < K; ss++) {
+    lb200_mix1_state* s = &a->state[ss];
+    for (int b = 0; b < B; b++) {
+      Mix1Job& j = jobs[(size_t)ss * B + b];
+      j.src = (uint32_t)((a->fft1_px + (size_t)b * plan->fft1_block) & (a->fft1_float.size - 1));
+      j.dst = (uint32_t)((a->timf3_pa + (size_t)b * t3block) & (a->timf3_float.size - 1));
+      if (s->mix1_selfreq < 0) { j.point = -1; j.t1 = j.t2 = j.r1 = j.r2 = 0; continue; }
+      const int rc = lb200_set_mix1_phases(&plan->cfg, s, (float)s->mix1_selfreq);   /* mix1.c:1007,1013 */
+      if (rc) return rc;
+      j.point = s->mix1_point;
+      j.t1 = s->mix1_phase;
+      j.t2 = s->mix1_phase_rot;
+      j.r1 = s->mix1_old_phase;
+      j.r2 = (float)((double)j.t2 - (double)(2 * (s->mix1_old_point - s->mix1_point)) * LB_PI / (double)plan->M);  /* mix1.c:167 */
+      s->mix1_phase = lb_phase_advance(j.t1, j.t2, Mn);                             /* mix1.c:154,187,260 */
+    }
+  }
+  return 0;
+}
+
+static int launch_mix1(lb200_plan* plan, const lb200_mix1_args* a, const float* d_fft1, uint32_t fft1_mask,
+                       float* d_timf3, const std::vector<Mix1Job>& jobs)
+{
+  const int K = a->no_of_channels, B = a->nblocks;
+  const size_t bytes = sizeof(Mix1Job) * jobs.size();
+  if (plan->mixjobs_bytes < bytes) {
+    if (plan->d_mixjobs) cudaFree(plan->d_mixjobs);
+    if (plan->h_mixjobs) cudaFreeHost(plan->h_mixjobs);
+    plan->d_mixjobs = nullptr; plan->h_mixjobs = nullptr;
+    LB_CUDA(cudaMalloc(&plan->d_mixjobs, bytes));
+    LB_CUDA(cudaMallocHost(&plan->h_mixjobs, bytes));
+    plan->mixjobs_bytes = bytes;
+  }
+  // the pinned staging buffer may still feed the previous call's copy
+  LB_CUDA(cudaStreamSynchronize(plan->stream));
+  memcpy(plan->h_mixjobs, jobs.data(), bytes);
+  LB_CUDA(cudaMemcpyAsync(plan->d_mixjobs, plan->h_mixjobs, bytes, cudaMemcpyHostToDevice, plan->stream));
+  Mix1K k;
+  memset(&k, 0, sizeof(k));
+  k.fft1 = d_fft1;
+  k.fft1_mask = fft1_mask;
+  k.jobs = (const Mix1Job*)plan->d_mixjobs;
+  k.nblocks = B;
+  k.nsel = K;
+  k.timf3 = d_timf3;
+  k.sel_stride = 2 * a->timf3_float.size;
+  k.timf3_mask = (uint32_t)(a->timf3_float.size - 1);
+  k.Wm = plan->d_Wm;
+  k.fqwin = plan->d_fqwin;
+  k.window = plan->d_mixwin;
+  k.cos2win = plan->d_cos2win;
+  k.sin2win = plan->d_sin2win;
+  k.first_point = plan->cfg.fft1_first_point;
+  k.last_point = plan->cfg.fft1_last_point;
+  k.Mi = plan->cfg.mix1_interleave_points;
+  k.Mn = plan->M - k.Mi;
+  k.cross = plan->cfg.mix1_crossover_points;
+  k.mode = mix1_mode(plan);
+  int threads = 0;
+  size_t smem = 0;
+  mix1_launch_t fn = lb_get_mix1(plan->cfg.mix1_n, plan->nch, &threads, &smem);
+  if (!fn) return LB200_ERR_UNSUPPORTED;
+  // run length: long enough to amortise the one rebuilt predecessor, short enough to fill the GPU
+  int target = plan->sm_count * 4;
+  int runlen = (int)(((size_t)K * B + target - 1) / target);
+  if (runlen < 1) runlen = 1;
+  if (runlen > 32) runlen = 32;
+  runlen = env_int("LB200_MIX1_RUNLEN", runlen);
+  k.runlen = runlen;
+  const int nruns = ((B + runlen - 1) / runlen) * K;
+  int grid = nruns;
+  const int cap = plan->sm_count * 16;
+  if (grid > cap) grid = cap;
+  LB_CUDA(fn(k, grid, plan->stream));
+  plan->launches++;
+  return LB200_OK;
+}
+
+static int check_mix1_args(lb200_plan* plan, const lb200_mix1_args* a)
+{
+  if (!plan || !a || !a->state || !a->fft1_float.base || !a->timf3_float.base) return LB200_ERR_BAD_ARG;
+  if (plan->M == 0) return LB200_ERR_BAD_CONFIG;
+  if (a->no_of_channels < 1 || a->no_of_channels > LB200_MAX_MIX1) return LB200_ERR_BAD_ARG;
+  if (!is_pow2(a->fft1_float.size) || !is_pow2(a->timf3_float.size)) return LB200_ERR_BAD_ARG;
+  const int Mn = plan->M - plan->cfg.mix1_interleave_points;
+  // the whole call (plus the parked tail) must fit the ring without lapping itself
+  if ((size_t)plan->mm * ((size_t)Mn * a->nblocks + plan->M) > a->timf3_float.size) return LB200_ERR_BAD_ARG;
+  return 0;
+}
+
+extern "C" int lb200_mix1_dev(lb200_plan* plan, const lb200_mix1_args* a)
+{
+  int rc = check_mix1_args(plan, a);
+  if (rc) return rc;
+  if (a->nblocks <= 0) return LB200_OK;
+  cudaSetDevice(plan->device);
+  std::vector<Mix1Job> jobs;
+  if ((rc = build_mix1_jobs(plan, a, jobs))) return rc;
+  return launch_mix1(plan, a, (const float*)a->fft1_float.base, (uint32_t)(a->fft1_float.size - 1),
+                     (float*)a->timf3_float.base, jobs);
+}
+
+extern "C" int lb200_mix1(lb200_plan* plan, const lb200_mix1_args* a)
+{
+  int rc = check_mix1_args(plan, a);
+  if (rc) return rc;
+  if (a->nblocks <= 0) return LB200_OK;
+  cudaSetDevice(plan->device);
+  const int K = a->no_of_channels;
+  const int Mn = plan->M - plan->cfg.mix1_interleave_points;
+  const int mode = mix1_mode(plan);
+  const int carry = mode == 1 ? plan->M / 2 : (mode == 2 ? plan->cfg.mix1_crossover_points : 0);
+  std::vector<Mix1Job> jobs;
+  if ((rc = build_mix1_jobs(plan, a, jobs))) return rc;
+  // spectra: the source blocks go to the device mirror of fft1_float (whole blocks; a selection
+  // only needs M bins but the blocks are usually already there from lb200_fft1 on this plan)
+  if ((rc = ensure_mirror(plan, plan->m_fft1, a->fft1_float.base, a->fft1_float.size * 4))) return rc;
+  if ((rc = ensure_mirror(plan, plan->m_timf3, a->timf3_float.base, (size_t)K * 2 * a->timf3_float.size * 4))) return rc;
+  if (!env_int("LB200_MIX1_TRUST_MIRROR", 0))
+    if ((rc = ring_copy(plan, plan->m_fft1.d, a->fft1_float.base, a->fft1_float.size * 4, (size_t)a->fft1_px * 4,
+                        (size_t)plan->fft1_block * a->nblocks * 4, true))) return rc;
+  // parked tails of the previous call (mix1.c:188-194): carry samples per selection
+  for (int ss = 0; ss < K && carry > 0; ss++) {
+    char* hbase = (char*)a->timf3_float.base + (size_t)ss * 2 * a->timf3_float.size * 4;
+    char* dbase = (char*)plan->m_timf3.d + (size_t)ss * 2 * a->timf3_float.size * 4;
+    if ((rc = ring_copy(plan, dbase, hbase, a->timf3_float.size * 4, (size_t)a->timf3_pa * 4, (size_t)carry * plan->mm * 4, true))) return rc;
+  }
+  if ((rc = launch_mix1(plan, a, (const float*)plan->m_fft1.d, (uint32_t)(a->fft1_float.size - 1), (float*)plan->m_timf3.d, jobs))) return rc;
+  for (int ss = 0; ss < K; ss++) {
+    char* hbase = (char*)a->timf3_float.base + (size_t)ss * 2 * a->timf3_float.size * 4;
+    char* dbase = (char*)plan->m_timf3.d + (size_t)ss * 2 * a->timf3_float.size * 4;
+    if ((rc = ring_copy(plan, dbase, hbase, a->timf3_float.size * 4, (size_t)a->timf3_pa * 4,
+                        ((size_t)Mn * a->nblocks + carry) * plan->mm * 4, false))) return rc;
+  }
+  LB_CUDA(cudaStreamSynchronize(plan->stream));
+  return LB200_OK;
+}

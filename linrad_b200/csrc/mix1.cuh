@@ -1,0 +1,221 @@
+// mix1.cuh -- first mixer: select M bins around mix1_point, taper, back-transform to the
+// decimated baseband and overlap into timf3.  Replaces, for a batch of transforms and any
+// number of selections,
+//   fft1_mix1_fixed   (mix1.c:995-1041: bin gather with the first/last point clamps)
+//   do_mix1           (mix1.c:55-272 one channel, 453-645 two channels): mix1_fqwin taper,
+//                     fftback (fft0.c:481-533; 2-ch dual_fftback fft0.c:341), phase rotation
+//                     and the three overlap schemes (none / sin^2 50 % / crossover windows)
+//   mix1_clear        (mix1.c:770-779)
+// set_mix1_phases (mix1.c:781-861) stays on the host (plan.cu builds one Mix1Job per
+// transform and selection, carrying the reference's float phase state bit-exactly).
+//
+// One CTA walks a *run* of consecutive transforms of one selection so that the raw tail of
+// transform b-1 (which the reference parks in timf3 and re-reads, mix1.c:178-194) stays in
+// shared memory; only the first transform of a run has to rebuild its predecessor.
+#pragma once
+#include "fft_core.cuh"
+#include "phase.h"
+
+namespace lb {
+
+struct Mix1Job {          // one (transform, selection)
+  uint32_t src;           // float index of the transform's block in fft1_float
+  uint32_t dst;           // timf3_pa for this transform (float index inside the selection's ring)
+  int point;              // mix1_point[ss]; <0: selection empty -> mix1_clear
+  float t1, t2;           // mix1_phase[ss] after set_mix1_phases, mix1_phase_rot[ss]
+  float r1, r2;           // mix1_old_phase[ss], r2 of mix1.c:167
+};
+
+struct Mix1K {
+  const float* fft1;      // fft1_float ring
+  uint32_t fft1_mask;     // floats
+  const Mix1Job* jobs;    // [nsel][nblocks]
+  int nblocks, nsel, runlen;
+  float* timf3;           // selection ss at timf3 + ss*sel_stride
+  size_t sel_stride;      // floats between selections (2*timf3_size)
+  uint32_t timf3_mask;    // floats
+  const float2* Wm;       // exp(-2 pi i m / M)
+  const float* fqwin;
+  const float* window;    // inverse window (crossover mode)
+  const float* cos2win;
+  const float* sin2win;
+  int first_point, last_point;
+  int Mi, Mn, cross;      // mix1.interleave_points, new_points, crossover_points
+  int mode;               // 0 none, 1 sin^2 (Mi==Mn), 2 crossover
+};
+
+// taper index of do_mix1 (mix1.c:113-135 / 455-491, including the doubled factors of the
+// two-channel loop at i==M-1 and i==M/2)
+template <int NCH>
+LB_D float mix1_taper(const float* fqwin, int i, int M)
+{
+  const int h = M / 2;
+  float w;
+  if (i == 0) w = fqwin[h - 1];
+  else if (i <= h) w = fqwin[h - i];
+  else w = fqwin[i - h];
+  if (NCH == 2) {
+    if (i == M - 1) w *= fqwin[h - 1];
+    if (i == h) w *= fqwin[0];
+  }
+  return w;
+}
+
+template <int LOG2M, int LOG2E, int NCH>
+__global__ void __launch_bounds__(NCH << (LOG2M - LOG2E))
+mix1_kernel(const Mix1K p)
+{
+  using P = Plan<LOG2M, LOG2E>;
+  constexpr int M = P::N, E = P::E, T = P::T, MM = 2 * NCH;
+  constexpr int NTHREADS = NCH * T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: xch[NCH][M+M/32+32] | ybuf[2][NCH][M] | ph_t[M] | ph_r[M]
+  float2* xch_all = reinterpret_cast<float2*>(smem_raw);
+  constexpr int XCH = M + M / 32 + 32;
+  float2* ybuf_all = xch_all + NCH * XCH;
+  float* ph_t = reinterpret_cast<float*>(ybuf_all + 2 * NCH * M);
+  float* ph_r = ph_t + M;
+
+  const int tid = threadIdx.x;
+  const int ch = tid / T;
+  const int t = tid - ch * T;
+  float2* xch = xch_all + ch * XCH;
+  Twiddles<P> tw;
+  load_twiddles<P>(tw, p.Wm, t);
+
+  const int runs_per_sel = (p.nblocks + p.runlen - 1) / p.runlen;
+  const int nruns = runs_per_sel * p.nsel;
+  const int carry_len = p.mode == 1 ? M / 2 : (p.mode == 2 ? p.cross : 0);
+  const int yoff = p.mode == 2 ? (p.Mi / 2 - p.cross / 2) : 0;
+  const int carry_src = p.mode == 1 ? M / 2 : p.Mn + yoff;
+  const int nt = p.Mn;                         // rotated samples per transform
+  const int nr = carry_len;
+
+  for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
+    const int ss = run / runs_per_sel;
+    const int bfirst = (run - ss * runs_per_sel) * p.runlen;
+    int blast = bfirst + p.runlen;
+    if (blast > p.nblocks) blast = p.nblocks;
+    const Mix1Job* jobs = p.jobs + (size_t)ss * p.nblocks;
+    float* t3 = p.timf3 + (size_t)ss * p.sel_stride;
+    int cur = 0;
+    // bstart = bfirst-1 rebuilds the predecessor's tail when this run does not start the call
+    const int bstart = (bfirst > 0 && carry_len > 0) ? bfirst - 1 : bfirst;
+    for (int b = bstart; b < blast; b++) {
+      const Mix1Job job = jobs[b];
+      const bool warm = (b < bfirst);          // predecessor: only its tail is wanted
+      float2* ybuf = ybuf_all + (cur * NCH + ch) * M;
+      __syncthreads();                         // previous iteration's readers are done
+      if (job.point >= 0) {
+        // ---- gather + taper (mix1.c:1015-1030, 113-135)
+        float2 v[E];
+        const float* src = p.fft1 + (job.src & p.fft1_mask);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const int i = t + T * e;
+          const int bin = (i < M / 2) ? job.point + i : job.point - M + i;
+          const bool ok = (i < M / 2) ? (bin < p.last_point) : (bin >= p.first_point);
+          float2 z = make_float2(0.f, 0.f);
+          if (ok) z = *reinterpret_cast<const float2*>(src + (size_t)bin * MM + 2 * ch);
+          const float w = mix1_taper<NCH>(p.fqwin, i, M);
+          v[e] = make_float2(z.x * w, z.y * w);
+        }
+        fft_forward<P>(v, xch, t, tw);         // fftback: sum_k y_k exp(-2 pi i n k / M)
+#pragma unroll
+        for (int e = 0; e < E; e++) ybuf[t + T * e] = v[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; e++) ybuf[t + T * e] = make_float2(0.f, 0.f);
+      }
+      // ---- exact float phase chains for this transform (mix1.c:143-153,164-186)
+      constexpr int NL = NTHREADS < 32 ? NTHREADS : 32;
+      if (!warm && job.point >= 0 && tid < NL) {
+        const int chunk_t = (nt + NL - 1) / NL;
+        int i0 = tid * chunk_t;
+        if (i0 < nt) {
+          float x = lb_phase_advance(job.t1, job.t2, i0);
+          int i1 = i0 + chunk_t; if (i1 > nt) i1 = nt;
+          for (int i = i0; i < i1; i++) { ph_t[i] = x; x = lb_float_add(x, job.t2); }
+        }
+        const int chunk_r = (nr + NL - 1) / NL;
+        i0 = tid * chunk_r;
+        if (chunk_r > 0 && i0 < nr) {
+          float x = lb_phase_advance(job.r1, job.r2, i0);
+          int i1 = i0 + chunk_r; if (i1 > nr) i1 = nr;
+          for (int i = i0; i < i1; i++) { ph_r[i] = x; x = lb_float_add(x, job.r2); }
+        }
+      }
+      __syncthreads();
+      if (!warm) {
+        const float2* yb = ybuf_all + (cur * NCH) * M;          // [NCH][M]
+        const float2* cb = ybuf_all + ((cur ^ 1) * NCH) * M;    // predecessor
+        const bool from_ring = (b == 0);      // first transform of the call: tail is in timf3
+        if (job.point < 0) {
+          // mix1_clear: zero timf3_block floats
+          for (int s = tid; s < p.Mn * MM; s += NTHREADS) t3[(job.dst + s) & p.timf3_mask] = 0.f;
+        } else {
+          for (int s = tid; s < nt; s += NTHREADS) {
+            float st, ct;
+            sincosf(ph_t[s], &st, &ct);
+            float sr = 0.f, cr = 1.f;
+            if (s < nr) sincosf(ph_r[s], &sr, &cr);
+            const uint32_t o = (job.dst + (uint32_t)s * MM) & p.timf3_mask;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+              const float2 y = yb[c * M + s + yoff];
+              float re = ct * y.x - st * y.y;
+              float im = ct * y.y + st * y.x;
+              if (p.mode == 1) {
+                float2 a;
+                if (from_ring) a = *reinterpret_cast<const float2*>(t3 + o + 2 * c);
+                else a = cb[c * M + carry_src + s];
+                re = cr * a.x - sr * a.y + re;           // mix1.c:180-181
+                im = cr * a.y + sr * a.x + im;
+              } else if (p.mode == 2) {
+                if (s < p.cross) {
+                  float2 a;
+                  if (from_ring) a = *reinterpret_cast<const float2*>(t3 + o + 2 * c);
+                  else a = cb[c * M + carry_src + s];
+                  const float w1 = p.sin2win[s], w2 = p.cos2win[s];
+                  a.x *= w2; a.y *= w2;
+                  re = cr * a.x - sr * a.y + re * w1;    // mix1.c:219-224
+                  im = cr * a.y + sr * a.x + im * w1;
+                } else {
+                  const int sb = p.Mn / 2 + 1 + p.cross / 2;
+                  const int j = (s < sb) ? (yoff + s) : (yoff + 2 * sb - 2 - s);
+                  const float w = p.window[j];
+                  re *= w; im *= w;                      // mix1.c:237-239,253-255
+                }
+              }
+              *reinterpret_cast<float2*>(t3 + o + 2 * c) = make_float2(re, im);
+            }
+          }
+        }
+        // the raw tail of the LAST transform of the call is parked in timf3 for the next call
+        if (b == p.nblocks - 1 && carry_len > 0) {
+          for (int s = tid; s < carry_len; s += NTHREADS) {
+            const uint32_t o = (job.dst + (uint32_t)(p.Mn + s) * MM) & p.timf3_mask;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+              float2 y = make_float2(0.f, 0.f);
+              if (job.point >= 0) y = yb[c * M + carry_src + s];
+              // after mix1_clear the reference leaves whatever the ring held; a cleared
+              // selection has no defined tail, zeros keep the next blend finite
+              *reinterpret_cast<float2*>(t3 + o + 2 * c) = y;
+            }
+          }
+        }
+      }
+      cur ^= 1;
+    }
+  }
+}
+
+template <int LOG2M, int NCH>
+constexpr size_t mix1_smem()
+{
+  return sizeof(float2) * (size_t)(NCH * ((1 << LOG2M) + (1 << LOG2M) / 32 + 32) + 2 * NCH * (1 << LOG2M)) +
+         sizeof(float) * 2 * (1 << LOG2M);
+}
+
+}  // namespace lb

@@ -1,0 +1,69 @@
+// plan.h -- internal plan object behind the opaque lb200_plan of include/linrad_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+#include <map>
+#include "../../include/linrad_b200.h"
+
+struct HostMirror {            // device mirror of one of Linrad's host rings
+  void* d = nullptr;
+  size_t bytes = 0;
+  const void* host = nullptr;
+  bool registered = false;
+};
+
+struct lb200_plan {
+  lb200_config cfg;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  // derived geometry
+  int N = 0;                   // fft1_size
+  int nch = 1;                 // rx_rf_channels
+  int mm = 2;                  // twice_rxchan
+  int frame = 4;               // bytes per input frame
+  int fmt = 0;                 // lb::InFmt
+  bool iq = true;
+  int fft1_block = 0;          // mm*N floats
+  int new_points = 0;          // P
+  uint32_t blockbytes = 0;     // timf1_blockbytes
+  int M = 0;                   // mix1.size
+  // device tables
+  float* d_window = nullptr;
+  float2* d_Wn = nullptr;      // fft1 twiddles, N entries
+  float* d_filtercorr = nullptr;
+  int fc_mode = 2;
+  float fc_gain = 0.f;
+  int fc_edge = 0;
+  float2* d_Wm = nullptr;      // mix1 twiddles, M entries
+  float* d_fqwin = nullptr;
+  float* d_mixwin = nullptr;
+  float* d_cos2win = nullptr;
+  float* d_sin2win = nullptr;
+  // large-N (four-step) scratch
+  float2* d_scratch = nullptr;
+  size_t scratch_elems = 0;
+  float2* d_Wbig = nullptr;    // exp(-2 pi i m / N) for the inter-pass twiddle, N entries
+  // mix1 per-call staging
+  void* d_mixjobs = nullptr;
+  size_t mixjobs_bytes = 0;
+  void* h_mixjobs = nullptr;   // pinned
+  // host-pointer API mirrors
+  HostMirror m_timf1, m_fft1, m_sumsq, m_timf3, m_power;
+  std::map<const void*, size_t> registered;
+  // counters
+  uint64_t launches = 0, h2d = 0, d2h = 0;
+  int last_cuda_error = 0;
+};
+
+#define LB_CUDA(call)                                                 \
+  do {                                                                \
+    cudaError_t e_ = (call);                                          \
+    if (e_ != cudaSuccess) {                                          \
+      plan->last_cuda_error = (int)e_;                                \
+      fprintf(stderr, "[lb200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return LB200_ERR_CUDA;                                          \
+    }                                                                 \
+  } while (0)
