@@ -112,37 +112,52 @@ struct DftS<1, S> {
 // j = t + T*q; it consumes v[q + r*(E/R)], r = 0..R-1 (== data[j + r*N/R]) and its r-th
 // output belongs at index (j-k)*R + k + r*Ns with k = j mod Ns.
 //
-// Twiddles: input r is multiplied by w1^r, w1 = exp(-2*pi*i*k/(Ns*R)).  Only w1 is fetched
-// (tw1[q], hoisted by the caller); the powers are built with four interleaved chains
-// w[r] = w[r-4]*w[4] to keep both latency and live registers low.
+// Twiddles: input r is multiplied by w^r, w = exp(-2*pi*i*k/(Ns*R)).  Raising one rounded w
+// to the r-th power multiplies its angle error by r (measured: 4e-7 relative rms on the whole
+// transform instead of 1.4e-7), so the binary powers w^1, w^2, w^4, ... are each fetched
+// correctly rounded from the table (wb[b] = w^(2^b)) and w^r is assembled from at most
+// log2(R) of them with a two-level split r = hi*2^LB + lo that keeps few twiddles live.
+template <int R>
+struct Log2 { static constexpr int value = 1 + Log2<R / 2>::value; };
+template <>
+struct Log2<1> { static constexpr int value = 0; };
+
 template <int E, int R, int T>
-LB_HD void pass_butterflies(float2 (&v)[E], const float2* tw1, bool twiddled)
+LB_HD void pass_butterflies(float2 (&v)[E], const float2* wb, bool twiddled)
 {
   constexpr int Q = E / R;
+  constexpr int LR = Log2<R>::value;
+  constexpr int LB = LR / 2;               // low bits
+  constexpr int NLO = 1 << LB, NHI = R >> LB;
 #pragma unroll
   for (int q = 0; q < Q; q++) {
     float2 x[R];
 #pragma unroll
     for (int r = 0; r < R; r++) x[r] = v[q + r * Q];
-    if (twiddled) {
-      const float2 w1 = tw1[q];
-      if (R >= 2) x[1] = cmul(x[1], w1);
-      if (R > 2) {
-        float2 w[R > 4 ? R : 5];
-        w[1] = w1;
-        w[2] = cmul(w1, w1);
-        w[3] = cmul(w[2], w1);
-        x[2] = cmul(x[2], w[2]);
-        x[3] = cmul(x[3], w[3]);
-        if (R > 4) {
-          w[4] = cmul(w[2], w[2]);
-          x[4] = cmul(x[4], w[4]);
+    if (twiddled && R > 1) {
+      const float2* w2 = wb + q * (LR > 0 ? LR : 1);
+      float2 lo[NLO > 1 ? NLO : 2], hi[NHI > 1 ? NHI : 2];
+      // lo[i] = w^i (i < 2^LB), hi[j] = w^(j*2^LB): binary products of the exact powers
 #pragma unroll
-          for (int r = 5; r < R; r++) {
-            w[r] = cmul(w[r - 4], w[4]);
-            x[r] = cmul(x[r], w[r]);
-          }
-        }
+      for (int i = 1; i < NLO; i++) {
+        const int hb = 31 - __builtin_clz(i);            // highest set bit
+        if ((i & (i - 1)) == 0) lo[i] = w2[hb];
+        else lo[i] = cmul(w2[hb], lo[i - (1 << hb)]);
+      }
+#pragma unroll
+      for (int j = 1; j < NHI; j++) {
+        const int hb = 31 - __builtin_clz(j);
+        if ((j & (j - 1)) == 0) hi[j] = w2[LB + hb];
+        else hi[j] = cmul(w2[LB + hb], hi[j - (1 << hb)]);
+      }
+#pragma unroll
+      for (int r = 1; r < R; r++) {
+        const int l = r & (NLO - 1), h = r >> LB;
+        float2 w;
+        if (h == 0) w = lo[l];
+        else if (l == 0) w = hi[h];
+        else w = cmul(hi[h], lo[l]);
+        x[r] = cmul(x[r], w);
       }
     }
     DftS<R, 1>::run(x);
@@ -151,15 +166,15 @@ LB_HD void pass_butterflies(float2 (&v)[E], const float2* tw1, bool twiddled)
   }
 }
 
-// index of the twiddle base w1 for butterfly q of thread t inside a table
-// W[m] = exp(-2*pi*i*m/N): m = k * N/(Ns*R)
+// index of w^(2^b) for butterfly q of thread t inside the table W[m] = exp(-2*pi*i*m/N):
+// m = 2^b * k * N/(Ns*R)   (always < N because 2^b <= R/2 and k < Ns)
 template <int E, int R, int T>
-LB_HD int tw1_index(int t, int q, int Ns)
+LB_HD int tw_index(int t, int q, int Ns, int b)
 {
   constexpr int N = E * T;
   const int j = t + T * q;
   const int k = j & (Ns - 1);
-  return k * (N / (Ns * R));
+  return (k * (N / (Ns * R))) << b;
 }
 
 // shared-memory slot for logical index i; one pad slot every 32 keeps the strided scatter of
@@ -207,20 +222,23 @@ struct Plan {
   static constexpr int NTW = NPASS - 1;                     // twiddled passes (each has Q = 1 ... or E/R)
 };
 
-// Per-thread hoisted twiddle bases: tw[p-1][q] for pass p >= 1 (all later passes have R == E,
-// hence exactly one butterfly per thread).
+// Per-thread twiddle bases: for every pass p >= 1 (all of radix E, one butterfly per thread)
+// the LOG2E exact binary powers of its w.
 template <class P>
 struct Twiddles {
-  float2 w[P::NTW > 0 ? P::NTW : 1];
+  static constexpr int LE = Log2<P::E>::value;
+  float2 w[(P::NTW > 0 ? P::NTW : 1) * (LE > 0 ? LE : 1)];
 };
 
 template <class P>
 LB_D void load_twiddles(Twiddles<P>& tw, const float2* __restrict__ Wn, int t)
 {
+  constexpr int LE = Twiddles<P>::LE;
 #pragma unroll
   for (int p = 1; p < P::NPASS; p++) {
     const int Ns = P::ns(p);
-    tw.w[p - 1] = Wn[tw1_index<P::E, P::E, P::T>(t, 0, Ns)];
+#pragma unroll
+    for (int b = 0; b < LE; b++) tw.w[(p - 1) * LE + b] = Wn[tw_index<P::E, P::E, P::T>(t, 0, Ns, b)];
   }
 }
 
@@ -242,7 +260,7 @@ LB_D void fft_forward(float2 (&v)[P::E], float2* sm, int t, const Twiddles<P>& t
     __syncthreads();
     exchange_load<E, T, 5>(v, sm, t);
     __syncthreads();
-    pass_butterflies<E, E, T>(v, &tw.w[p - 1], true);
+    pass_butterflies<E, E, T>(v, &tw.w[(p - 1) * Twiddles<P>::LE], true);
   }
 }
 #endif

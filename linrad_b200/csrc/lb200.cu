@@ -154,9 +154,13 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   if (plan->stream) cudaStreamSynchronize(plan->stream);
   for (auto& kv : plan->registered) cudaHostUnregister(const_cast<void*>(kv.first));
   void* ptrs[] = {plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
-                  plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wbig, plan->d_mixjobs};
+                  plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wbig};
   for (void* p : ptrs) if (p) cudaFree(p);
-  if (plan->h_mixjobs) cudaFreeHost(plan->h_mixjobs);
+  for (int i = 0; i < lb200_plan::kJobSlots; i++) {
+    if (plan->d_mixjobs[i]) cudaFree(plan->d_mixjobs[i]);
+    if (plan->h_mixjobs[i]) cudaFreeHost(plan->h_mixjobs[i]);
+    if (plan->mixjobs_done[i]) cudaEventDestroy(plan->mixjobs_done[i]);
+  }
   free_mirror(plan->m_timf1); free_mirror(plan->m_fft1); free_mirror(plan->m_sumsq);
   free_mirror(plan->m_timf3); free_mirror(plan->m_power);
   if (plan->stream) cudaStreamDestroy(plan->stream);
@@ -377,23 +381,25 @@ static int launch_mix1(lb200_plan* plan, const lb200_mix1_args* a, const float* 
 {
   const int K = a->no_of_channels, B = a->nblocks;
   const size_t bytes = sizeof(Mix1Job) * jobs.size();
-  if (plan->mixjobs_bytes < bytes) {
-    if (plan->d_mixjobs) cudaFree(plan->d_mixjobs);
-    if (plan->h_mixjobs) cudaFreeHost(plan->h_mixjobs);
-    plan->d_mixjobs = nullptr; plan->h_mixjobs = nullptr;
-    LB_CUDA(cudaMalloc(&plan->d_mixjobs, bytes));
-    LB_CUDA(cudaMallocHost(&plan->h_mixjobs, bytes));
-    plan->mixjobs_bytes = bytes;
+  const int slot = plan->mixjobs_next;
+  plan->mixjobs_next = (slot + 1) % lb200_plan::kJobSlots;
+  if (!plan->mixjobs_done[slot]) LB_CUDA(cudaEventCreateWithFlags(&plan->mixjobs_done[slot], cudaEventDisableTiming));
+  else LB_CUDA(cudaEventSynchronize(plan->mixjobs_done[slot]));   // the launch that used this slot has finished
+  if (plan->mixjobs_bytes[slot] < bytes) {
+    if (plan->d_mixjobs[slot]) cudaFree(plan->d_mixjobs[slot]);
+    if (plan->h_mixjobs[slot]) cudaFreeHost(plan->h_mixjobs[slot]);
+    plan->d_mixjobs[slot] = nullptr; plan->h_mixjobs[slot] = nullptr;
+    LB_CUDA(cudaMalloc(&plan->d_mixjobs[slot], bytes));
+    LB_CUDA(cudaMallocHost(&plan->h_mixjobs[slot], bytes));
+    plan->mixjobs_bytes[slot] = bytes;
   }
-  // the pinned staging buffer may still feed the previous call's copy
-  LB_CUDA(cudaStreamSynchronize(plan->stream));
-  memcpy(plan->h_mixjobs, jobs.data(), bytes);
-  LB_CUDA(cudaMemcpyAsync(plan->d_mixjobs, plan->h_mixjobs, bytes, cudaMemcpyHostToDevice, plan->stream));
+  memcpy(plan->h_mixjobs[slot], jobs.data(), bytes);
+  LB_CUDA(cudaMemcpyAsync(plan->d_mixjobs[slot], plan->h_mixjobs[slot], bytes, cudaMemcpyHostToDevice, plan->stream));
   Mix1K k;
   memset(&k, 0, sizeof(k));
   k.fft1 = d_fft1;
   k.fft1_mask = fft1_mask;
-  k.jobs = (const Mix1Job*)plan->d_mixjobs;
+  k.jobs = (const Mix1Job*)plan->d_mixjobs[slot];
   k.nblocks = B;
   k.nsel = K;
   k.timf3 = d_timf3;
@@ -426,6 +432,7 @@ static int launch_mix1(lb200_plan* plan, const lb200_mix1_args* a, const float* 
   const int cap = plan->sm_count * 16;
   if (grid > cap) grid = cap;
   LB_CUDA(fn(k, grid, plan->stream));
+  LB_CUDA(cudaEventRecord(plan->mixjobs_done[slot], plan->stream));
   plan->launches++;
   return LB200_OK;
 }

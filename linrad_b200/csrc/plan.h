@@ -46,10 +46,14 @@ struct lb200_plan {
   float2* d_scratch = nullptr;
   size_t scratch_elems = 0;
   float2* d_Wbig = nullptr;    // exp(-2 pi i m / N) for the inter-pass twiddle, N entries
-  // mix1 per-call staging
-  void* d_mixjobs = nullptr;
-  size_t mixjobs_bytes = 0;
-  void* h_mixjobs = nullptr;   // pinned
+  // mix1 per-call staging: a small ring of pinned/device job tables so that consecutive
+  // calls never wait for each other on the host
+  static constexpr int kJobSlots = 4;
+  void* d_mixjobs[kJobSlots] = {nullptr, nullptr, nullptr, nullptr};
+  void* h_mixjobs[kJobSlots] = {nullptr, nullptr, nullptr, nullptr};   // pinned
+  size_t mixjobs_bytes[kJobSlots] = {0, 0, 0, 0};
+  cudaEvent_t mixjobs_done[kJobSlots] = {nullptr, nullptr, nullptr, nullptr};
+  int mixjobs_next = 0;
   // host-pointer API mirrors
   HostMirror m_timf1, m_fft1, m_sumsq, m_timf3, m_power;
   std::map<const void*, size_t> registered;

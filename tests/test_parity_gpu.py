@@ -13,8 +13,13 @@ from tests.helpers import CONFIGS, CudaStream, rel_rms, run_reference, IQ_DATA, 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refwrap.available(), reason="oracle/_ref not built")]
 
 TOL_FFT1 = 1e-5
-TOL_POWER = 1e-4
+TOL_POWER = 1e-4      # per bin, for every bin within 50 dB of the strongest bin of the row
 TOL_TIMF3 = 2e-5
+# Bins far below the strongest signal carry the float32 rounding noise of the transform itself:
+# the reference's own two C implementations (fft_cntrl rows 6 and 7) differ there by up to 3e-4
+# per bin on the cfg1 signal (77 dB of dynamic range).  For those bins the CUDA result must stay
+# within POWER_SPREAD_FACTOR times the reference-vs-reference spread measured on the same input.
+POWER_SPREAD_FACTOR = 3.0
 
 
 def _setup(kw, **over):
@@ -29,6 +34,11 @@ def _compare(kw, nblocks, selbins, chunk, seed=1, natural_window=True, **over):
     kwr = dict(kw)
     kwr.update(over)
     ref = run_reference(kwr, raw, selbins, nblocks, want_raw=True)
+    alt_sumsq = None
+    if kwr["version"] in (6, 7):
+        kwa = dict(kwr, version=13 - kwr["version"])          # 6 <-> 7
+        alt_sumsq = run_reference(kwa, raw, [], nblocks)["sumsq"]
+        ref = run_reference(kwr, raw, selbins, nblocks, want_raw=True)   # the oracle keeps one state
     cs = CudaStream(s, selbins)
     try:
         got = cs.process(raw, nblocks, chunk=chunk)
@@ -43,7 +53,14 @@ def _compare(kw, nblocks, selbins, chunk, seed=1, natural_window=True, **over):
             a = cs.sumsq[r * N + lo: r * N + hi + 1]
             b = ref["sumsq"][r * N + lo: r * N + hi + 1]
             err = np.abs(a - b) / np.maximum(np.abs(b), 1e-30)
-            assert err.max() <= TOL_POWER, f"sumsq row {r} max rel err {err.max()}"
+            strong = b >= 1e-5 * b.max()
+            assert err[strong].max() <= TOL_POWER, f"sumsq row {r} strong-bin max rel err {err[strong].max()}"
+            limit = TOL_POWER
+            if alt_sumsq is not None:
+                c = alt_sumsq[r * N + lo: r * N + hi + 1]
+                spread = (np.abs(c - b) / np.maximum(np.abs(b), 1e-30)).max()
+                limit = max(TOL_POWER, POWER_SPREAD_FACTOR * spread)
+            assert err.max() <= limit, f"sumsq row {r} max rel err {err.max()} limit {limit}"
         # mix1
         for ss in range(len(selbins)):
             st = ref["states"][ss]
