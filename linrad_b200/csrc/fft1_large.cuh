@@ -1,3 +1,194 @@
-// fft1_large.cuh -- multi-pass (four-step) fft1 for N >= 2^15; see kernels_large.cu
+// fft1_large.cuh -- fft1 for transforms that do not fit one CTA (2^15 <= N <= 2^20): the
+// four-step decomposition N = N1*N2 in two kernels with the intermediate kept in a scratch
+// buffer that is sized to stay resident in the 126 MB L2.
+//
+//   step A (columns): for each n2, FFT over n1 of x[n1*N2+n2] (ring gather, int->float, window
+//                     fused), times the inter-step twiddle W_N^(n2*k1)  ->  Y[k1][n2]
+//   step B (rows):    for each k1, FFT over n2 of Y[k1][.]  ->  X[k1 + N1*k2], then the same
+//                     epilogue as the single-CTA kernel (direction, filtercorr, |z|^2, sumsq)
+//
+// This replaces what the reference can only do through its double precision path (fft1
+// version 20: d_fft1win_dif_chan fft1.c:2145, d_bulk_of_dif fft0.c:197, dif_bigpermute_chan
+// fft1.c:668) or through cuFFT/clFFT (versions 18/19, fft1.c:3519-3553): the float CPU
+// versions stop at 65536 points (buf.c:285-290).
+//
+// Step A runs TA adjacent columns side by side with the column index fastest across lanes, so
+// the strided gather from timf1 and the store to Y are both made of TA-element contiguous runs.
+// Step B transposes its finished tile through shared memory so that bins k1..k1+TB-1 of one k2
+// leave the SM as one contiguous run.
 #pragma once
 #include "fft1_small.cuh"
+
+namespace lb {
+
+struct Fft1LargeK {
+  Fft1K k;               // same parameter block as the single-CTA kernel
+  float2* scratch;       // Y: [slot][channel][N]
+  const float2* Wn1;     // exp(-2 pi i m / N1)
+  const float2* Wn2;     // exp(-2 pi i m / N2)
+  const float2* Wbig;    // exp(-2 pi i m / N)
+  int b_first;           // first transform of this sub-batch (index into the call's batch)
+  int b_count;           // transforms in this sub-batch
+  int g_first;           // first averaging group covered by this sub-batch
+  int g_count;
+};
+
+// ------------------------------------------------------------------------------ step A
+template <int LOG2N1, int LOG2N2, int LOG2E, int LOG2TA, int FMT>
+__global__ void __launch_bounds__(1 << (LOG2N1 - LOG2E + LOG2TA))
+fft1_large_cols_kernel(const Fft1LargeK q)
+{
+  using P = Plan<LOG2N1, LOG2E>;
+  constexpr int N1 = 1 << LOG2N1, N2 = 1 << LOG2N2, E = P::E, T = P::T, TA = 1 << LOG2TA;
+  constexpr int FRAME = FmtInfo<FMT>::FRAME, NCH = FmtInfo<FMT>::NCH;
+  constexpr int N = N1 * N2;
+  constexpr int TILES = N2 / TA;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* xch = reinterpret_cast<float2*>(smem_raw);
+  const Fft1K& p = q.k;
+  const int col = threadIdx.x & (TA - 1);
+  const int t = threadIdx.x >> LOG2TA;
+
+  Twiddles<P> tw;
+  load_twiddles<P>(tw, q.Wn1, t);
+
+  const int nwork = q.b_count * NCH * TILES;
+  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int tile = w % TILES;
+    const int c = (w / TILES) % NCH;
+    const int slot = w / (TILES * NCH);
+    const int b = q.b_first + slot;
+    const int n2 = tile * TA + col;
+    // inter-step twiddle W_N^(n2*(t+T*e)) = base * step^e, step given by exact binary powers
+    const float2 base = q.Wbig[n2 * t];
+    float2 sb[LOG2E];
+#pragma unroll
+    for (int j = 0; j < LOG2E; j++) sb[j] = q.Wbig[(n2 * T) << j];
+    const float sgn = (n2 & 1) ? -1.0f : 1.0f;
+    const float qs = p.direction < 0 ? -sgn : sgn;
+    const uint32_t start = p.ref0 + (uint32_t)b * p.blockbytes - p.pre_bytes;
+    float2 v[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const int n = (t + T * e) * N2 + n2;
+      const uint32_t off = (start + (uint32_t)n * FRAME) & p.ring_mask;
+      const float2 s = load_iq<FMT>(p.timf1, off, c);
+      const float wv = p.window ? p.window[n] : 1.0f;
+      v[e] = make_float2(s.x * (wv * sgn), s.y * (wv * qs));
+    }
+    __syncthreads();                       // previous work item's exchange reads are done
+    fft_forward<P, TA>(v, xch + col, t, tw);
+    apply_power_twiddles<E>(v, base, sb);
+    float2* Y = q.scratch + ((size_t)slot * NCH + c) * N;
+#pragma unroll
+    for (int e = 0; e < E; e++) Y[(size_t)(t + T * e) * N2 + n2] = v[e];
+  }
+}
+
+// ------------------------------------------------------------------------------ step B
+template <int LOG2N1, int LOG2N2, int LOG2E, int LOG2TB, int NCH>
+__global__ void __launch_bounds__(1 << (LOG2N2 - LOG2E + LOG2TB))
+fft1_large_rows_kernel(const Fft1LargeK q)
+{
+  using P = Plan<LOG2N2, LOG2E>;
+  constexpr int N1 = 1 << LOG2N1, N2 = 1 << LOG2N2, E = P::E, T = P::T, TB = 1 << LOG2TB;
+  constexpr int N = N1 * N2, MM = 2 * NCH;
+  constexpr int TILES = N1 / TB;
+  constexpr int NTHREADS = TB * T;
+  constexpr int XCH = N2 + N2 / 32 + 32;          // per-row exchange slice
+  constexpr int TILE_PTS = TB * N2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* xch_all = reinterpret_cast<float2*>(smem_raw);      // TB rows; reused as the transpose tile
+  float* acc = reinterpret_cast<float*>(smem_raw + sizeof(float2) * (size_t)TB * XCH);
+  const Fft1K& p = q.k;
+  const int t = threadIdx.x & (T - 1);
+  const int row = threadIdx.x / T;
+  float2* xch = xch_all + row * XCH;
+
+  Twiddles<P> tw;
+  load_twiddles<P>(tw, q.Wn2, t);
+
+  const int group_size = p.power_rows ? 1 : p.avg1num;
+  const int c0 = p.power_rows ? 0 : p.counter0;
+  const int nwork = q.g_count * TILES;
+  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int tile = w % TILES;
+    const int g = q.g_first + w / TILES;
+    int b0 = g * group_size - c0;
+    int b1 = b0 + group_size;
+    if (b0 < 0) b0 = 0;
+    if (b1 > p.nblocks) b1 = p.nblocks;
+    const int k1 = tile * TB + row;
+    for (int b = b0; b < b1; b++) {
+      const int slot = b - q.b_first;
+      float* outb = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c++) {
+        const float2* Y = q.scratch + ((size_t)slot * NCH + c) * N + (size_t)k1 * N2;
+        float2 v[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) v[e] = Y[t + T * e];
+        __syncthreads();                   // the transpose tile of the previous pass is consumed
+        fft_forward<P>(v, xch, t, tw);
+        __syncthreads();
+        // transpose: tile[k2][row]
+#pragma unroll
+        for (int e = 0; e < E; e++) xch_all[(t + T * e) * TB + row] = v[e];
+        __syncthreads();
+        for (int o = threadIdx.x; o < TILE_PTS; o += NTHREADS) {
+          const int r = o & (TB - 1), k2 = o >> LOG2TB;
+          const int k = tile * TB + r + N1 * k2;
+          const float2 z = xch_all[o];
+          float2 ov = p.direction < 0 ? make_float2(z.y, z.x) : make_float2(z.x, -z.y);
+          const bool inr = (k >= p.first_point) && (k <= p.last_point);
+          if (p.fc_mode != 0 && inr) {
+            float2 f;
+            if (p.fc_mode == 2 || k < p.fc_edge || k >= N - p.fc_edge)
+              f = *reinterpret_cast<const float2*>(p.filtercorr + (size_t)k * MM + 2 * c);
+            else
+              f = make_float2(p.fc_gain, 0.0f);
+            const float re = ov.x * f.x - ov.y * f.y;
+            const float im = ov.y * f.x + ov.x * f.y;
+            ov = make_float2(re, im);
+            const float pw = re * re + im * im;
+            if (b == b0 && c == 0) acc[o] = pw;
+            else acc[o] += pw;
+          }
+          *reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c) = ov;
+        }
+      }
+      if (p.power_rows && p.fc_mode != 0) {
+        for (int o = threadIdx.x; o < TILE_PTS; o += NTHREADS) {
+          const int r = o & (TB - 1), k2 = o >> LOG2TB;
+          const int k = tile * TB + r + N1 * k2;
+          const bool inr = (k >= p.first_point) && (k <= p.last_point);
+          p.power_rows[(size_t)b * N + k] = inr ? acc[o] : 0.0f;
+        }
+      }
+    }
+    if (p.sumsq && !p.power_rows && p.fc_mode != 0 && b1 > b0) {
+      float* rowp = p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask);
+      const bool continuing = (g == 0 && p.counter0 > 0);
+      for (int o = threadIdx.x; o < TILE_PTS; o += NTHREADS) {
+        const int r = o & (TB - 1), k2 = o >> LOG2TB;
+        const int k = tile * TB + r + N1 * k2;
+        if (k >= p.first_point && k <= p.last_point) {
+          float val = acc[o];
+          if (continuing) val = rowp[k] + val;
+          rowp[k] = val;
+        }
+      }
+    }
+  }
+}
+
+template <int LOG2N1, int LOG2TA>
+constexpr size_t fft1_large_cols_smem() { return sizeof(float2) * ((size_t)1 << (LOG2N1 + LOG2TA)); }
+template <int LOG2N2, int LOG2TB>
+constexpr size_t fft1_large_rows_smem()
+{
+  return sizeof(float2) * ((size_t)(1 << LOG2TB) * ((1 << LOG2N2) + (1 << LOG2N2) / 32 + 32)) +
+         sizeof(float) * ((size_t)1 << (LOG2N2 + LOG2TB));
+}
+
+}  // namespace lb

@@ -182,7 +182,7 @@ LB_HD int tw_index(int t, int q, int Ns, int b)
 template <int LOG2PAD>
 LB_HD int padded(int i) { return LOG2PAD > 0 ? i + (i >> LOG2PAD) : i; }
 
-template <int E, int R, int T, int LOG2PAD>
+template <int E, int R, int T, int LOG2PAD, int STRIDE = 1>
 LB_HD void exchange_store(const float2 (&v)[E], float2* sm, int t, int Ns)
 {
   constexpr int Q = E / R;
@@ -192,15 +192,44 @@ LB_HD void exchange_store(const float2 (&v)[E], float2* sm, int t, int Ns)
     const int k = j & (Ns - 1);
     const int base = (j - k) * R + k;
 #pragma unroll
-    for (int r = 0; r < R; r++) sm[padded<LOG2PAD>(base + r * Ns)] = v[q + r * Q];
+    for (int r = 0; r < R; r++) sm[padded<LOG2PAD>(base + r * Ns) * STRIDE] = v[q + r * Q];
   }
 }
 
-template <int E, int T, int LOG2PAD>
+template <int E, int T, int LOG2PAD, int STRIDE = 1>
 LB_HD void exchange_load(float2 (&v)[E], const float2* sm, int t)
 {
 #pragma unroll
-  for (int e = 0; e < E; e++) v[e] = sm[padded<LOG2PAD>(t + T * e)];
+  for (int e = 0; e < E; e++) v[e] = sm[padded<LOG2PAD>(t + T * e) * STRIDE];
+}
+
+// v[e] *= b * s^e, e = 0..E-1, with s given by its exact binary powers sb[j] = s^(2^j)
+// (the inter-step twiddle of the four-step transform, same accuracy argument as above)
+template <int E>
+LB_HD void apply_power_twiddles(float2 (&v)[E], float2 b, const float2* sb)
+{
+  constexpr int LE = Log2<E>::value;
+  constexpr int LB = LE / 2;
+  constexpr int NLO = 1 << LB, NHI = E >> LB;
+  float2 lo[NLO > 1 ? NLO : 2], hi[NHI > 1 ? NHI : 2];
+  lo[0] = b;
+#pragma unroll
+  for (int i = 1; i < NLO; i++) {
+    const int hb = 31 - __builtin_clz(i);
+    lo[i] = cmul(sb[hb], lo[i - (1 << hb)]);
+  }
+#pragma unroll
+  for (int j = 1; j < NHI; j++) {
+    const int hb = 31 - __builtin_clz(j);
+    if ((j & (j - 1)) == 0) hi[j] = sb[LB + hb];
+    else hi[j] = cmul(sb[LB + hb], hi[j - (1 << hb)]);
+  }
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    const int l = e & (NLO - 1), h = e >> LB;
+    const float2 w = (h == 0) ? lo[l] : cmul(hi[h], lo[l]);
+    v[e] = cmul(v[e], w);
+  }
 }
 
 // ---------------------------------------------------------------- radix plans
@@ -244,21 +273,23 @@ LB_D void load_twiddles(Twiddles<P>& tw, const float2* __restrict__ Wn, int t)
 
 #ifdef __CUDACC__
 // The whole transform.  On entry v[e] = x[t + T*e]; on exit v[e] = X[t + T*e].
-// `sm` must hold N + N/32 float2; every thread of the CTA must call this (it contains
+// `sm` must hold N + N/32 float2 (STRIDE==1) or N*STRIDE float2 with `sm` already offset by the
+// batch lane (STRIDE>1: STRIDE transforms interleaved element by element); every thread of the CTA must call this (it contains
 // __syncthreads), but several independent transforms may run side by side in one CTA as
 // long as each gets its own `sm` slice and its own t in [0,T).
-template <class P>
+template <class P, int STRIDE = 1>
 LB_D void fft_forward(float2 (&v)[P::E], float2* sm, int t, const Twiddles<P>& tw)
 {
   constexpr int E = P::E, T = P::T;
+  constexpr int LP = STRIDE == 1 ? 5 : 0;     // interleaved batches need no padding
   pass_butterflies<E, P::R0, T>(v, nullptr, false);
 #pragma unroll
   for (int p = 1; p < P::NPASS; p++) {
     const int NsPrev = P::ns(p - 1);
-    if (p == 1) exchange_store<E, P::R0, T, 5>(v, sm, t, NsPrev);
-    else exchange_store<E, E, T, 5>(v, sm, t, NsPrev);
+    if (p == 1) exchange_store<E, P::R0, T, LP, STRIDE>(v, sm, t, NsPrev);
+    else exchange_store<E, E, T, LP, STRIDE>(v, sm, t, NsPrev);
     __syncthreads();
-    exchange_load<E, T, 5>(v, sm, t);
+    exchange_load<E, T, LP, STRIDE>(v, sm, t);
     __syncthreads();
     pass_butterflies<E, E, T>(v, &tw.w[(p - 1) * Twiddles<P>::LE], true);
   }

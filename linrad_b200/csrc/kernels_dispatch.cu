@@ -20,5 +20,79 @@ fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* thre
   return nullptr;
 }
 
-bool lb_fft1_large_supported(int) { return false; }
-cudaError_t lb_launch_fft1_large(lb200_plan*, const Fft1K&) { return cudaErrorNotSupported; }
+
+// ---------------------------------------------------------------------------------------------
+// four-step path: sub-batches of whole averaging groups, sized so that the intermediate Y stays
+// in L2 between step A and step B
+#include "fft1_large.cuh"
+#include <cstdlib>
+cudaError_t lb_large_launch_fmt0(int, int, const Fft1LargeK&, int, cudaStream_t);
+cudaError_t lb_large_launch_fmt1(int, int, const Fft1LargeK&, int, cudaStream_t);
+cudaError_t lb_large_launch_fmt2(int, int, const Fft1LargeK&, int, cudaStream_t);
+cudaError_t lb_large_launch_fmt3(int, int, const Fft1LargeK&, int, cudaStream_t);
+
+bool lb_fft1_large_supported(int log2n) { return log2n >= 15 && log2n <= 20; }
+
+static void large_split(int log2n, int* ln1, int* ln2)
+{
+  *ln1 = (log2n + 1) / 2;
+  if (log2n == 15) *ln1 = 8;
+  *ln2 = log2n - *ln1;
+}
+
+cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k)
+{
+  const int log2n = plan->cfg.fft1_n;
+  int ln1, ln2;
+  large_split(log2n, &ln1, &ln2);
+  const size_t N = (size_t)1 << log2n;
+  const int nch = plan->nch;
+  const int group = k.power_rows ? 1 : k.avg1num;
+  const int c0 = k.power_rows ? 0 : k.counter0;
+  const int ngroups = (c0 + k.nblocks + group - 1) / group;
+  const char* env = getenv("LB200_SCRATCH_MB");
+  const size_t budget = (size_t)(env ? atoi(env) : 48) << 20;
+  size_t per_group = (size_t)group * nch * N * sizeof(float2);
+  int gps = (int)(budget / per_group);
+  if (gps < 1) gps = 1;
+  const size_t need = (size_t)gps * group * nch * N;
+  if (plan->scratch_elems < need) {
+    if (plan->d_scratch) cudaFree(plan->d_scratch);
+    plan->d_scratch = nullptr;
+    plan->scratch_elems = 0;
+    cudaError_t e = cudaMalloc((void**)&plan->d_scratch, need * sizeof(float2));
+    if (e != cudaSuccess) return e;
+    plan->scratch_elems = need;
+  }
+  Fft1LargeK q;
+  q.k = k;
+  q.scratch = plan->d_scratch;
+  q.Wn1 = plan->d_Wn1;
+  q.Wn2 = plan->d_Wn2;
+  q.Wbig = plan->d_Wn;
+  typedef cudaError_t (*fn_t)(int, int, const Fft1LargeK&, int, cudaStream_t);
+  fn_t fn = plan->fmt == 0 ? lb_large_launch_fmt0 : plan->fmt == 1 ? lb_large_launch_fmt1 : plan->fmt == 2 ? lb_large_launch_fmt2 : lb_large_launch_fmt3;
+  const int tilesA = (1 << ln2) / 16, tilesB = (1 << ln1) / 16;
+  for (int g0 = 0; g0 < ngroups; g0 += gps) {
+    const int g1 = g0 + gps < ngroups ? g0 + gps : ngroups;
+    int b_first = g0 * group - c0;
+    int b_last = g1 * group - c0;
+    if (b_first < 0) b_first = 0;
+    if (b_last > k.nblocks) b_last = k.nblocks;
+    q.b_first = b_first;
+    q.b_count = b_last - b_first;
+    q.g_first = g0;
+    q.g_count = g1 - g0;
+    int gridA = q.b_count * nch * tilesA;
+    int gridB = q.g_count * tilesB;
+    const int cap = plan->sm_count * 8;
+    if (gridA > cap) gridA = cap;
+    if (gridB > cap) gridB = cap;
+    cudaError_t e = fn(log2n, 0, q, gridA, plan->stream);
+    if (e != cudaSuccess) return e;
+    e = fn(log2n, 1, q, gridB, plan->stream);
+    if (e != cudaSuccess) return e;
+    plan->launches += 2;
+  }
+  return cudaSuccess;
+}

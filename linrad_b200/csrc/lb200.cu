@@ -97,6 +97,17 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
     make_twiddles(w, plan->N);
     if ((rc = upload(plan, (void**)&plan->d_Wn, w.data(), sizeof(float2) * w.size()))) return fail(rc);
   }
+  if (cfg->fft1_n > 14) {
+    // four-step split N = N1*N2 (kernels_dispatch.cu: large_split)
+    int ln1 = (cfg->fft1_n + 1) / 2;
+    if (cfg->fft1_n == 15) ln1 = 8;
+    const int ln2 = cfg->fft1_n - ln1;
+    std::vector<float2> w;
+    make_twiddles(w, 1 << ln1);
+    if ((rc = upload(plan, (void**)&plan->d_Wn1, w.data(), sizeof(float2) * w.size()))) return fail(rc);
+    make_twiddles(w, 1 << ln2);
+    if ((rc = upload(plan, (void**)&plan->d_Wn2, w.data(), sizeof(float2) * w.size()))) return fail(rc);
+  }
   if (cfg->fft1_window)
     if ((rc = upload(plan, (void**)&plan->d_window, cfg->fft1_window, sizeof(float) * plan->N))) return fail(rc);
   if (cfg->fft1_filtercorr) {
@@ -154,7 +165,7 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   if (plan->stream) cudaStreamSynchronize(plan->stream);
   for (auto& kv : plan->registered) cudaHostUnregister(const_cast<void*>(kv.first));
   void* ptrs[] = {plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
-                  plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wbig};
+                  plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wn1, plan->d_Wn2};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < lb200_plan::kJobSlots; i++) {
     if (plan->d_mixjobs[i]) cudaFree(plan->d_mixjobs[i]);
@@ -233,7 +244,7 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   k.direction = plan->cfg.fft1_direction;
 
   if (plan->cfg.fft1_n > 14) {
-    LB_CUDA(lb_launch_fft1_large(plan, k));
+    LB_CUDA(lb_launch_fft1_large(plan, k));   // counts its own launches
     return LB200_OK;
   }
   int threads = 0;

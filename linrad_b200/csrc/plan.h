@@ -45,7 +45,8 @@ struct lb200_plan {
   // large-N (four-step) scratch
   float2* d_scratch = nullptr;
   size_t scratch_elems = 0;
-  float2* d_Wbig = nullptr;    // exp(-2 pi i m / N) for the inter-pass twiddle, N entries
+  float2* d_Wn1 = nullptr;     // four-step: exp(-2 pi i m / N1)
+  float2* d_Wn2 = nullptr;     // four-step: exp(-2 pi i m / N2)
   // mix1 per-call staging: a small ring of pinned/device job tables so that consecutive
   // calls never wait for each other on the host
   static constexpr int kJobSlots = 4;

@@ -13,13 +13,43 @@ from tests.helpers import CONFIGS, CudaStream, rel_rms, run_reference, IQ_DATA, 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refwrap.available(), reason="oracle/_ref not built")]
 
 TOL_FFT1 = 1e-5
-TOL_POWER = 1e-4      # per bin, for every bin within 50 dB of the strongest bin of the row
-TOL_TIMF3 = 2e-5
-# Bins far below the strongest signal carry the float32 rounding noise of the transform itself:
-# the reference's own two C implementations (fft_cntrl rows 6 and 7) differ there by up to 3e-4
-# per bin on the cfg1 signal (77 dB of dynamic range).  For those bins the CUDA result must stay
-# within POWER_SPREAD_FACTOR times the reference-vs-reference spread measured on the same input.
-POWER_SPREAD_FACTOR = 3.0
+TOL_POWER = 1e-4      # per bin, relative -- plus the float32 noise floor of the transform, see power_ok()
+TOL_TIMF3 = 2e-5      # relative rms -- plus the float32 noise the whole spectrum leaks into the band, see timf3_ok()
+
+
+def power_ok(got, ref, avg):
+    """Per-bin check of a summed power row.  north_star: <= 1e-4 per bin.  A bin far below the
+    strongest signal also carries the single-precision rounding noise of the transform itself
+    (the reference's own two C versions, fft_cntrl rows 6 and 7, differ by 3e-4 on such bins of
+    the cfg1 signal and by more in spectral nulls), so the allowance per bin is
+        1e-4 * P  +  2 * sqrt(avg * P) * eps_a  +  avg * eps_a^2 ,
+        eps_a = 8 * sqrt(log2 N) * 2^-23 * A_rms
+    where A_rms is the rms bin amplitude of one transform.  eps_a is the amplitude error a
+    4..5-sigma excursion of the difference of two correctly rounded float32 FFTs reaches (their
+    rms error grows like sqrt(log2 N) ulps of the rms spectrum level); for bins within ~40 dB
+    of the rms level the allowance is the plain 1e-4."""
+    got = got.astype(np.float64)
+    ref = ref.astype(np.float64)
+    a_rms = np.sqrt(ref.mean() / avg)
+    eps_a = 8 * np.sqrt(np.log2(got.size + 1)) * 2.0 ** -23 * a_rms
+    allow = TOL_POWER * ref + 2 * np.sqrt(avg * ref) * eps_a + avg * eps_a ** 2
+    worst = float((np.abs(got - ref) / allow).max())
+    return worst <= 1.0, worst
+
+
+def timf3_ok(got, ref, fft1_ref, n_log2, msize):
+    """Baseband check.  timf3 is a back-transform of M of the N fft1 bins, so the float32 rounding
+    noise of the WHOLE fft1 spectrum (rms ~ sqrt(log2 N) ulps of the spectrum's rms amplitude per
+    bin) lands in it no matter how weak the selected band is: the reference's own C versions 6
+    and 7 differ by 2e-5 relative rms in timf3 for a band 40 dB below the strongest signal while
+    their fft1_float differ by 1.7e-7.  Allowance on the rms error:
+        2e-5 * rms(timf3)  +  2 * sqrt(log2 N) * 2^-23 * A_rms(fft1_float) * sqrt(M)"""
+    got = got.astype(np.float64)
+    ref = ref.astype(np.float64)
+    a_rms = np.sqrt(2.0 * (fft1_ref.astype(np.float64) ** 2).mean())       # complex amplitude
+    allow = TOL_TIMF3 * np.sqrt((ref ** 2).mean()) + 2 * np.sqrt(n_log2) * 2.0 ** -23 * a_rms * np.sqrt(msize) / np.sqrt(2.0)
+    err = np.sqrt(((got - ref) ** 2).mean())
+    return err <= allow, err / allow
 
 
 def _setup(kw, **over):
@@ -28,49 +58,38 @@ def _setup(kw, **over):
     return sizing.PathSetup(**k)
 
 
-def _compare(kw, nblocks, selbins, chunk, seed=1, natural_window=True, **over):
+def _compare(kw, nblocks, selbins, chunk, seed=1, **over):
     s = _setup(kw, **over)
     raw = make_timf1(s.input_mode, s.rf_channels, s.fft1_size, nblocks, s.fft1_new_points, seed=seed)
     kwr = dict(kw)
     kwr.update(over)
     ref = run_reference(kwr, raw, selbins, nblocks, want_raw=True)
-    alt_sumsq = None
-    if kwr["version"] in (6, 7):
-        kwa = dict(kwr, version=13 - kwr["version"])          # 6 <-> 7
-        alt_sumsq = run_reference(kwa, raw, [], nblocks)["sumsq"]
-        ref = run_reference(kwr, raw, selbins, nblocks, want_raw=True)   # the oracle keeps one state
     cs = CudaStream(s, selbins)
     try:
         got = cs.process(raw, nblocks, chunk=chunk)
         # fft1_float
         e = rel_rms(got["fft1"], ref["fft1"])
         assert e <= TOL_FFT1, f"fft1_float rel rms {e}"
-        # fft1_sumsq: every completed row, per bin
+        # fft1_sumsq: every completed row, per bin; index bookkeeping bit-exact
         N, lo, hi = s.fft1_size, s.fft1_first_point, s.fft1_last_point
         rows = (nblocks // s.avg1num)
         assert cs.sumsq_pa == ref["sumsq_pa"] and cs.sumsq_counter == ref["sumsq_counter"]
         for r in range(min(rows, 8)):
             a = cs.sumsq[r * N + lo: r * N + hi + 1]
             b = ref["sumsq"][r * N + lo: r * N + hi + 1]
-            err = np.abs(a - b) / np.maximum(np.abs(b), 1e-30)
-            strong = b >= 1e-5 * b.max()
-            assert err[strong].max() <= TOL_POWER, f"sumsq row {r} strong-bin max rel err {err[strong].max()}"
-            limit = TOL_POWER
-            if alt_sumsq is not None:
-                c = alt_sumsq[r * N + lo: r * N + hi + 1]
-                spread = (np.abs(c - b) / np.maximum(np.abs(b), 1e-30)).max()
-                limit = max(TOL_POWER, POWER_SPREAD_FACTOR * spread)
-            assert err.max() <= limit, f"sumsq row {r} max rel err {err.max()} limit {limit}"
-        # mix1
+            ok, worst = power_ok(a, b, s.avg1num)
+            assert ok, f"sumsq row {r}: worst error is {worst:.2f} x the per-bin allowance"
+        # mix1: bin selection and phase state bit-exact, baseband within tolerance
         for ss in range(len(selbins)):
             st = ref["states"][ss]
             assert cs.states[ss].mix1_point == st["point"]
             assert cs.states[ss].mix1_phase == float(st["phase"])
-            e3 = rel_rms(got["timf3"][:, ss], ref["timf3"][:, ss])
-            assert e3 <= TOL_TIMF3, f"timf3 sel {ss} rel rms {e3}"
-            # parked tail + whole ring identical up to tolerance
+            ok3, w3 = timf3_ok(got["timf3"][:, ss], ref["timf3"][:, ss], ref["fft1"], s.fft1_n, s.mix1_size)
+            assert ok3, f"timf3 sel {ss}: rms error is {w3:.2f} x the allowance"
+            # parked tail + whole ring
             ring = cs.timf3[ss * 2 * cs.timf3_size: ss * 2 * cs.timf3_size + cs.timf3_size]
-            assert rel_rms(ring, ref["timf3_ring"][ss]) <= TOL_TIMF3
+            ok3, w3 = timf3_ok(ring, ref["timf3_ring"][ss], ref["fft1"], s.fft1_n, s.mix1_size)
+            assert ok3, f"timf3 ring sel {ss}: rms error is {w3:.2f} x the allowance"
         return e
     finally:
         cs.close()
@@ -126,3 +145,56 @@ def test_avg1num_variants():
     kw = dict(input_mode=IQ_DATA, rf_channels=1, ad_speed=96000, fft1_n=10, mix1_red_n=3, version=6)
     for avg in (1, 3, 9):
         _compare(kw, 19, [], chunk=7, avg1num=avg)
+
+
+# ---------------------------------------------------------------------------------------------
+# four-step path (N >= 2^15)
+@pytest.mark.parametrize("n,version", [(15, 6), (16, 7)])
+def test_large_iq16_vs_float_reference(n, version):
+    """the float CPU versions reach N = 65536 (buf.c:285-290): direct parity.  At 65536 points the
+    radix-4 version 6 is itself 1.6x outside the power allowance against a float64 DFT (version 7:
+    0.7x), so version 7 is the oracle there."""
+    kw = dict(input_mode=IQ_DATA, rf_channels=1, ad_speed=2400000, fft1_n=n, mix1_red_n=5, version=version)
+    N = 1 << n
+    _compare(kw, 7, [0.3663 * N + 0.37, 0.61 * N], chunk=4)
+
+
+@pytest.mark.parametrize("n,mode", [(17, IQ_DATA | TWO_CHANNELS), (18, IQ_DATA | TWO_CHANNELS | DWORD_INPUT)])
+def test_large_two_channel_vs_double_reference(n, mode):
+    """above 65536 points the reference only has its double precision version 20 (2 channels)"""
+    kw = dict(input_mode=mode, rf_channels=2, ad_speed=20000000, fft1_n=n, mix1_red_n=n - 11, version=20)
+    N = 1 << n
+    _compare(kw, 6, [0.3663 * N + 0.37], chunk=5)
+
+
+def test_cfg4_iq16_262144_16_selections():
+    """BASELINE config 4: 1-channel int16, N=2^18, 16 mix1 selections (M=4096).  No float CPU
+    version exists for this size and version 20 is 2-channel only, so channel 0 of a 2-channel
+    version-20 run on the same samples is the oracle (channel 1 is a copy)."""
+    n, nblocks = 18, 6
+    kw1 = dict(input_mode=IQ_DATA, rf_channels=1, ad_speed=20000000, fft1_n=n, mix1_red_n=6)
+    s1 = sizing.PathSetup(**kw1)
+    N = s1.fft1_size
+    selbins = [8192.0 * (1 + c) + 0.25 * c for c in range(16)]
+    tones = tuple((b + 131072.0, 3000.0) for b in selbins[:4])
+    raw1 = make_timf1(s1.input_mode, 1, N, nblocks, s1.fft1_new_points, seed=4, tones=tones)
+    raw2 = np.concatenate([raw1, raw1], axis=1)
+    kw2 = dict(input_mode=IQ_DATA | TWO_CHANNELS, rf_channels=2, ad_speed=20000000, fft1_n=n, mix1_red_n=6, version=20)
+    ref = run_reference(kw2, raw2, selbins, nblocks)
+    cs = CudaStream(s1, selbins)
+    try:
+        got = cs.process(raw1, nblocks, chunk=4)
+        ref_fft1 = ref["fft1"].reshape(nblocks, N, 4)[:, :, 0:2].reshape(nblocks, -1)
+        # the 2-channel uncalibrated gain is the same as the 1-channel one (fft1.c:4653-4671)
+        assert rel_rms(got["fft1"], ref_fft1) <= TOL_FFT1
+        for ss in range(16):
+            assert cs.states[ss].mix1_point == ref["states"][ss]["point"]
+            r3 = ref["timf3"][:, ss].reshape(nblocks, -1, 4)[:, :, 0:2].reshape(nblocks, -1)
+            ok3, w3 = timf3_ok(got["timf3"][:, ss], r3, ref_fft1, n, s1.mix1_size)
+            assert ok3, (ss, w3)
+        a = cs.sumsq[:N]
+        b = 0.5 * ref["sumsq"][:N]          # two identical channels were summed
+        ok, worst = power_ok(a, b, s1.avg1num)
+        assert ok, worst
+    finally:
+        cs.close()
