@@ -206,10 +206,18 @@ class PathSetup:
         self.mix1_lowest_fq = float(f32(f32(self.fft1_first_point + 1) * f32(self.fft1_hz_per_point)))   # wide_graph.c:1336-1341
         self.mix1_highest_fq = float(f32(f32(self.fft1_last_point - 1) * f32(self.fft1_hz_per_point)))
         # tables
-        wsize = N if iq else 2 * N
-        self.window = make_window(4, wsize, self.sinpow) if self.sinpow else None
+        if not self.sinpow:
+            self.window = None
+        elif iq:
+            self.window = make_window(4, N, self.sinpow)
+        else:
+            # real input = fft1 version 2 (fft1_re.c): make_window(2,N,..) is the first half of a
+            # 2N-point window and sample 2N-1-i shares w[i] with sample i (fft1_re.c:48-57)
+            half = make_window(2, N, self.sinpow)
+            self.window = np.concatenate([half[:N], half[:N][::-1]]).astype(f32)
+        # version 2 is fft_cntrl row {2,2,...}: permute==2, real2complex==0 (fft1var.c:46)
         self.filtercorr, self.desired = clear_fft1_filtercorr(N, self.rf_channels, self.input_mode, self.fft1_gain,
-                                                              real2complex=False)
+                                                              permute2=not iq, real2complex=False)
         self.mix1_fqwin = make_window(5, M, 4)
         self._prepare_mixer()
 
@@ -256,9 +264,10 @@ class PathSetup:
         t1 = f32(f32(FFT1_WATERFALL_ZERO) / f32(self.waterfall_avgnum))
         if xpoints_per_pixel > 1:
             t1 = f32(t1 * f32(self.rf_channels))
-        y = np.where(self.desired > f32(0.3162278),
-                     (t1 / np.power(self.desired.astype(np.float64), 2.0).astype(f32)).astype(f32),
-                     f32(t1 * f32(10)))
+        with np.errstate(divide="ignore"):
+            y = np.where(self.desired > f32(0.3162278),
+                         (t1 / np.power(self.desired.astype(np.float64), 2.0).astype(f32)).astype(f32),
+                         f32(t1 * f32(10)))
         y = y.astype(f32)
         y[0] = t1
         y[-1] = t1

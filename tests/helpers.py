@@ -36,10 +36,11 @@ def run_reference(kw, raw, selbins, nblocks, want_raw=False, **extra):
     kw = dict(kw)
     version = kw.pop("version")
     r = RefOracle(fft1_version=version, n_sel=len(selbins), max_fft1n=8, **kw, **extra)
-    hz = kw["ad_speed"] / (1 << kw["fft1_n"])
+    hz = kw["ad_speed"] / (1 << kw["fft1_n"]) / (1 if kw["input_mode"] & IQ_DATA else 2)
     for i, fb in enumerate(selbins):
         r.set_selfreq(i, fb * hz if fb >= 0 else -1.0)
-    out = r.process(raw[: nblocks * r.new_points], want_raw=want_raw)
+    rawb = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+    out = r.process(rawb[: nblocks * r.timf1_blockbytes], want_raw=want_raw)
     out["sumsq"] = r.sumsq()
     out["sumsq_pa"] = r.sumsq_pa()
     out["sumsq_counter"] = r.sumsq_counter()
@@ -68,7 +69,7 @@ class CudaStream:
         self.timf3_size = timf3_size or 16 * setup.mix1_size * 2 * setup.rf_channels
         self.nsel = len(selbins)
         self.timf3 = np.zeros(max(self.nsel, 1) * 2 * self.timf3_size, np.float32)
-        hz = setup.ad_speed / N
+        hz = setup.ad_speed / N / (1 if setup.input_mode & IQ_DATA else 2)
         self.states = api.new_states([fb * hz if fb >= 0 else -1.0 for fb in selbins])
         self.pa = self.px = 0
         self.fft1_pa = self.fft1_px = 0
