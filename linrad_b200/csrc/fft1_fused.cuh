@@ -1,0 +1,256 @@
+// fft1_fused.cuh -- the fused fft1 kernel for 2^10 <= N <= 2^14 (one CTA per transform, 32 points
+// per thread).  One launch replaces, for a batch of consecutive time blocks,
+//   fft1win_dit_one / fft1win_dif_chan   (fft1.c:684-1028, 2041-2247: ring gather, int->float, window)
+//   bulk_of_dit / bulk_of_dif + permute  (fft0.c:1590-1769, 161-195; fft1.c:637-682)
+//   the direction flip of fft1_b         (fft1.c:3660-3680, 4029-4060)
+//   fft1_c                               (fft1.c:4115-4200: filtercorr multiply, |z|^2, fft1_sumsq)
+// Output convention (probed from the compiled reference):
+//   fft1_float[k] = conj( sum_n w[n] x[n] exp(-2 pi i n ((k+N/2) mod N)/N) ) * filtercorr[k]
+//
+// How the conventions are folded away so that they cost no instructions:
+//   * the (k+N/2) rotation is (-1)^n on the input: the sign is stored in the window table;
+//   * conj(DFT(z)) = swap(DFT(swap(conj z))) with swap(a+ib) = b+ia, so the kernel loads
+//     (-Q*w, I*w), runs the forward transform and stores (im, re); for fft1_direction < 0 the
+//     reference reverses the spectrum and swaps re/im, which is DFT(conj z) stored as (im, re):
+//     load (I*w, -Q*w).  Negated operands are free in FMUL.
+//   * FC == 1: an uncalibrated fft1_filtercorr (clear_fft1_filtercorr, fft1.c:4673-4724) is one
+//     real gain except on the 16 outermost bins at each end; the gain is folded into the window
+//     table and the edge bins are corrected by their ratio to it.
+//
+// Work decomposition: one CTA owns one averaging group (the wg.fft_avg1num consecutive
+// transforms summed into one fft1_sumsq row, fft1.c:4507-4520) and walks through its transforms
+// and channels in time order, so the row is accumulated on chip in the reference's own order
+// and written exactly once.  While transform b is computed the new timf1 bytes of transform
+// b+1 are pulled into L2 with one TMA bulk prefetch (cp.async.bulk.prefetch.L2).
+#pragma once
+#include "fft32_core.cuh"
+#include "fft1_small.cuh"
+
+namespace lb {
+
+enum FcMode { FC_RAW = 0, FC_FOLDED = 1, FC_TABLE = 2 };
+
+LB_D void l2_prefetch_span(const uint8_t* ring, uint32_t mask, uint32_t start, uint32_t bytes)
+{
+#if defined(__CUDA_ARCH__)
+  // [start, start+bytes) on the ring, widened to 16-byte granules, split at the wrap
+  uint32_t a = start & mask & ~15u;
+  uint32_t len = (bytes + (start & 15u) + 15u) & ~15u;
+  const uint32_t size = mask + 1u;
+  while (len > 0) {
+    uint32_t n = size - a;
+    if (n > len) n = len;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ring + a), "r"(n) : "memory");
+    len -= n;
+    a = 0;
+  }
+#endif
+}
+
+template <int FMT>
+LB_D float2 cvt_iq(const uint8_t* p)
+{
+  if (FMT == FMT_I16_1CH || FMT == FMT_I16_2CH) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+    return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+  } else {
+    const int2 w = *reinterpret_cast<const int2*>(p);
+    return make_float2((float)w.x, (float)w.y);
+  }
+}
+
+template <int LOG2N, int FMT, int FC>
+__global__ void __launch_bounds__(1 << (LOG2N - 5), 512 >> (LOG2N - 5))
+fft1_fused_kernel(const Fft1K p)
+{
+  using P = Plan32<LOG2N>;
+  constexpr int N = P::N, T = P::T;
+  constexpr int FRAME = FmtInfo<FMT>::FRAME, NCH = FmtInfo<FMT>::NCH, MM = 2 * NCH;
+  constexpr int CHB = FRAME / NCH;                         // bytes of one channel's IQ pair
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* xch = reinterpret_cast<float2*>(smem_raw);
+  float4* tab1 = reinterpret_cast<float4*>(smem_raw + sizeof(float2) * P::XCH);
+  float* acc = reinterpret_cast<float*>(smem_raw + sizeof(float2) * P::XCH + sizeof(float4) * P::TAB1);
+  const int t = threadIdx.x;
+
+  // pass-1 twiddle table [pair][k] -> shared memory; last-pass exact powers -> registers
+  if (P::NPASS == 3)
+    for (int i = t; i < P::TAB1; i += T) tab1[i] = p.tab1[i];
+  float2 wb[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) wb[j] = p.Wn[t << j];
+  const float* wtab = p.wtab + t;
+  __syncthreads();
+
+  const int group_size = p.power_rows ? 1 : p.avg1num;
+  const int c0 = p.power_rows ? 0 : p.counter0;
+  const int ngroups = (c0 + p.nblocks + group_size - 1) / group_size;
+  const uint32_t span = (uint32_t)N * FRAME;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    int b0 = g * group_size - c0;
+    int b1 = b0 + group_size;
+    if (b0 < 0) b0 = 0;
+    if (b1 > p.nblocks) b1 = p.nblocks;
+    for (int b = b0; b < b1; b++) {
+      const uint32_t start = (p.ref0 + (uint32_t)b * p.blockbytes - p.pre_bytes) & p.ring_mask;
+      if (t == 0) {
+        // what this CTA reads next: the new bytes of b+1, or the whole span of its next group
+        if (b + 1 < b1) {
+          l2_prefetch_span(p.timf1, p.ring_mask, start + span, p.blockbytes);
+        } else {
+          const int gn = g + gridDim.x;
+          int bn = gn * group_size - c0;
+          if (bn < 0) bn = 0;
+          if (gn < ngroups && bn < p.nblocks)
+            l2_prefetch_span(p.timf1, p.ring_mask, p.ref0 + (uint32_t)bn * p.blockbytes - p.pre_bytes, span);
+        }
+      }
+      float* outb = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask) + (size_t)t * MM;
+      const bool wraps = start + span > p.ring_mask + 1u;
+#pragma unroll 1
+      for (int c = 0; c < NCH; c++) {
+        float2 v[32];
+        // ---- load, int -> float, window (sign and, for FC_FOLDED, gain are in the table)
+        if (!wraps) {
+          const uint8_t* src = p.timf1 + start + (uint32_t)t * FRAME + c * CHB;
+          if (p.direction > 0) {
+#pragma unroll
+            for (int e = 0; e < 32; e++) {
+              const float2 s = cvt_iq<FMT>(src + (size_t)e * (T * FRAME));
+              const float w = wtab[e * T];
+              v[e] = make_float2(s.y * -w, s.x * w);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e++) {
+              const float2 s = cvt_iq<FMT>(src + (size_t)e * (T * FRAME));
+              const float w = wtab[e * T];
+              v[e] = make_float2(s.x * w, s.y * -w);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e++) {
+            const uint32_t off = (start + (uint32_t)(t + T * e) * FRAME) & p.ring_mask;
+            const float2 s = cvt_iq<FMT>(p.timf1 + off + c * CHB);
+            const float w = wtab[e * T];
+            v[e] = p.direction > 0 ? make_float2(s.y * -w, s.x * w) : make_float2(s.x * w, s.y * -w);
+          }
+        }
+        // ---- transform
+        pass0<P::R0>(v);
+        exch1_store<LOG2N>(v, xch, t);
+        __syncthreads();
+        exch1_load<LOG2N>(v, xch, t);
+        if (P::NPASS == 3) {
+          {
+            float2 w[32];
+            const float4* tp = tab1 + (t & (P::R0 - 1));
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+              const float4 f = tp[q * P::R0];
+              w[2 * q] = make_float2(f.x, f.y);
+              w[2 * q + 1] = make_float2(f.z, f.w);
+            }
+            radix32_table(v, w);
+          }
+          __syncthreads();                       // everybody has read exchange 1
+          exch2_store<LOG2N>(v, xch, t);
+          __syncthreads();
+          exch2_load<LOG2N>(v, xch, t);
+        }
+        radix32_gen(v, wb);
+        __syncthreads();                         // exchange buffer is free for the next transform
+        // ---- epilogue: bin k = t + T*e; v holds (im, re) of the output value
+        const bool first = (b == b0 && c == 0);
+        float* ac = acc + t;
+        if (FC == FC_FOLDED) {                   // host guarantees the full bin range here
+          if (t < 16) {                          // bins 0..15 and N-16..N-1 carry the taper of fft1.c:4703-4722
+            const float2 f = p.edge[t];
+            v[0] = make_float2(v[0].x * f.x + v[0].y * f.y, v[0].y * f.x - v[0].x * f.y);
+          }
+          if (t >= T - 16) {
+            const float2 f = p.edge[16 + t - (T - 16)];
+            v[31] = make_float2(v[31].x * f.x + v[31].y * f.y, v[31].y * f.x - v[31].x * f.y);
+          }
+          if (first) {
+#pragma unroll
+            for (int e = 0; e < 32; e++) ac[e * T] = fmaf(v[e].x, v[e].x, v[e].y * v[e].y);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e++) ac[e * T] = fmaf(v[e].x, v[e].x, fmaf(v[e].y, v[e].y, ac[e * T]));
+          }
+        } else if (FC == FC_TABLE) {
+          // general path: full filtercorr table and/or a limited bin range (fft1.c:4115-4131)
+          const float* fcp = p.filtercorr + (size_t)t * MM + 2 * c;
+#pragma unroll
+          for (int e = 0; e < 32; e++) {
+            const int k = t + T * e;
+            if (k >= p.first_point && k <= p.last_point) {
+              const float2 f = *reinterpret_cast<const float2*>(fcp + (size_t)e * (T * MM));
+              const float re = v[e].y * f.x - v[e].x * f.y;
+              const float im = v[e].x * f.x + v[e].y * f.y;
+              v[e] = make_float2(im, re);
+              const float pw = re * re + im * im;
+              ac[e * T] = first ? pw : ac[e * T] + pw;
+            }
+          }
+        }
+        if (NCH == 1) {
+          float* oc = outb;
+#pragma unroll
+          for (int e = 0; e < 32; e++) *reinterpret_cast<float2*>(oc + (size_t)e * (T * MM)) = make_float2(v[e].y, v[e].x);
+        } else {
+          // two channels share every 16-byte output slot: channel 0 waits in an L2-resident
+          // scratch row of this CTA so that the slot is written once, whole (a half-written
+          // 32-byte sector costs a DRAM fill read)
+          float2* sc = p.scratch2 + (size_t)blockIdx.x * N + t;
+          if (c == 0) {
+#pragma unroll
+            for (int e = 0; e < 32; e++) sc[e * T] = make_float2(v[e].y, v[e].x);
+          } else {
+#pragma unroll
+            for (int e0 = 0; e0 < 32; e0 += 8) {
+              float2 o0[8];
+#pragma unroll
+              for (int e = 0; e < 8; e++) o0[e] = sc[(e0 + e) * T];
+#pragma unroll
+              for (int e = 0; e < 8; e++)
+                *reinterpret_cast<float4*>(outb + (size_t)(e0 + e) * (T * MM)) = make_float4(o0[e].x, o0[e].y, v[e0 + e].y, v[e0 + e].x);
+              asm volatile("" ::: "memory");     // keep the next chunk's loads from being hoisted (registers)
+            }
+          }
+        }
+      }
+      if (p.power_rows && FC != FC_RAW) {
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          const int k = t + T * e;
+          const bool inr = (k >= p.first_point) && (k <= p.last_point);
+          p.power_rows[(size_t)b * N + k] = inr ? acc[k] : 0.0f;
+        }
+      }
+    }
+    if (p.sumsq && !p.power_rows && FC != FC_RAW && b1 > b0) {
+      float* row = p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask);
+      const bool continuing = (g == 0 && p.counter0 > 0);
+#pragma unroll
+      for (int e = 0; e < 32; e++) {
+        const int k = t + T * e;
+        if (k >= p.first_point && k <= p.last_point) {
+          float val = acc[k];
+          if (continuing) val = row[k] + val;
+          row[k] = val;
+        }
+      }
+    }
+  }
+}
+
+template <int LOG2N>
+constexpr size_t fft1_fused_smem()
+{
+  return sizeof(float2) * Plan32<LOG2N>::XCH + sizeof(float4) * Plan32<LOG2N>::TAB1 + sizeof(float) * (1 << LOG2N);
+}
+
+}  // namespace lb

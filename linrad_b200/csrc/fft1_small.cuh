@@ -49,6 +49,11 @@ struct Fft1K {
   float* power_rows;        // per-transform |z|^2 rows or nullptr
   int first_point, last_point;
   int direction;
+  // fft1_fused_kernel only
+  const float* wtab;        // window * (-1)^n [* uniform gain for FC_FOLDED], natural order
+  const float2* edge;       // FC_FOLDED: filtercorr/gain for bins 0..15 and N-16..N-1 (32 entries)
+  float2* scratch2;         // 2-channel formats: gridDim.x rows of N float2 (channel 0 parked until channel 1 is done)
+  const float4* tab1;       // pass-1 twiddles [pair][k] = (w^(2q), w^(2q+1)), w = exp(-2 pi i k/(32 R0))
 };
 
 template <int FMT>

@@ -21,6 +21,22 @@ fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* thre
 }
 
 
+#define LB_DECL_FUSED(F, C) fft1_small_launch_t lb_get_fft1_fused_fmt##F##_fc##C(int, int*, size_t*);
+LB_DECL_FUSED(0, 0) LB_DECL_FUSED(0, 1) LB_DECL_FUSED(0, 2) LB_DECL_FUSED(1, 0) LB_DECL_FUSED(1, 1) LB_DECL_FUSED(1, 2)
+LB_DECL_FUSED(2, 0) LB_DECL_FUSED(2, 1) LB_DECL_FUSED(2, 2) LB_DECL_FUSED(3, 0) LB_DECL_FUSED(3, 1) LB_DECL_FUSED(3, 2)
+
+fft1_small_launch_t lb_get_fft1_fused(int log2n, int fmt, int fc, int* threads, size_t* smem)
+{
+  typedef fft1_small_launch_t (*getter_t)(int, int*, size_t*);
+  static const getter_t g[4][3] = {
+      {lb_get_fft1_fused_fmt0_fc0, lb_get_fft1_fused_fmt0_fc1, lb_get_fft1_fused_fmt0_fc2},
+      {lb_get_fft1_fused_fmt1_fc0, lb_get_fft1_fused_fmt1_fc1, lb_get_fft1_fused_fmt1_fc2},
+      {lb_get_fft1_fused_fmt2_fc0, lb_get_fft1_fused_fmt2_fc1, lb_get_fft1_fused_fmt2_fc2},
+      {lb_get_fft1_fused_fmt3_fc0, lb_get_fft1_fused_fmt3_fc1, lb_get_fft1_fused_fmt3_fc2}};
+  if (fmt < 0 || fmt > 3 || fc < 0 || fc > 2) return nullptr;
+  return g[fmt][fc](log2n, threads, smem);
+}
+
 // ---------------------------------------------------------------------------------------------
 // four-step path: sub-batches of whole averaging groups, sized so that the intermediate Y stays
 // in L2 between step A and step B

@@ -1,0 +1,4 @@
+#define LB_FMT 0
+#define LB_FC 0
+#define LB_GETTER lb_get_fft1_fused_fmt0_fc0
+#include "kernels_fused.inc"

@@ -10,6 +10,7 @@
 #include <vector>
 #include "plan.h"
 #include "fft1_small.cuh"
+#include "fft1_fused.cuh"
 #include "fft1_large.cuh"
 #include "mix1.cuh"
 
@@ -23,6 +24,7 @@ typedef cudaError_t (*fft1_small_launch_t)(const Fft1K&, int grid, cudaStream_t)
 typedef cudaError_t (*mix1_launch_t)(const Mix1K&, int grid, cudaStream_t);
 fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* threads, size_t* smem);
 mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem);
+fft1_small_launch_t lb_get_fft1_fused(int log2n, int fmt, int fc, int* threads, size_t* smem);
 cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k);
 bool lb_fft1_large_supported(int log2n);
 
@@ -127,6 +129,50 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
     plan->fc_mode = 0;
   }
 
+  // ---- tables of the fused single-CTA kernel (fft1_fused.cuh)
+  if (cfg->fft1_n >= 10 && cfg->fft1_n <= 14) {
+    const int N = plan->N, mm = plan->mm;
+    std::vector<float> ws(N), wsg(N);
+    for (int i = 0; i < N; i++) {
+      const float w = cfg->fft1_window ? cfg->fft1_window[i] : 1.0f;
+      ws[i] = (i & 1) ? -w : w;                       // (-1)^n rotates the spectrum by N/2
+      wsg[i] = ws[i] * plan->fc_gain;
+    }
+    if ((rc = upload(plan, (void**)&plan->d_wsign, ws.data(), sizeof(float) * N))) return fail(rc);
+    plan->fc_foldable = false;
+    if (plan->fc_mode == 1 && plan->fc_gain != 0.0f) {
+      const float* fc = cfg->fft1_filtercorr;
+      std::vector<float2> edge(32);
+      bool ok = true;
+      for (int j = 0; j < 32; j++) {
+        const int k = j < 16 ? j : N - 32 + j;
+        edge[j] = make_float2((float)((double)fc[(size_t)k * mm] / plan->fc_gain), (float)((double)fc[(size_t)k * mm + 1] / plan->fc_gain));
+        for (int c = 1; c < plan->nch; c++)
+          if (fc[(size_t)k * mm + 2 * c] != fc[(size_t)k * mm] || fc[(size_t)k * mm + 2 * c + 1] != fc[(size_t)k * mm + 1]) ok = false;
+      }
+      if (ok && !env_int("LB200_NO_FOLD", 0)) {
+        plan->fc_foldable = true;
+        if ((rc = upload(plan, (void**)&plan->d_wsign_g, wsg.data(), sizeof(float) * N))) return fail(rc);
+        if ((rc = upload(plan, (void**)&plan->d_edge, edge.data(), sizeof(float2) * 32))) return fail(rc);
+      }
+    }
+    if (plan->nch == 2) {
+      const size_t rows = (size_t)plan->sm_count * (512 / (N / 32)) * 4;   // grid cap incl. LB200_GRID_WAVES <= 4
+      if (cudaMalloc((void**)&plan->d_scratch2, rows * N * sizeof(float2)) != cudaSuccess) return fail(LB200_ERR_CUDA);
+    }
+    if (cfg->fft1_n > 10) {
+      const int R0 = N >> 10;
+      std::vector<float4> tab((size_t)16 * R0);
+      for (int q = 0; q < 16; q++)
+        for (int k = 0; k < R0; k++) {
+          const double a0 = -2.0 * LB_PI * (double)(k * (2 * q)) / (32.0 * R0);
+          const double a1 = -2.0 * LB_PI * (double)(k * (2 * q + 1)) / (32.0 * R0);
+          tab[(size_t)q * R0 + k] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
+        }
+      if ((rc = upload(plan, (void**)&plan->d_tab1, tab.data(), sizeof(float4) * tab.size()))) return fail(rc);
+    }
+  }
+
   // ---- mix1 (buf.c:1297-1300, prepare_mixer buf.c:55-111)
   if (cfg->mix1_n > 0) {
     if (cfg->mix1_n < 3 || cfg->mix1_n > 13 || cfg->mix1_n > cfg->fft1_n) return fail(LB200_ERR_UNSUPPORTED);
@@ -165,7 +211,8 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   if (plan->stream) cudaStreamSynchronize(plan->stream);
   for (auto& kv : plan->registered) cudaHostUnregister(const_cast<void*>(kv.first));
   void* ptrs[] = {plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
-                  plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wn1, plan->d_Wn2};
+                  plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wn1, plan->d_Wn2,
+                  plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < lb200_plan::kJobSlots; i++) {
     if (plan->d_mixjobs[i]) cudaFree(plan->d_mixjobs[i]);
@@ -249,9 +296,32 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   }
   int threads = 0;
   size_t smem = 0;
+  const int group = k.power_rows ? 1 : k.avg1num;
+  if (plan->cfg.fft1_n >= 10 && !env_int("LB200_FFT1_LEGACY", 0)) {
+    // fused 32-points-per-thread kernel
+    const bool full = (k.first_point == 0 && k.last_point == plan->N - 1);
+    int fc = FC_TABLE;
+    if (k.fc_mode == 0) fc = FC_RAW;
+    else if (plan->fc_foldable && full) fc = FC_FOLDED;
+    k.wtab = fc == FC_FOLDED ? plan->d_wsign_g : plan->d_wsign;
+    k.edge = plan->d_edge;
+    k.tab1 = plan->d_tab1;
+    k.scratch2 = plan->d_scratch2;
+    fft1_small_launch_t fn = lb_get_fft1_fused(plan->cfg.fft1_n, plan->fmt, fc, &threads, &smem);
+    if (!fn) return LB200_ERR_UNSUPPORTED;
+    const int ngroups = (k.counter0 + k.nblocks + group - 1) / group;
+    int grid = ngroups;
+    int waves = env_int("LB200_GRID_WAVES", 1);
+    if (waves < 1) waves = 1;
+    if (waves > 4) waves = 4;
+    const int cap = plan->sm_count * (512 / threads) * waves;
+    if (grid > cap) grid = cap;
+    LB_CUDA(fn(k, grid, plan->stream));
+    plan->launches++;
+    return LB200_OK;
+  }
   fft1_small_launch_t fn = lb_get_fft1_small(plan->cfg.fft1_n, plan->fmt, env_int("LB200_FFT1_VARIANT", 0), &threads, &smem);
   if (!fn) return LB200_ERR_UNSUPPORTED;
-  const int group = k.power_rows ? 1 : k.avg1num;
   const int ngroups = (k.counter0 + k.nblocks + group - 1) / group;
   int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;

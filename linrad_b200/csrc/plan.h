@@ -37,6 +37,13 @@ struct lb200_plan {
   int fc_mode = 2;
   float fc_gain = 0.f;
   int fc_edge = 0;
+  // fft1_fused_kernel tables (2^10 <= N <= 2^14)
+  float* d_wsign = nullptr;    // window * (-1)^n
+  float* d_wsign_g = nullptr;  // window * (-1)^n * fc_gain (FC_FOLDED)
+  float2* d_edge = nullptr;    // filtercorr/fc_gain on the 16 outermost bins at each end
+  float4* d_tab1 = nullptr;    // pass-1 twiddle table
+  float2* d_scratch2 = nullptr; // fused kernel, 2 channels: one row of N float2 per resident CTA
+  bool fc_foldable = false;    // fc_mode==1, all channels alike, gain != 0
   float2* d_Wm = nullptr;      // mix1 twiddles, M entries
   float* d_fqwin = nullptr;
   float* d_mixwin = nullptr;
