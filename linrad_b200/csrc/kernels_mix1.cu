@@ -3,32 +3,50 @@
 #include "mix1.cuh"
 using namespace lb;
 
+// transforms side by side in one CTA: fill about 512 threads, at most 8
+template <int LOG2M, int LOG2E, int NCH>
+struct Mix1Par {
+  static constexpr int LANE = NCH << (LOG2M - LOG2E);
+  static constexpr int RAW = 512 / LANE;
+  static constexpr int value = RAW < 1 ? 1 : (RAW > 8 ? 8 : RAW);
+};
+
 template <int LOG2M, int LOG2E, int NCH>
 static cudaError_t launch_mix1(const Mix1K& k, int grid, cudaStream_t s)
 {
-  constexpr size_t smem = mix1_smem<LOG2M, NCH>();
+  constexpr int PAR = Mix1Par<LOG2M, LOG2E, NCH>::value;
+  constexpr size_t smem = mix1_smem<LOG2M, NCH, PAR>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mix1_kernel<LOG2M, LOG2E, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mix1_kernel<LOG2M, LOG2E, NCH, PAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  mix1_kernel<LOG2M, LOG2E, NCH><<<grid, NCH << (LOG2M - LOG2E), smem, s>>>(k);
+  mix1_kernel<LOG2M, LOG2E, NCH, PAR><<<grid, (PAR * NCH) << (LOG2M - LOG2E), smem, s>>>(k);
   return cudaGetLastError();
 }
 
 typedef cudaError_t (*mix1_launch_t)(const Mix1K&, int grid, cudaStream_t);
 
+#define LB_MCASE1(LM, LE, NC)                                                  \
+  {                                                                            \
+    *par = Mix1Par<LM, LE, NC>::value;                                         \
+    *threads = (*par * NC) << (LM - LE);                                       \
+    *smem = mix1_smem<LM, NC, Mix1Par<LM, LE, NC>::value>();                   \
+    return launch_mix1<LM, LE, NC>;                                            \
+  }
 #define LB_MCASE(LM, LE)                                                       \
   if (log2m == LM) {                                                           \
-    *threads = nch << (LM - LE);                                               \
-    if (nch == 1) { *smem = mix1_smem<LM, 1>(); return launch_mix1<LM, LE, 1>; } \
-    *smem = mix1_smem<LM, 2>(); return launch_mix1<LM, LE, 2>;                 \
+    if (nch == 1) LB_MCASE1(LM, LE, 1)                                         \
+    LB_MCASE1(LM, LE, 2)                                                       \
   }
 
-mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem)
+// mix1.size 8 .. 8192 (one channel) / 8 .. 4096 (two channels): what fits the 227 KB of shared
+// memory with the predecessor's tail kept on chip.  (The reference allows up to 32768, buf.c:856.)
+mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem, int* par)
 {
   LB_MCASE(3, 3) LB_MCASE(4, 3) LB_MCASE(5, 3) LB_MCASE(6, 3) LB_MCASE(7, 3) LB_MCASE(8, 3) LB_MCASE(9, 3)
   LB_MCASE(10, 3) LB_MCASE(11, 4) LB_MCASE(12, 4)
+  if (log2m == 13 && nch == 1) LB_MCASE1(13, 4, 1)
   return nullptr;
 }

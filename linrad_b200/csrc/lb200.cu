@@ -23,7 +23,7 @@ using namespace lb;
 typedef cudaError_t (*fft1_small_launch_t)(const Fft1K&, int grid, cudaStream_t);
 typedef cudaError_t (*mix1_launch_t)(const Mix1K&, int grid, cudaStream_t);
 fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* threads, size_t* smem);
-mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem);
+mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem, int* par);
 fft1_small_launch_t lb_get_fft1_fused(int log2n, int fmt, int fc, int* threads, size_t* smem);
 cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k);
 bool lb_fft1_large_supported(int log2n);
@@ -175,7 +175,7 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
 
   // ---- mix1 (buf.c:1297-1300, prepare_mixer buf.c:55-111)
   if (cfg->mix1_n > 0) {
-    if (cfg->mix1_n < 3 || cfg->mix1_n > 13 || cfg->mix1_n > cfg->fft1_n) return fail(LB200_ERR_UNSUPPORTED);
+    if (cfg->mix1_n < 3 || cfg->mix1_n > (plan->nch == 2 ? 12 : 13) || cfg->mix1_n > cfg->fft1_n) return fail(LB200_ERR_UNSUPPORTED);
     plan->M = 1 << cfg->mix1_n;
     if (!cfg->mix1_fqwin) return fail(LB200_ERR_BAD_CONFIG);
     std::vector<float2> w;
@@ -439,19 +439,39 @@ static int build_mix1_jobs(lb200_plan* plan, const lb200_mix1_args* a, std::vect
   jobs.resize((size_t)K * B);
   for (int ss = 0; ss < K; ss++) {
     lb200_mix1_state* s = &a->state[ss];
+    Mix1Job* row = &jobs[(size_t)ss * B];
     for (int b = 0; b < B; b++) {
-      Mix1Job& j = jobs[(size_t)ss * B + b];
-      j.src = (uint32_t)((a->fft1_px + (size_t)b * plan->fft1_block) & (a->fft1_float.size - 1));
-      j.dst = (uint32_t)((a->timf3_pa + (size_t)b * t3block) & (a->timf3_float.size - 1));
-      if (s->mix1_selfreq < 0) { j.point = -1; j.t1 = j.t2 = j.r1 = j.r2 = 0; continue; }
-      const int rc = lb200_set_mix1_phases(&plan->cfg, s, (float)s->mix1_selfreq);   /* mix1.c:1007,1013 */
-      if (rc) return rc;
+      row[b].src = (uint32_t)((a->fft1_px + (size_t)b * plan->fft1_block) & (a->fft1_float.size - 1));
+      row[b].dst = (uint32_t)((a->timf3_pa + (size_t)b * t3block) & (a->timf3_float.size - 1));
+    }
+    if (s->mix1_selfreq < 0) {
+      for (int b = 0; b < B; b++) { row[b].point = -1; row[b].t1 = row[b].t2 = row[b].r1 = row[b].r2 = 0; }
+      continue;
+    }
+    // The first two transforms go through set_mix1_phases itself (mix1.c:1007,1013): they absorb
+    // a fresh selection (mix1_point == -1) and the phase step left by the previous call.  After
+    // that the selection is in its steady state -- point, old_point, phase_rot and phase_step
+    // repeat -- and only mix1.c:847-848,859-860 plus do_mix1's running sum change the phase.
+    lb_phase_stepper stepper(0.0f);
+    for (int b = 0; b < B; b++) {
+      Mix1Job& j = row[b];
+      if (b < 2) {
+        const int rc = lb200_set_mix1_phases(&plan->cfg, s, (float)s->mix1_selfreq);
+        if (rc) return rc;
+        if (b == 1 || B == 1) stepper = lb_phase_stepper(s->mix1_phase_rot);
+      } else {
+        s->mix1_old_phase = s->mix1_phase;                                            /* mix1.c:847 */
+        s->mix1_phase = lb_float_add(s->mix1_phase, s->mix1_phase_step);              /* mix1.c:848 */
+        if ((double)s->mix1_phase > LB_PI) s->mix1_phase = (float)((double)s->mix1_phase - 2 * LB_PI);   /* mix1.c:859 */
+        if ((double)s->mix1_phase < LB_PI) s->mix1_phase = (float)((double)s->mix1_phase + 2 * LB_PI);   /* mix1.c:860 */
+      }
       j.point = s->mix1_point;
       j.t1 = s->mix1_phase;
       j.t2 = s->mix1_phase_rot;
       j.r1 = s->mix1_old_phase;
       j.r2 = (float)((double)j.t2 - (double)(2 * (s->mix1_old_point - s->mix1_point)) * LB_PI / (double)plan->M);  /* mix1.c:167 */
-      s->mix1_phase = lb_phase_advance(j.t1, j.t2, Mn);                             /* mix1.c:154,187,260 */
+      if (b < 1) s->mix1_phase = lb_phase_advance(j.t1, j.t2, Mn);                    /* mix1.c:154,187,260 */
+      else s->mix1_phase = stepper.advance(j.t1, Mn);
     }
   }
   return 0;
@@ -497,20 +517,26 @@ static int launch_mix1(lb200_plan* plan, const lb200_mix1_args* a, const float* 
   k.Mn = plan->M - k.Mi;
   k.cross = plan->cfg.mix1_crossover_points;
   k.mode = mix1_mode(plan);
-  int threads = 0;
+  int threads = 0, par = 1;
   size_t smem = 0;
-  mix1_launch_t fn = lb_get_mix1(plan->cfg.mix1_n, plan->nch, &threads, &smem);
+  mix1_launch_t fn = lb_get_mix1(plan->cfg.mix1_n, plan->nch, &threads, &smem, &par);
   if (!fn) return LB200_ERR_UNSUPPORTED;
-  // run length: long enough to amortise the one rebuilt predecessor, short enough to fill the GPU
-  int target = plan->sm_count * 4;
-  int runlen = (int)(((size_t)K * B + target - 1) / target);
+  // run length: a whole number of PAR-wide chunks (the first chunk of a run spends one lane on
+  // the rebuilt predecessor), long enough to amortise that lane, short enough to fill the GPU
+  int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (ctas_per_sm > 2048 / threads) ctas_per_sm = 2048 / threads;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int target = plan->sm_count * ctas_per_sm;
+  int chunks = (int)(((size_t)K * B + (size_t)target * par - 1) / ((size_t)target * par));
+  if (chunks < 1) chunks = 1;
+  if (chunks > 8) chunks = 8;
+  int runlen = chunks * par - (mix1_mode(plan) != 0 ? 1 : 0);
   if (runlen < 1) runlen = 1;
-  if (runlen > 32) runlen = 32;
   runlen = env_int("LB200_MIX1_RUNLEN", runlen);
   k.runlen = runlen;
   const int nruns = ((B + runlen - 1) / runlen) * K;
   int grid = nruns;
-  const int cap = plan->sm_count * 16;
+  const int cap = target * 4;
   if (grid > cap) grid = cap;
   LB_CUDA(fn(k, grid, plan->stream));
   LB_CUDA(cudaEventRecord(plan->mixjobs_done[slot], plan->stream));

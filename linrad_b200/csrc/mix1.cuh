@@ -9,9 +9,10 @@
 // set_mix1_phases (mix1.c:781-861) stays on the host (plan.cu builds one Mix1Job per
 // transform and selection, carrying the reference's float phase state bit-exactly).
 //
-// One CTA walks a *run* of consecutive transforms of one selection so that the raw tail of
-// transform b-1 (which the reference parks in timf3 and re-reads, mix1.c:178-194) stays in
-// shared memory; only the first transform of a run has to rebuild its predecessor.
+// One CTA walks a *run* of consecutive transforms of one selection, PAR of them at a time side
+// by side, so that the raw tail of transform b-1 (which the reference parks in timf3 and
+// re-reads, mix1.c:178-194) is found in shared memory; only the first transform of a run has to
+// rebuild its predecessor.
 #pragma once
 #include "fft_core.cuh"
 #include "phase.h"
@@ -61,25 +62,30 @@ LB_D float mix1_taper(const float* fqwin, int i, int M)
   return w;
 }
 
-template <int LOG2M, int LOG2E, int NCH>
-__global__ void __launch_bounds__(NCH << (LOG2M - LOG2E))
+// Threads per CTA: PAR transforms side by side, each by NCH*T threads.
+template <int LOG2M, int LOG2E, int NCH, int PAR>
+__global__ void __launch_bounds__((PAR * NCH) << (LOG2M - LOG2E), (((PAR * NCH) << (LOG2M - LOG2E)) <= 512 ? 2 : 1))
 mix1_kernel(const Mix1K p)
 {
   using P = Plan<LOG2M, LOG2E>;
   constexpr int M = P::N, E = P::E, T = P::T, MM = 2 * NCH;
-  constexpr int NTHREADS = NCH * T;
+  constexpr int LANE_THREADS = NCH * T;
+  constexpr int SLOTS = PAR + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: xch[NCH][M+M/32+32] | ybuf[2][NCH][M] | ph_t[M] | ph_r[M]
+  // layout: xch[PAR][NCH][M+M/32+32] | ybuf[SLOTS][NCH][M]; after its transform a lane reuses
+  // its first exchange slice for the two phase chains (ph_t[M] | ph_r[M/2] floats)
   float2* xch_all = reinterpret_cast<float2*>(smem_raw);
   constexpr int XCH = M + M / 32 + 32;
-  float2* ybuf_all = xch_all + NCH * XCH;
-  float* ph_t = reinterpret_cast<float*>(ybuf_all + 2 * NCH * M);
-  float* ph_r = ph_t + M;
+  float2* ybuf_all = xch_all + PAR * NCH * XCH;
 
   const int tid = threadIdx.x;
-  const int ch = tid / T;
-  const int t = tid - ch * T;
-  float2* xch = xch_all + ch * XCH;
+  const int lane = tid / LANE_THREADS;          // which transform of the chunk
+  const int lt = tid - lane * LANE_THREADS;
+  const int ch = lt / T;
+  const int t = lt - ch * T;
+  float2* xch = xch_all + (lane * NCH + ch) * XCH;
+  float* ph_t = reinterpret_cast<float*>(xch_all + lane * NCH * XCH);
+  float* ph_r = ph_t + M;
   Twiddles<P> tw;
   load_twiddles<P>(tw, p.Wm, t);
 
@@ -98,17 +104,19 @@ mix1_kernel(const Mix1K p)
     if (blast > p.nblocks) blast = p.nblocks;
     const Mix1Job* jobs = p.jobs + (size_t)ss * p.nblocks;
     float* t3 = p.timf3 + (size_t)ss * p.sel_stride;
-    int cur = 0;
-    // bstart = bfirst-1 rebuilds the predecessor's tail when this run does not start the call
-    const int bstart = (bfirst > 0 && carry_len > 0) ? bfirst - 1 : bfirst;
-    for (int b = bstart; b < blast; b++) {
-      const Mix1Job job = jobs[b];
-      const bool warm = (b < bfirst);          // predecessor: only its tail is wanted
-      float2* ybuf = ybuf_all + (cur * NCH + ch) * M;
-      __syncthreads();                         // previous iteration's readers are done
+    // ystart = bfirst-1 rebuilds the predecessor's tail when this run does not start the call
+    const int ystart = (bfirst > 0 && carry_len > 0) ? bfirst - 1 : bfirst;
+    for (int y0 = ystart; y0 < blast; y0 += PAR) {
+      const int b = y0 + lane;                 // this lane's transform
+      const bool active = b < blast;
+      const bool emit = active && b >= bfirst; // the predecessor only lends its tail
+      Mix1Job job;
+      job.point = -1;
+      if (active) job = jobs[b];
+      float2* ybuf = ybuf_all + (((b - ystart) % SLOTS) * NCH + ch) * M;
+      // ---- gather + taper (mix1.c:1015-1030, 113-135); idle lanes run the transform on zeros
+      float2 v[E];
       if (job.point >= 0) {
-        // ---- gather + taper (mix1.c:1015-1030, 113-135)
-        float2 v[E];
         const float* src = p.fft1 + (job.src & p.fft1_mask);
 #pragma unroll
         for (int e = 0; e < E; e++) {
@@ -120,25 +128,26 @@ mix1_kernel(const Mix1K p)
           const float w = mix1_taper<NCH>(p.fqwin, i, M);
           v[e] = make_float2(z.x * w, z.y * w);
         }
-        fft_forward<P>(v, xch, t, tw);         // fftback: sum_k y_k exp(-2 pi i n k / M)
-#pragma unroll
-        for (int e = 0; e < E; e++) ybuf[t + T * e] = v[e];
       } else {
 #pragma unroll
-        for (int e = 0; e < E; e++) ybuf[t + T * e] = make_float2(0.f, 0.f);
+        for (int e = 0; e < E; e++) v[e] = make_float2(0.f, 0.f);
+      }
+      fft_forward<P>(v, xch, t, tw);           // fftback: sum_k y_k exp(-2 pi i n k / M)
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < E; e++) ybuf[t + T * e] = v[e];
       }
       // ---- exact float phase chains for this transform (mix1.c:143-153,164-186)
-      constexpr int NL = NTHREADS < 32 ? NTHREADS : 32;
-      if (!warm && job.point >= 0 && tid < NL) {
-        const int chunk_t = (nt + NL - 1) / NL;
-        int i0 = tid * chunk_t;
+      if (emit && job.point >= 0) {
+        const int chunk_t = (nt + LANE_THREADS - 1) / LANE_THREADS;
+        int i0 = lt * chunk_t;
         if (i0 < nt) {
           float x = lb_phase_advance(job.t1, job.t2, i0);
           int i1 = i0 + chunk_t; if (i1 > nt) i1 = nt;
           for (int i = i0; i < i1; i++) { ph_t[i] = x; x = lb_float_add(x, job.t2); }
         }
-        const int chunk_r = (nr + NL - 1) / NL;
-        i0 = tid * chunk_r;
+        const int chunk_r = (nr + LANE_THREADS - 1) / LANE_THREADS;
+        i0 = lt * chunk_r;
         if (chunk_r > 0 && i0 < nr) {
           float x = lb_phase_advance(job.r1, job.r2, i0);
           int i1 = i0 + chunk_r; if (i1 > nr) i1 = nr;
@@ -146,15 +155,15 @@ mix1_kernel(const Mix1K p)
         }
       }
       __syncthreads();
-      if (!warm) {
-        const float2* yb = ybuf_all + (cur * NCH) * M;          // [NCH][M]
-        const float2* cb = ybuf_all + ((cur ^ 1) * NCH) * M;    // predecessor
+      if (emit) {
+        const float2* yb = ybuf_all + (((b - ystart) % SLOTS) * NCH) * M;          // [NCH][M]
+        const float2* cb = ybuf_all + (((b - 1 - ystart + SLOTS) % SLOTS) * NCH) * M;   // predecessor
         const bool from_ring = (b == 0);      // first transform of the call: tail is in timf3
         if (job.point < 0) {
           // mix1_clear: zero timf3_block floats
-          for (int s = tid; s < p.Mn * MM; s += NTHREADS) t3[(job.dst + s) & p.timf3_mask] = 0.f;
+          for (int s = lt; s < p.Mn * MM; s += LANE_THREADS) t3[(job.dst + s) & p.timf3_mask] = 0.f;
         } else {
-          for (int s = tid; s < nt; s += NTHREADS) {
+          for (int s = lt; s < nt; s += LANE_THREADS) {
             float st, ct;
             sincosf(ph_t[s], &st, &ct);
             float sr = 0.f, cr = 1.f;
@@ -193,7 +202,7 @@ mix1_kernel(const Mix1K p)
         }
         // the raw tail of the LAST transform of the call is parked in timf3 for the next call
         if (b == p.nblocks - 1 && carry_len > 0) {
-          for (int s = tid; s < carry_len; s += NTHREADS) {
+          for (int s = lt; s < carry_len; s += LANE_THREADS) {
             const uint32_t o = (job.dst + (uint32_t)(p.Mn + s) * MM) & p.timf3_mask;
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
@@ -206,16 +215,15 @@ mix1_kernel(const Mix1K p)
           }
         }
       }
-      cur ^= 1;
+      __syncthreads();                         // slots and phase chains are free for the next chunk
     }
   }
 }
 
-template <int LOG2M, int NCH>
+template <int LOG2M, int NCH, int PAR>
 constexpr size_t mix1_smem()
 {
-  return sizeof(float2) * (size_t)(NCH * ((1 << LOG2M) + (1 << LOG2M) / 32 + 32) + 2 * NCH * (1 << LOG2M)) +
-         sizeof(float) * 2 * (1 << LOG2M);
+  return sizeof(float2) * (size_t)(PAR * NCH * ((1 << LOG2M) + (1 << LOG2M) / 32 + 32) + (PAR + 1) * NCH * (1 << LOG2M));
 }
 
 }  // namespace lb
