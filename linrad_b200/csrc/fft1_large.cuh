@@ -73,8 +73,13 @@ fft1_large_cols_kernel(const Fft1LargeK q)
       const int n = (t + T * e) * N2 + n2;
       const uint32_t off = (start + (uint32_t)n * FRAME) & p.ring_mask;
       const float2 s = load_iq<FMT>(p.timf1, off, c);
-      const float wv = p.window ? p.window[n] : 1.0f;
-      v[e] = make_float2(s.x * (wv * sgn), s.y * (wv * qs));
+      if (FmtInfo<FMT>::REAL) {            // packed real pair, plain transform (fft1_re.c)
+        const float2 wv = p.window ? reinterpret_cast<const float2*>(p.window)[n] : make_float2(1.0f, 1.0f);
+        v[e] = make_float2(s.x * wv.x, s.y * wv.y);
+      } else {
+        const float wv = p.window ? p.window[n] : 1.0f;
+        v[e] = make_float2(s.x * (wv * sgn), s.y * (wv * qs));
+      }
     }
     __syncthreads();                       // previous work item's exchange reads are done
     fft_forward<P, TA>(v, xch + col, t, tw);
@@ -139,6 +144,10 @@ fft1_large_rows_kernel(const Fft1LargeK q)
           const int r = o & (TB - 1), k2 = o >> LOG2TB;
           const int k = tile * TB + r + N1 * k2;
           const float2 z = xch_all[o];
+          if (p.zbuf) {                    // real input: plain Z, finished by fft1_real_post_kernel
+            p.zbuf[((size_t)(b - p.zb_first) * NCH + c) * N + k] = z;
+            continue;
+          }
           float2 ov = p.direction < 0 ? make_float2(z.y, z.x) : make_float2(z.x, -z.y);
           const bool inr = (k >= p.first_point) && (k <= p.last_point);
           if (p.fc_mode != 0 && inr) {

@@ -18,12 +18,20 @@
 
 namespace lb {
 
-enum InFmt { FMT_I16_1CH = 0, FMT_I16_2CH = 1, FMT_I32_1CH = 2, FMT_I32_2CH = 3 };
+// Input formats.  IQ: one timf1 frame per complex point.  Real input (fft1_re.c): two
+// consecutive frames are packed as one complex point z[m] = x[2m] + i x[2m+1]; FRAME is then
+// the byte size of the PAIR of frames.
+enum InFmt { FMT_I16_1CH = 0, FMT_I16_2CH = 1, FMT_I32_1CH = 2, FMT_I32_2CH = 3,
+             FMT_R16_1CH = 4, FMT_R16_2CH = 5, FMT_R32_1CH = 6, FMT_R32_2CH = 7 };
 template <int FMT> struct FmtInfo;
-template <> struct FmtInfo<FMT_I16_1CH> { static constexpr int FRAME = 4, NCH = 1; };
-template <> struct FmtInfo<FMT_I16_2CH> { static constexpr int FRAME = 8, NCH = 2; };
-template <> struct FmtInfo<FMT_I32_1CH> { static constexpr int FRAME = 8, NCH = 1; };
-template <> struct FmtInfo<FMT_I32_2CH> { static constexpr int FRAME = 16, NCH = 2; };
+template <> struct FmtInfo<FMT_I16_1CH> { static constexpr int FRAME = 4, NCH = 1; static constexpr bool REAL = false; };
+template <> struct FmtInfo<FMT_I16_2CH> { static constexpr int FRAME = 8, NCH = 2; static constexpr bool REAL = false; };
+template <> struct FmtInfo<FMT_I32_1CH> { static constexpr int FRAME = 8, NCH = 1; static constexpr bool REAL = false; };
+template <> struct FmtInfo<FMT_I32_2CH> { static constexpr int FRAME = 16, NCH = 2; static constexpr bool REAL = false; };
+template <> struct FmtInfo<FMT_R16_1CH> { static constexpr int FRAME = 4, NCH = 1; static constexpr bool REAL = true; };
+template <> struct FmtInfo<FMT_R16_2CH> { static constexpr int FRAME = 8, NCH = 2; static constexpr bool REAL = true; };
+template <> struct FmtInfo<FMT_R32_1CH> { static constexpr int FRAME = 8, NCH = 1; static constexpr bool REAL = true; };
+template <> struct FmtInfo<FMT_R32_2CH> { static constexpr int FRAME = 16, NCH = 2; static constexpr bool REAL = true; };
 
 struct Fft1K {
   const uint8_t* timf1;     // device ring
@@ -54,6 +62,11 @@ struct Fft1K {
   const float2* edge;       // FC_FOLDED: filtercorr/gain for bins 0..15 and N-16..N-1 (32 entries)
   float2* scratch2;         // 2-channel formats: gridDim.x rows of N float2 (channel 0 parked until channel 1 is done)
   const float4* tab1;       // pass-1 twiddles [pair][k] = (w^(2q), w^(2q+1)), w = exp(-2 pi i k/(32 R0))
+  // real input (fft1_re.c): the transform kernels leave the plain packed spectrum Z in zbuf
+  // ([transform - zb_first][channel][N] float2, L2-resident) and fft1_real_post_kernel finishes
+  float2* zbuf;
+  int zb_first;
+  const float2* Wre;        // exp(-i pi k / N), k = 0..N
 };
 
 template <int FMT>
@@ -68,9 +81,22 @@ LB_D float2 load_iq(const uint8_t* ring, uint32_t off, int c)
   } else if (FMT == FMT_I32_1CH) {
     const int2 w = *reinterpret_cast<const int2*>(ring + off);
     return make_float2((float)w.x, (float)w.y);
-  } else {
+  } else if (FMT == FMT_I32_2CH) {
     const int2 w = *reinterpret_cast<const int2*>(ring + off + 8 * c);
     return make_float2((float)w.x, (float)w.y);
+  } else if (FMT == FMT_R16_1CH) {                     // [x(2m), x(2m+1)]
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(ring + off);
+    return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+  } else if (FMT == FMT_R16_2CH) {                     // [x1(2m), x2(2m), x1(2m+1), x2(2m+1)]
+    const uint2 w = *reinterpret_cast<const uint2*>(ring + off);
+    const uint32_t a = c ? (w.x >> 16) : (w.x & 0xffffu), b = c ? (w.y >> 16) : (w.y & 0xffffu);
+    return make_float2((float)(short)a, (float)(short)b);
+  } else if (FMT == FMT_R32_1CH) {
+    const int2 w = *reinterpret_cast<const int2*>(ring + off);
+    return make_float2((float)w.x, (float)w.y);
+  } else {                                             // FMT_R32_2CH
+    const int4 w = *reinterpret_cast<const int4*>(ring + off);
+    return c ? make_float2((float)w.y, (float)w.w) : make_float2((float)w.x, (float)w.z);
   }
 }
 
@@ -81,6 +107,7 @@ fft1_small_kernel(const Fft1K p)
   using P = Plan<LOG2N, LOG2E>;
   constexpr int N = P::N, E = P::E, T = P::T;
   constexpr int FRAME = FmtInfo<FMT>::FRAME, NCH = FmtInfo<FMT>::NCH, MM = 2 * NCH;
+  constexpr bool REAL = FmtInfo<FMT>::REAL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* xch = reinterpret_cast<float2*>(smem_raw);
   float* acc = reinterpret_cast<float*>(smem_raw + sizeof(float2) * (N + N / 32 + 32));
@@ -110,10 +137,21 @@ fft1_small_kernel(const Fft1K p)
           const int idx = t + T * e;
           const uint32_t off = (start + (uint32_t)idx * FRAME) & p.ring_mask;
           const float2 s = load_iq<FMT>(p.timf1, off, c);
-          const float w = p.window ? p.window[idx] : 1.0f;
-          v[e] = make_float2(s.x * (w * sgn), s.y * (w * qs));
+          if (REAL) {
+            const float2 w = p.window ? reinterpret_cast<const float2*>(p.window)[idx] : make_float2(1.0f, 1.0f);
+            v[e] = make_float2(s.x * w.x, s.y * w.y);
+          } else {
+            const float w = p.window ? p.window[idx] : 1.0f;
+            v[e] = make_float2(s.x * (w * sgn), s.y * (w * qs));
+          }
         }
         fft_forward<P>(v, xch, t, tw);
+        if (REAL) {
+          float2* z = p.zbuf + ((size_t)(b - p.zb_first) * NCH + c) * N;
+#pragma unroll
+          for (int e = 0; e < E; e++) z[t + T * e] = v[e];
+          continue;
+        }
 #pragma unroll
         for (int e = 0; e < E; e++) {
           const int k = t + T * e;
@@ -136,7 +174,7 @@ fft1_small_kernel(const Fft1K p)
           *reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c) = o;
         }
       }
-      if (p.power_rows && p.fc_mode != 0) {
+      if (!REAL && p.power_rows && p.fc_mode != 0) {
 #pragma unroll
         for (int e = 0; e < E; e++) {
           const int k = t + T * e;
@@ -145,7 +183,7 @@ fft1_small_kernel(const Fft1K p)
         }
       }
     }
-    if (p.sumsq && !p.power_rows && p.fc_mode != 0 && b1 > b0) {
+    if (!REAL && p.sumsq && !p.power_rows && p.fc_mode != 0 && b1 > b0) {
       float* row = p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask);
       const bool continuing = (g == 0 && p.counter0 > 0);
 #pragma unroll

@@ -8,6 +8,10 @@ fft1_small_launch_t lb_get_fft1_small_fmt0(int, int, int*, size_t*);
 fft1_small_launch_t lb_get_fft1_small_fmt1(int, int, int*, size_t*);
 fft1_small_launch_t lb_get_fft1_small_fmt2(int, int, int*, size_t*);
 fft1_small_launch_t lb_get_fft1_small_fmt3(int, int, int*, size_t*);
+fft1_small_launch_t lb_get_fft1_small_fmt4(int, int, int*, size_t*);
+fft1_small_launch_t lb_get_fft1_small_fmt5(int, int, int*, size_t*);
+fft1_small_launch_t lb_get_fft1_small_fmt6(int, int, int*, size_t*);
+fft1_small_launch_t lb_get_fft1_small_fmt7(int, int, int*, size_t*);
 
 fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* threads, size_t* smem)
 {
@@ -16,6 +20,10 @@ fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* thre
     case 1: return lb_get_fft1_small_fmt1(log2n, variant, threads, smem);
     case 2: return lb_get_fft1_small_fmt2(log2n, variant, threads, smem);
     case 3: return lb_get_fft1_small_fmt3(log2n, variant, threads, smem);
+    case 4: return lb_get_fft1_small_fmt4(log2n, variant, threads, smem);
+    case 5: return lb_get_fft1_small_fmt5(log2n, variant, threads, smem);
+    case 6: return lb_get_fft1_small_fmt6(log2n, variant, threads, smem);
+    case 7: return lb_get_fft1_small_fmt7(log2n, variant, threads, smem);
   }
   return nullptr;
 }
@@ -46,6 +54,17 @@ cudaError_t lb_large_launch_fmt0(int, int, const Fft1LargeK&, int, cudaStream_t)
 cudaError_t lb_large_launch_fmt1(int, int, const Fft1LargeK&, int, cudaStream_t);
 cudaError_t lb_large_launch_fmt2(int, int, const Fft1LargeK&, int, cudaStream_t);
 cudaError_t lb_large_launch_fmt3(int, int, const Fft1LargeK&, int, cudaStream_t);
+cudaError_t lb_large_launch_fmt4(int, int, const Fft1LargeK&, int, cudaStream_t);
+cudaError_t lb_large_launch_fmt5(int, int, const Fft1LargeK&, int, cudaStream_t);
+cudaError_t lb_large_launch_fmt6(int, int, const Fft1LargeK&, int, cudaStream_t);
+cudaError_t lb_large_launch_fmt7(int, int, const Fft1LargeK&, int, cudaStream_t);
+typedef cudaError_t (*large_fn_t)(int, int, const Fft1LargeK&, int, cudaStream_t);
+static large_fn_t large_fn(int fmt)
+{
+  static const large_fn_t t[8] = {lb_large_launch_fmt0, lb_large_launch_fmt1, lb_large_launch_fmt2, lb_large_launch_fmt3,
+                                  lb_large_launch_fmt4, lb_large_launch_fmt5, lb_large_launch_fmt6, lb_large_launch_fmt7};
+  return (fmt >= 0 && fmt < 8) ? t[fmt] : nullptr;
+}
 
 bool lb_fft1_large_supported(int log2n) { return log2n >= 15 && log2n <= 20; }
 
@@ -86,8 +105,7 @@ cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k)
   q.Wn1 = plan->d_Wn1;
   q.Wn2 = plan->d_Wn2;
   q.Wbig = plan->d_Wn;
-  typedef cudaError_t (*fn_t)(int, int, const Fft1LargeK&, int, cudaStream_t);
-  fn_t fn = plan->fmt == 0 ? lb_large_launch_fmt0 : plan->fmt == 1 ? lb_large_launch_fmt1 : plan->fmt == 2 ? lb_large_launch_fmt2 : lb_large_launch_fmt3;
+  large_fn_t fn = large_fn(plan->fmt);
   const int tilesA = (1 << ln2) / 16, tilesB = (1 << ln1) / 16;
   for (int g0 = 0; g0 < ngroups; g0 += gps) {
     const int g1 = g0 + gps < ngroups ? g0 + gps : ngroups;
@@ -109,6 +127,117 @@ cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k)
     e = fn(log2n, 1, q, gridB, plan->stream);
     if (e != cudaSuccess) return e;
     plan->launches += 2;
+  }
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------
+// real input (fft1_re.c): packed complex transform into an L2-resident Z buffer, then the
+// untangle / output-mapping / fft1_c kernel, in sub-batches of whole averaging groups
+#include "fft1_real.cuh"
+
+static cudaError_t ensure_buf(float2** buf, size_t* have, size_t need)
+{
+  if (*have >= need) return cudaSuccess;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *have = 0;
+  cudaError_t e = cudaMalloc((void**)buf, need * sizeof(float2));
+  if (e == cudaSuccess) *have = need;
+  return e;
+}
+
+cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k)
+{
+  const int log2n = plan->cfg.fft1_n;
+  const bool large = log2n > 14;
+  const size_t N = (size_t)1 << log2n;
+  const int nch = plan->nch;
+  const int group = k.power_rows ? 1 : k.avg1num;
+  const int c0 = k.power_rows ? 0 : k.counter0;
+  const int ngroups = (c0 + k.nblocks + group - 1) / group;
+  const char* env = getenv("LB200_SCRATCH_MB");
+  const size_t budget = (size_t)(env ? atoi(env) : 48) << 20;
+  const size_t per_group = (size_t)group * nch * N * sizeof(float2) * (large ? 2 : 1);
+  int gps = (int)(budget / per_group);
+  if (gps < 1) gps = 1;
+  const size_t need = (size_t)gps * group * nch * N;
+  cudaError_t e = ensure_buf(&plan->d_zbuf, &plan->zbuf_elems, need);
+  if (e != cudaSuccess) return e;
+  if (large) {
+    e = ensure_buf(&plan->d_scratch, &plan->scratch_elems, need);
+    if (e != cudaSuccess) return e;
+  }
+  int ln1 = 0, ln2 = 0;
+  if (large) large_split(log2n, &ln1, &ln2);
+  for (int g0 = 0; g0 < ngroups; g0 += gps) {
+    const int g1 = g0 + gps < ngroups ? g0 + gps : ngroups;
+    int b_first = g0 * group - c0;
+    int b_last = g1 * group - c0;
+    if (b_first < 0) b_first = 0;
+    if (b_last > k.nblocks) b_last = k.nblocks;
+    const int b_count = b_last - b_first;
+    if (b_count <= 0) continue;
+    // ---- transform: every block on its own, plain Z to zbuf
+    Fft1K k1 = k;
+    k1.fc_mode = 0;
+    k1.sumsq = nullptr;
+    k1.power_rows = nullptr;
+    k1.avg1num = 1;
+    k1.counter0 = 0;
+    k1.zbuf = plan->d_zbuf;
+    if (!large) {
+      int threads = 0;
+      size_t smem = 0;
+      fft1_small_launch_t fn = lb_get_fft1_small(log2n, plan->fmt, 0, &threads, &smem);
+      if (!fn) return cudaErrorNotSupported;
+      k1.ref0 = k.ref0 + (uint32_t)b_first * k.blockbytes;
+      k1.nblocks = b_count;
+      k1.zb_first = 0;
+      int ctas = (int)((227 * 1024) / (smem + 1024));
+      if (ctas > 2048 / threads) ctas = 2048 / threads;
+      if (ctas < 1) ctas = 1;
+      int grid = b_count;
+      if (grid > plan->sm_count * ctas) grid = plan->sm_count * ctas;
+      e = fn(k1, grid, plan->stream);
+      if (e != cudaSuccess) return e;
+      plan->launches += 1;
+    } else {
+      Fft1LargeK q;
+      k1.zb_first = b_first;
+      q.k = k1;
+      q.scratch = plan->d_scratch;
+      q.Wn1 = plan->d_Wn1;
+      q.Wn2 = plan->d_Wn2;
+      q.Wbig = plan->d_Wn;
+      q.b_first = b_first;
+      q.b_count = b_count;
+      q.g_first = b_first;          // groups of one transform (avg1num = 1, counter0 = 0)
+      q.g_count = b_count;
+      const int tilesA = (1 << ln2) / 16, tilesB = (1 << ln1) / 16;
+      int gridA = b_count * nch * tilesA, gridB = b_count * tilesB;
+      const int cap = plan->sm_count * 8;
+      if (gridA > cap) gridA = cap;
+      if (gridB > cap) gridB = cap;
+      large_fn_t fn = large_fn(plan->fmt);
+      e = fn(log2n, 0, q, gridA, plan->stream);
+      if (e != cudaSuccess) return e;
+      e = fn(log2n, 1, q, gridB, plan->stream);
+      if (e != cudaSuccess) return e;
+      plan->launches += 2;
+    }
+    // ---- untangle + output mapping + fft1_c
+    Fft1K kp = k;
+    kp.zbuf = plan->d_zbuf;
+    kp.zb_first = b_first;
+    const int chunks = (int)((N + 255) / 256);
+    int grid = (g1 - g0) * chunks;
+    if (grid > plan->sm_count * 16) grid = plan->sm_count * 16;
+    if (nch == 1) fft1_real_post_kernel<1><<<grid, 256, 0, plan->stream>>>(kp, log2n, b_first, b_count, g0, g1 - g0);
+    else fft1_real_post_kernel<2><<<grid, 256, 0, plan->stream>>>(kp, log2n, b_first, b_count, g0, g1 - g0);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    plan->launches += 1;
   }
   return cudaSuccess;
 }

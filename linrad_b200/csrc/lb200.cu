@@ -26,6 +26,7 @@ fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* thre
 mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem, int* par);
 fft1_small_launch_t lb_get_fft1_fused(int log2n, int fmt, int fc, int* threads, size_t* smem);
 cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k);
+cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k);
 bool lb_fft1_large_supported(int log2n);
 
 static int env_int(const char* name, int dflt)
@@ -79,17 +80,17 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
   const bool dword = (cfg->rx_input_mode & LB200_DWORD_INPUT) != 0;
   if (((cfg->rx_input_mode & LB200_TWO_CHANNELS) != 0) != (plan->nch == 2)) return fail(LB200_ERR_BAD_CONFIG);
   plan->frame = (plan->iq ? 2 : 1) * plan->nch * (dword ? 4 : 2);
-  plan->fmt = (dword ? 2 : 0) + (plan->nch == 2 ? 1 : 0);
+  plan->fmt = (plan->iq ? 0 : 4) + (dword ? 2 : 0) + (plan->nch == 2 ? 1 : 0);
   plan->fft1_block = plan->mm * plan->N;
   if (cfg->fft1_interleave_points < 0 || cfg->fft1_interleave_points >= plan->N) return fail(LB200_ERR_BAD_CONFIG);
   plan->new_points = plan->N - cfg->fft1_interleave_points;
   plan->blockbytes = (uint32_t)plan->new_points * plan->frame * (plan->iq ? 1 : 2);
+  plan->pre_bytes = (uint32_t)cfg->fft1_interleave_points * plan->frame * (plan->iq ? 1 : 2);   // fft1.c:700, fft1_re.c:44
   if (cfg->fft1_first_point < 0 || cfg->fft1_last_point >= plan->N || cfg->fft1_first_point > cfg->fft1_last_point)
     return fail(LB200_ERR_BAD_CONFIG);
   if (cfg->fft_avg1num < 1) return fail(LB200_ERR_BAD_CONFIG);
   if (cfg->sample_shift != 0) return fail(LB200_ERR_UNSUPPORTED);
   if (cfg->fft1_foldcorr != nullptr) return fail(LB200_ERR_UNSUPPORTED);
-  if (!plan->iq) return fail(LB200_ERR_UNSUPPORTED);   // real input: fft1_re path, see DESIGN.md
   if (cfg->fft1_n > 14 && !lb_fft1_large_supported(cfg->fft1_n)) return fail(LB200_ERR_UNSUPPORTED);
   if (cfg->fft1_n < 7) return fail(LB200_ERR_UNSUPPORTED);
 
@@ -110,8 +111,16 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
     make_twiddles(w, 1 << ln2);
     if ((rc = upload(plan, (void**)&plan->d_Wn2, w.data(), sizeof(float2) * w.size()))) return fail(rc);
   }
-  if (cfg->fft1_window)
-    if ((rc = upload(plan, (void**)&plan->d_window, cfg->fft1_window, sizeof(float) * plan->N))) return fail(rc);
+  if (cfg->fft1_window)   // real input: 2N real samples per transform (fft1_re.c:44-57)
+    if ((rc = upload(plan, (void**)&plan->d_window, cfg->fft1_window, sizeof(float) * plan->N * (plan->iq ? 1 : 2)))) return fail(rc);
+  if (!plan->iq) {
+    std::vector<float2> w(plan->N + 1);
+    for (int i = 0; i <= plan->N; i++) {
+      const double a = -LB_PI * (double)i / (double)plan->N;
+      w[i] = make_float2((float)cos(a), (float)sin(a));
+    }
+    if ((rc = upload(plan, (void**)&plan->d_Wre, w.data(), sizeof(float2) * w.size()))) return fail(rc);
+  }
   if (cfg->fft1_filtercorr) {
     const float* fc = cfg->fft1_filtercorr;
     if ((rc = upload(plan, (void**)&plan->d_filtercorr, fc, sizeof(float) * plan->fft1_block))) return fail(rc);
@@ -130,7 +139,7 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
   }
 
   // ---- tables of the fused single-CTA kernel (fft1_fused.cuh)
-  if (cfg->fft1_n >= 10 && cfg->fft1_n <= 14) {
+  if (plan->iq && cfg->fft1_n >= 10 && cfg->fft1_n <= 14) {
     const int N = plan->N, mm = plan->mm;
     std::vector<float> ws(N), wsg(N);
     for (int i = 0; i < N; i++) {
@@ -212,7 +221,7 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   for (auto& kv : plan->registered) cudaHostUnregister(const_cast<void*>(kv.first));
   void* ptrs[] = {plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
                   plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wn1, plan->d_Wn2,
-                  plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2};
+                  plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2, plan->d_zbuf, plan->d_Wre};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < lb200_plan::kJobSlots; i++) {
     if (plan->d_mixjobs[i]) cudaFree(plan->d_mixjobs[i]);
@@ -247,7 +256,7 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   if (!is_pow2(a->timf1.size) || !is_pow2(a->fft1_float.size)) return LB200_ERR_BAD_ARG;
   if (a->timf1p_ref % plan->frame) return LB200_ERR_BAD_ARG;
   if ((size_t)plan->fft1_block * a->nblocks > a->fft1_float.size) return LB200_ERR_BAD_ARG;
-  if ((size_t)plan->blockbytes * a->nblocks + (size_t)plan->cfg.fft1_interleave_points * plan->frame > a->timf1.size) return LB200_ERR_BAD_ARG;
+  if ((size_t)plan->blockbytes * a->nblocks + (size_t)plan->pre_bytes > a->timf1.size) return LB200_ERR_BAD_ARG;
   if (a->fft1_pa % plan->fft1_block) return LB200_ERR_BAD_ARG;
   if (a->apply_filtercorr && plan->fc_mode == 0) return LB200_ERR_BAD_CONFIG;
   cudaSetDevice(plan->device);
@@ -257,7 +266,7 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   k.ring_mask = (uint32_t)(a->timf1.size - 1);
   k.ref0 = a->timf1p_ref;
   k.blockbytes = plan->blockbytes;
-  k.pre_bytes = (uint32_t)plan->cfg.fft1_interleave_points * plan->frame;
+  k.pre_bytes = plan->pre_bytes;
   k.nblocks = a->nblocks;
   k.window = plan->d_window;
   k.Wn = plan->d_Wn;
@@ -290,6 +299,11 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   k.last_point = plan->cfg.fft1_last_point;
   k.direction = plan->cfg.fft1_direction;
 
+  if (!plan->iq) {
+    k.Wre = plan->d_Wre;
+    LB_CUDA(lb_launch_fft1_real(plan, k));    // counts its own launches
+    return LB200_OK;
+  }
   if (plan->cfg.fft1_n > 14) {
     LB_CUDA(lb_launch_fft1_large(plan, k));   // counts its own launches
     return LB200_OK;
@@ -380,7 +394,7 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
   cudaSetDevice(plan->device);
   int rc;
   lb200_fft1_args d = *a;
-  const size_t pre = (size_t)plan->cfg.fft1_interleave_points * plan->frame;
+  const size_t pre = plan->pre_bytes;
   const size_t span = pre + (size_t)plan->blockbytes * a->nblocks;
   if (span > a->timf1.size) return LB200_ERR_BAD_ARG;
   if ((rc = ensure_mirror(plan, plan->m_timf1, a->timf1.base, a->timf1.size))) return rc;

@@ -29,6 +29,7 @@ struct lb200_plan {
   int fft1_block = 0;          // mm*N floats
   int new_points = 0;          // P
   uint32_t blockbytes = 0;     // timf1_blockbytes
+  uint32_t pre_bytes = 0;      // bytes of the overlap span in front of timf1p_ref
   int M = 0;                   // mix1.size
   // device tables
   float* d_window = nullptr;
@@ -52,6 +53,9 @@ struct lb200_plan {
   // large-N (four-step) scratch
   float2* d_scratch = nullptr;
   size_t scratch_elems = 0;
+  float2* d_zbuf = nullptr;    // real input: packed spectrum Z of one sub-batch
+  size_t zbuf_elems = 0;
+  float2* d_Wre = nullptr;     // real input: exp(-i pi k / N), k = 0..N
   float2* d_Wn1 = nullptr;     // four-step: exp(-2 pi i m / N1)
   float2* d_Wn2 = nullptr;     // four-step: exp(-2 pi i m / N2)
   // mix1 per-call staging: a small ring of pinned/device job tables so that consecutive

@@ -1,0 +1,198 @@
+/* lb200_shim.c -- the Linrad-side binding of liblinrad_b200.so.
+ *
+ * Linrad has no FFI on this path; its boundary is a handful of C functions working on global
+ * ring buffers (fft1def.h:359-364,375).  This file is what a Linrad maintainer
+ * adds to the source tree (next to cuda.c) and lists in Makefile.in; it is compiled against
+ * Linrad's own headers and forwards, one call each, to the C ABI of include/linrad_b200.h.
+ * See INTEGRATION.md for the call-site edits in wcw.c.  Nothing else of Linrad changes: the
+ * buffers stay where buf.c put them, the ring indices are advanced by the same code as before.
+ *
+ *   lb200_shim_open()          at the cufftPlanMany site, wcw.c:552-576 (one plan per fft1b thread)
+ *   lb200_shim_close()         at wcw.c:1174-1184
+ *   lb200_shim_fft1_b()        in place of fft1_b()           (wcw.c:1036, do_fft1b wcw.c:500)
+ *   lb200_shim_fft1_c()        in place of fft1_c()           (wcw.c:338,366,423,1069,1098)
+ *   lb200_shim_mix1_fixed()    in place of fft1_mix1_fixed()  (wcw.c:1700,1712)
+ *
+ * fft1_b and fft1_c stay two calls on two threads, as in Linrad, but the arithmetic of both
+ * runs in ONE kernel: lb200_shim_fft1_b asks the library for the filter-corrected spectrum and
+ * the per-transform power row; lb200_shim_fft1_c only folds that row into fft1_sumsq in the
+ * reference's own order and does fft1_c's index bookkeeping (fft1.c:4507-4523).
+ */
+#include <string.h>
+#include <stdlib.h>
+#include "globdef.h"
+#include "uidef.h"
+#include "fft1def.h"
+#include "fft3def.h"
+#include "seldef.h"
+#include "screendef.h"
+#include "thrdef.h"
+#include "linrad_b200.h"
+
+#define LB200_SHIM_MAX_THREADS MAX_FFT1_THREADS      /* thrdef.h:106 */
+
+static lb200_plan *shim_plan[LB200_SHIM_MAX_THREADS];
+static float *shim_power;          /* max_fft1n rows of fft1_size floats, indexed like fft1_float blocks */
+static float *shim_window;         /* natural-order copy of fft1_window */
+
+static void shim_fail(int code)
+{
+/* LB200_ERR_* are new lirerr numbers (texts for errors.lir in INTEGRATION.md); 1211/1212 are */
+/* the codes set_mix1_phases raises itself (mix1.c:787-796). */
+lirerr(code);
+}
+
+int lb200_shim_open(int no_of_threads)
+{
+int i, k, mo;
+lb200_config c;
+memset(&c,0,sizeof(c));
+c.abi_version=LB200_ABI_VERSION;
+c.device=0;
+c.rx_input_mode=ui.rx_input_mode;
+c.rx_rf_channels=ui.rx_rf_channels;
+c.sample_shift=ui.sample_shift;
+c.fft1_n=fft1_n;
+c.fft1_interleave_points=fft1_interleave_points;
+c.fft1_direction=fft1_direction;
+c.fft1_first_point=fft1_first_point;
+c.fft1_last_point=fft1_last_point;
+/* make_window() layouts differ per fft version (fft0.c:812-921): hand over natural order */
+k=fft1_size;
+if( (ui.rx_input_mode&IQ_DATA) == 0)k*=2;
+shim_window=NULL;
+if(genparm[FIRST_FFT_SINPOW] != 0)
+  {
+  shim_window=malloc((size_t)k*sizeof(float));
+  if(shim_window == NULL){shim_fail(LB200_ERR_BAD_CONFIG); return -1;}
+  mo=fft_cntrl[FFT1_CURMODE].window;
+  lb200_window_to_natural(mo, fft1_size, fft1_window, shim_window);
+  }
+c.fft1_window=shim_window;
+c.fft1_filtercorr=fft1_filtercorr;
+c.fft1_foldcorr=(fft1_calibrate_flag&CALIQ) ? fft1_foldcorr : NULL;
+c.fft_avg1num=wg.fft_avg1num;
+c.mix1_n=(int)mix1.n;
+c.mix1_interleave_points=(int)mix1.interleave_points;
+c.mix1_crossover_points=(int)mix1.crossover_points;
+c.mix1_fqwin=mix1_fqwin;
+c.mix1_window=mix1.window;
+c.mix1_cos2win=mix1.cos2win;
+c.mix1_sin2win=mix1.sin2win;
+c.fftx_points_per_hz=fftx_points_per_hz;
+c.mix1_lowest_fq=mix1_lowest_fq;
+c.mix1_highest_fq=mix1_highest_fq;
+c.max_batch=1;
+shim_power=malloc((size_t)(fft1n_mask+1)*(size_t)fft1_size*sizeof(float));
+if(shim_power == NULL){shim_fail(LB200_ERR_BAD_CONFIG); return -1;}
+for(i=0; i<no_of_threads && i<LB200_SHIM_MAX_THREADS; i++)
+  {
+  k=lb200_create(&c,&shim_plan[i]);
+  if(k != LB200_OK){shim_fail(k); return -1;}
+  }
+return 0;
+}
+
+void lb200_shim_close(void)
+{
+int i;
+for(i=0; i<LB200_SHIM_MAX_THREADS; i++)
+  {
+  if(shim_plan[i])lb200_destroy(shim_plan[i]);
+  shim_plan[i]=NULL;
+  }
+free(shim_power); shim_power=NULL;
+free(shim_window); shim_window=NULL;
+}
+
+/* Same signature as fft1_b (fft1def.h:363).  `tmp` is not needed.  `out` is &fft1_float[fft1_pa]. */
+void lb200_shim_fft1_b(int timf1p_ref, float *out, float *tmp, int gpu_handle_number)
+{
+lb200_fft1_args a;
+int rc;
+(void)tmp;
+memset(&a,0,sizeof(a));
+a.timf1.base=timf1_char;
+a.timf1.size=(size_t)timf1_bytemask+1;
+a.timf1p_ref=(uint32_t)timf1p_ref;
+a.nblocks=1;
+a.fft1_float.base=fft1_float;
+a.fft1_float.size=(size_t)fft1_mask+1;
+a.fft1_pa=(uint32_t)(out-fft1_float);
+a.apply_filtercorr=1;
+a.power_rows=&shim_power[(size_t)((out-fft1_float)/fft1_block)*(size_t)fft1_size];
+rc=lb200_fft1(shim_plan[gpu_handle_number],&a);
+if(rc != LB200_OK)shim_fail(rc);
+}
+
+/* fft1_c (fft1.c:4085): the filtercorr multiply and |z|^2 were done on the GPU; what is */
+/* left is the accumulation order of fft1.c:4115-4200 and the bookkeeping of fft1.c:4507-4523. */
+void lb200_shim_fft1_c(void)
+{
+int ia;
+float *sum, *pwr;
+sum=&fft1_sumsq[fft1_sumsq_pa];
+pwr=&shim_power[(size_t)fft1_nb*(size_t)fft1_size];
+if(fft1_sumsq_counter == 0)
+  {
+  for(ia=fft1_first_point; ia <= fft1_last_point; ia++)sum[ia]=pwr[ia];
+  }
+else
+  {
+  for(ia=fft1_first_point; ia <= fft1_last_point; ia++)sum[ia]+=pwr[ia];
+  }
+fft1_sumsq_counter++;
+if(fft1_sumsq_counter >= wg.fft_avg1num)
+  {
+  fft1_sumsq_counter=0;
+  update_fft1_slowsum();
+  if(genparm[SECOND_FFT_ENABLE] != 0)fft1_liminfo_cnt++;
+  fft1_sumsq_pa=(fft1_sumsq_pa+fft1_size)&fft1_sumsq_mask;
+  }
+fft1_nb=(fft1_nb+1)&fft1n_mask;
+fft1_pb=fft1_nb*fft1_block;
+if(genparm[SECOND_FFT_ENABLE] == 0)ag_pa=(ag_pa+1)&ag_mask;
+}
+
+/* fft1_mix1_fixed (mix1.c:995): set_mix1_phases + gather + do_mix1 for every selection. */
+void lb200_shim_mix1_fixed(void)
+{
+lb200_mix1_args a;
+lb200_mix1_state st[MAX_MIX1];
+int ss, rc, k;
+k=genparm[MIX1_NO_OF_CHANNELS];
+for(ss=0; ss<k; ss++)
+  {
+  st[ss].mix1_selfreq=mix1_selfreq[ss];
+  st[ss].mix1_phase=mix1_phase[ss];
+  st[ss].mix1_phase_step=mix1_phase_step[ss];
+  st[ss].mix1_phase_rot=mix1_phase_rot[ss];
+  st[ss].mix1_old_phase=mix1_old_phase[ss];
+  st[ss].mix1_point=mix1_point[ss];
+  st[ss].mix1_old_point=mix1_old_point[ss];
+  }
+memset(&a,0,sizeof(a));
+a.fft1_float.base=fft1_float;
+a.fft1_float.size=(size_t)fft1_mask+1;
+a.fft1_px=(uint32_t)fft1_px;
+a.nblocks=1;
+a.no_of_channels=k;
+a.state=st;
+a.timf3_float.base=timf3_float;
+a.timf3_float.size=(size_t)timf3_size;
+a.timf3_pa=(uint32_t)timf3_pa;
+rc=lb200_mix1(shim_plan[0],&a);
+if(rc != LB200_OK){shim_fail(rc); return;}
+for(ss=0; ss<k; ss++)
+  {
+  mix1_phase[ss]=st[ss].mix1_phase;
+  mix1_phase_step[ss]=st[ss].mix1_phase_step;
+  mix1_phase_rot[ss]=st[ss].mix1_phase_rot;
+  mix1_old_phase[ss]=st[ss].mix1_old_phase;
+  mix1_point[ss]=st[ss].mix1_point;
+  mix1_old_point[ss]=st[ss].mix1_old_point;
+  }
+timf3_pa=(timf3_pa+timf3_block)&timf3_mask;         /* mix1.c:1038-1040 */
+fft1_nx=(fft1_nx+1)&fft1n_mask;
+fft1_px=(fft1_px+fft1_block)&fft1_mask;
+}

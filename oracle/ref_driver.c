@@ -238,7 +238,11 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   fft1_pa = fft1_pb = fft1_px = 0; fft1_na = fft1_nb = fft1_nx = fft1_nm = 0;
   fft1_tmp_bytes = fft1_blockbytes * (fft_cntrl[FFT1_CURMODE].real2complex + 1) * fft_cntrl[FFT1_CURMODE].parall_fft;
   if (fft_cntrl[FFT1_CURMODE].doub) fft1_tmp_bytes *= 2;
-  fftw_tmp = zalloc(fft1_tmp_bytes + 64);
+  /* buf.c:901-908 lays timf2_tmp (2*fft1_tmp_bytes of scratch) directly behind fftw_tmp.  That
+   * matters: when log2(2*fft1_size) is even, fft_real_to_hermitian's stray length-2 butterfly
+   * after its first loop (fft0.c:63-65) lands at z[2*size-2], i.e. outside fftw_tmp and inside
+   * timf2_tmp -- harmless in Linrad, heap corruption if fftw_tmp is allocated on its own. */
+  fftw_tmp = zalloc(3 * (size_t)fft1_tmp_bytes + 64);
   fft1_sumsq_bufsize = 16 * fft1_size; if (C.avg2num + 2 > 16) { k = C.avg2num + 2; make_power_of_two(&k); fft1_sumsq_bufsize = k * fft1_size; }
   fft1_sumsq_mask = fft1_sumsq_bufsize - 1;
   fft1_sumsq = zalloc(sizeof(float) * fft1_sumsq_bufsize);

@@ -14,6 +14,7 @@ CONFIGS = {
     "cfg1": dict(input_mode=IQ_DATA, rf_channels=1, ad_speed=96000, fft1_n=13, mix1_red_n=4, version=6),
     "cfg2": dict(input_mode=IQ_DATA | DWORD_INPUT | TWO_CHANNELS, rf_channels=2, ad_speed=192000, fft1_n=14,
                  mix1_red_n=4, version=7),
+    "cfg3": dict(input_mode=0, rf_channels=1, ad_speed=2400000, fft1_n=15, mix1_red_n=5, version=2),
     "cfg4": dict(input_mode=IQ_DATA, rf_channels=1, ad_speed=20000000, fft1_n=18, mix1_red_n=6, version=20),
 }
 
@@ -62,7 +63,8 @@ class CudaStream:
         self.s = setup
         self.plan = api.Plan(setup, window=window, filtercorr=filtercorr)
         N = setup.fft1_size
-        self.timf1_bytes = timf1_bytes or pow2_at_least(8 * N * setup.frame_bytes)
+        # 8 transforms' worth of input (a real-input transform covers 2N frames)
+        self.timf1_bytes = timf1_bytes or pow2_at_least(8 * N * setup.frame_bytes * (1 if setup.input_mode & IQ_DATA else 2))
         self.timf1 = np.zeros(self.timf1_bytes, np.uint8)
         self.fft1 = np.zeros(max_fft1n * setup.fft1_block, np.float32)
         self.sumsq = np.zeros(sumsq_rows * N, np.float32)

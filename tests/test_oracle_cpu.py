@@ -322,3 +322,16 @@ def test_two_rank_gloo_power_reduce(tmp_path):
         raw = make_timf1(s.input_mode, 1, s.fft1_size, 10, s.fft1_new_points, seed=100 + st)
         want += port.run_path(s, raw, [], 10)["sumsq"][: want.size]
     assert rel_rms(got, want) <= 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference headers not mounted")
+def test_shim_compiles_against_reference_headers():
+    """linrad_b200/host/lb200_shim.c is the binding a Linrad maintainer adds:
+    it must compile against Linrad's own headers with every identifier declared."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Werror=implicit-function-declaration", "-w", "-DOSNUM=1", "-DCPU=1",
+                        "-DIA64=1", "-DHAVE_CUFFT=0", "-DOPENCL_PRESENT=0", "-I/root/reference",
+                        "-I" + os.path.join(root, "include"), os.path.join(root, "linrad_b200", "host", "lb200_shim.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]

@@ -198,3 +198,40 @@ def test_cfg4_iq16_262144_16_selections():
         assert ok, worst
     finally:
         cs.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# real input: fft1 version 2 (fft1_re.c), packed half-length transform + untangle kernel
+def test_cfg3_real16_32768():
+    """BASELINE config 3: real 1-channel int16, 65536 real samples -> 32768 bins, power averaging;
+    one mix1 selection added so the real spectrum also feeds the mixer."""
+    _compare(CONFIGS["cfg3"], 11, [12000.37], chunk=5, seed=3)
+
+
+@pytest.mark.parametrize("n", [7, 9, 10, 12, 14])
+def test_real_sizes_int16(n):
+    kw = dict(input_mode=0, rf_channels=1, ad_speed=48000, fft1_n=n, mix1_red_n=3, version=2)
+    N = 1 << n
+    _compare(kw, 13, [0.3663 * N + 0.37], chunk=3)
+
+
+@pytest.mark.parametrize("mode,ch", [(TWO_CHANNELS, 2), (DWORD_INPUT, 1), (DWORD_INPUT | TWO_CHANNELS, 2)])
+def test_real_formats(mode, ch):
+    kw = dict(input_mode=mode, rf_channels=ch, ad_speed=48000, fft1_n=10, mix1_red_n=3, version=2)
+    _compare(kw, 9, [300.25], chunk=2)
+
+
+def test_real_direction_reversed():
+    kw = dict(input_mode=0, rf_channels=1, ad_speed=48000, fft1_n=10, mix1_red_n=3, version=2)
+    _compare(kw, 8, [400.3], chunk=8, direction=-1)
+
+
+@pytest.mark.parametrize("direction", [1, -1])
+def test_real_limited_display_range(direction):
+    kw = dict(input_mode=0, rf_channels=1, ad_speed=48000, fft1_n=10, mix1_red_n=3, version=2)
+    _compare(kw, 8, [500.6], chunk=3, first_xpoint=200, xpoints=600, direction=direction)
+
+
+def test_real_large_two_channel_int32():
+    kw = dict(input_mode=DWORD_INPUT | TWO_CHANNELS, rf_channels=2, ad_speed=2400000, fft1_n=15, mix1_red_n=5, version=2)
+    _compare(kw, 6, [9000.5], chunk=4)
