@@ -153,6 +153,63 @@ int lb200_fft1(lb200_plan *plan, const lb200_fft1_args *a);
 int lb200_mix1_dev(lb200_plan *plan, const lb200_mix1_args *a);
 int lb200_mix1(lb200_plan *plan, const lb200_mix1_args *a);
 
+/* ---- wide-graph consumers of fft1_sumsq -------------------------------------------------- */
+/* what update_fft1_slowsum / fft1_waterfall read from the wide-graph setup (WG_PARMS
+ * globdef.h:907-926, screendef.h; wg_first/last_point fft1.c:4612-4614) */
+typedef struct lb200_wg_config {
+  int wg_fft_avg2num;           /* wg_fft_avg2num */
+  int waterfall_avgnum;         /* wg.waterfall_avgnum */
+  int first_xpoint;             /* wg.first_xpoint */
+  int xpoints;                  /* wg.xpoints */
+  int wg_first_point;           /* wg_first_point */
+  int wg_last_point;            /* wg_last_point */
+  int wg_xpixels;               /* wg_xpixels */
+  int xpoints_per_pixel;        /* wg.xpoints_per_pixel */
+  int pixels_per_xpoint;        /* wg.pixels_per_xpoint */
+  int first_fft_bandwidth;      /* genparm[FIRST_FFT_BANDWIDTH] (selects fresh_recalc, fft1.c:4547) */
+} lb200_wg_config;
+
+/* the scalar globals the two functions advance */
+typedef struct lb200_wg_state {
+  int fft1_sumsq_pwg;           /* fft1_sumsq_pwg (floats) */
+  int fft1_sumsq_recalc;        /* fft1_sumsq_recalc */
+  int change_fft1_flag;         /* change_fft1_flag */
+  int wg_waterf_sum_counter;    /* wg_waterf_sum_counter */
+  int wg_waterf_ptr;            /* wg_waterf_ptr */
+  int latest_wg_spectrum;       /* latest_wg_spectrum */
+} lb200_wg_state;
+
+typedef struct lb200_wg_args {
+  lb200_ring fft1_sumsq;        /* fft1_sumsq, fft1_sumsq_mask+1 (floats) */
+  uint32_t fft1_sumsq_pa;       /* the FIRST newly completed row (fft1_sumsq_pa when fft1_c
+                                   called update_fft1_slowsum for it, fft1.c:4540) */
+  int nrows;                    /* newly completed rows, in ring order */
+  float *fft1_slowsum;          /* fft1_size floats */
+  float *wg_waterf_sum;         /* fft1_size floats */
+  const float *wg_waterf_yfac;  /* fft1_size floats (make_wg_yfac wide_graph.c:956-1001) */
+  short *wg_waterf;             /* wg_waterf_size shorts (+ pixels_per_xpoint+1 slack when
+                                   interpolating, like the reference's own allocation) */
+  int wg_waterf_size;
+  lb200_wg_state *state;        /* HOST, updated */
+} lb200_wg_args;
+
+/* update_fft1_slowsum (fft1.c:4526) incl. new_fft1_averages (wide_graph.c:1003), once per row */
+int lb200_update_fft1_slowsum_dev(lb200_plan *plan, const lb200_wg_config *wg, const lb200_wg_args *a);
+int lb200_update_fft1_slowsum(lb200_plan *plan, const lb200_wg_config *wg, const lb200_wg_args *a);
+/* fft1_waterfall (fft1.c:115) incl. update_wg_waterf (fft1.c:104): drains the rows from
+ * state->fft1_sumsq_pwg up to fft1_sumsq_pa + nrows*fft1_size */
+int lb200_fft1_waterfall_dev(lb200_plan *plan, const lb200_wg_config *wg, const lb200_wg_args *a);
+int lb200_fft1_waterfall(lb200_plan *plan, const lb200_wg_config *wg, const lb200_wg_args *a);
+
+/* ---- input codecs of file playback (bit-exact) -------------------------------------------- */
+/* expand_rawdat (getiq64.s:158-220): 18-bit packed -> int32; out_bytes multiple of 16, the
+ * packed input holds 9*out_bytes/16 bytes */
+int lb200_expand_rawdat_dev(lb200_plan *plan, const void *packed, void *out, size_t out_bytes);
+int lb200_expand_rawdat(lb200_plan *plan, const void *packed, void *out, size_t out_bytes);
+/* 24-bit PCM -> left-justified int32 (rxin.c:1603-1614); nsamples multiple of 4 */
+int lb200_widen_24bit_dev(lb200_plan *plan, const void *pcm24, void *out, size_t nsamples);
+int lb200_widen_24bit(lb200_plan *plan, const void *pcm24, void *out, size_t nsamples);
+
 /* Host helpers shared by the shim and the tests (pure integer / scalar logic) */
 /* set_mix1_phases (mix1.c:781-861) for one selection and one transform; returns 0 or 1211/1212 */
 int lb200_set_mix1_phases(const lb200_config *cfg, lb200_mix1_state *s, float fq);

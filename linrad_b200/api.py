@@ -19,7 +19,10 @@ ERR = {0: "OK", 3100: "NO_DEVICE", 3101: "CUDA", 3102: "BAD_CONFIG", 3103: "UNSU
 EXPORTS = ["lb200_create", "lb200_destroy", "lb200_strerror", "lb200_abi_version", "lb200_stream",
            "lb200_synchronize", "lb200_launch_count", "lb200_h2d_bytes", "lb200_d2h_bytes",
            "lb200_fft1_dev", "lb200_fft1", "lb200_mix1_dev", "lb200_mix1", "lb200_set_mix1_phases",
-           "lb200_phase_advance", "lb200_window_to_natural"]
+           "lb200_phase_advance", "lb200_window_to_natural",
+           "lb200_update_fft1_slowsum_dev", "lb200_update_fft1_slowsum", "lb200_fft1_waterfall_dev",
+           "lb200_fft1_waterfall", "lb200_expand_rawdat_dev", "lb200_expand_rawdat", "lb200_widen_24bit_dev",
+           "lb200_widen_24bit"]
 
 
 class Lb200Error(RuntimeError):
@@ -72,6 +75,26 @@ class Mix1Args(C.Structure):
     ]
 
 
+class WgConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "wg_fft_avg2num", "waterfall_avgnum", "first_xpoint", "xpoints", "wg_first_point", "wg_last_point",
+        "wg_xpixels", "xpoints_per_pixel", "pixels_per_xpoint", "first_fft_bandwidth")]
+
+
+class WgState(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "fft1_sumsq_pwg", "fft1_sumsq_recalc", "change_fft1_flag", "wg_waterf_sum_counter", "wg_waterf_ptr",
+        "latest_wg_spectrum")]
+
+
+class WgArgs(C.Structure):
+    _fields_ = [
+        ("fft1_sumsq", Ring), ("fft1_sumsq_pa", C.c_uint32), ("nrows", C.c_int),
+        ("fft1_slowsum", C.c_void_p), ("wg_waterf_sum", C.c_void_p), ("wg_waterf_yfac", C.c_void_p),
+        ("wg_waterf", C.c_void_p), ("wg_waterf_size", C.c_int), ("state", C.POINTER(WgState)),
+    ]
+
+
 _lib = None
 
 
@@ -104,6 +127,11 @@ def load_library():
     lib.lb200_phase_advance.restype = C.c_float
     lib.lb200_window_to_natural.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.lb200_window_to_natural.restype = None
+    for f in ("lb200_update_fft1_slowsum_dev", "lb200_update_fft1_slowsum", "lb200_fft1_waterfall_dev",
+              "lb200_fft1_waterfall"):
+        getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(WgConfig), C.POINTER(WgArgs)]
+    for f in ("lb200_expand_rawdat_dev", "lb200_expand_rawdat", "lb200_widen_24bit_dev", "lb200_widen_24bit"):
+        getattr(lib, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     _lib = lib
     return lib
 
@@ -254,6 +282,62 @@ class Plan:
         rc = self.lib.lb200_mix1(self.h, C.byref(a))
         if rc:
             raise Lb200Error(rc, "lb200_mix1")
+
+
+def _wg_args(sumsq_ptr, sumsq_floats, sumsq_pa, nrows, slowsum, wsum, yfac, waterf, waterf_size, state):
+    a = WgArgs()
+    a.fft1_sumsq = Ring(sumsq_ptr, sumsq_floats)
+    a.fft1_sumsq_pa = sumsq_pa
+    a.nrows = nrows
+    a.fft1_slowsum = slowsum
+    a.wg_waterf_sum = wsum
+    a.wg_waterf_yfac = yfac
+    a.wg_waterf = waterf
+    a.wg_waterf_size = waterf_size
+    a.state = C.pointer(state)
+    return a
+
+
+def wide_graph_host(plan, wg, state, *, sumsq, sumsq_pa, nrows, slowsum, wsum, yfac, waterf, waterf_size):
+    """update_fft1_slowsum for nrows new rows, then fft1_waterfall, on numpy host buffers."""
+    a = _wg_args(sumsq.ctypes.data, sumsq.size, sumsq_pa, nrows, slowsum.ctypes.data, wsum.ctypes.data,
+                 yfac.ctypes.data, waterf.ctypes.data, waterf_size, state)
+    rc = plan.lib.lb200_update_fft1_slowsum(plan.h, C.byref(wg), C.byref(a))
+    if rc:
+        raise Lb200Error(rc, "lb200_update_fft1_slowsum")
+    rc = plan.lib.lb200_fft1_waterfall(plan.h, C.byref(wg), C.byref(a))
+    if rc:
+        raise Lb200Error(rc, "lb200_fft1_waterfall")
+
+
+def wide_graph_dev(plan, wg, state, *, sumsq, sumsq_floats, sumsq_pa, nrows, slowsum, wsum, yfac, waterf, waterf_size):
+    """same on raw device addresses"""
+    a = _wg_args(sumsq, sumsq_floats, sumsq_pa, nrows, slowsum, wsum, yfac, waterf, waterf_size, state)
+    rc = plan.lib.lb200_update_fft1_slowsum_dev(plan.h, C.byref(wg), C.byref(a))
+    if rc:
+        raise Lb200Error(rc, "lb200_update_fft1_slowsum_dev")
+    rc = plan.lib.lb200_fft1_waterfall_dev(plan.h, C.byref(wg), C.byref(a))
+    if rc:
+        raise Lb200Error(rc, "lb200_fft1_waterfall_dev")
+
+
+def expand_rawdat_host(plan, packed, out_bytes):
+    packed = np.ascontiguousarray(packed, np.uint8)
+    out = np.zeros(out_bytes // 4, np.int32)
+    rc = plan.lib.lb200_expand_rawdat(plan.h, packed.ctypes.data, out.ctypes.data, out_bytes)
+    if rc:
+        raise Lb200Error(rc, "lb200_expand_rawdat")
+    return out
+
+
+def widen_24bit_host(plan, pcm):
+    pcm = np.ascontiguousarray(pcm, np.uint8)
+    n = pcm.size // 3
+    out = np.zeros(n, np.int32)
+    rc = plan.lib.lb200_widen_24bit(plan.h, pcm.ctypes.data, out.ctypes.data, n)
+    if rc:
+        raise Lb200Error(rc, "lb200_widen_24bit")
+    return out
 
 
 def new_states(selfreqs):

@@ -230,6 +230,8 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   }
   free_mirror(plan->m_timf1); free_mirror(plan->m_fft1); free_mirror(plan->m_sumsq);
   free_mirror(plan->m_timf3); free_mirror(plan->m_power);
+  free_mirror(plan->m_wg_sumsq); free_mirror(plan->m_wg_slowsum); free_mirror(plan->m_wg_wsum); free_mirror(plan->m_wg_yfac);
+  free_mirror(plan->m_wg_waterf); free_mirror(plan->m_codec_in); free_mirror(plan->m_codec_out);
   if (plan->stream) cudaStreamDestroy(plan->stream);
   delete plan;
 }

@@ -68,6 +68,7 @@ struct lb200_plan {
   int mixjobs_next = 0;
   // host-pointer API mirrors
   HostMirror m_timf1, m_fft1, m_sumsq, m_timf3, m_power;
+  HostMirror m_wg_sumsq, m_wg_slowsum, m_wg_wsum, m_wg_yfac, m_wg_waterf, m_codec_in, m_codec_out;
   std::map<const void*, size_t> registered;
   // counters
   uint64_t launches = 0, h2d = 0, d2h = 0;

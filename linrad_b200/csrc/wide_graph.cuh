@@ -1,0 +1,203 @@
+// wide_graph.cuh -- the two consumers of fft1_sumsq that feed Linrad's wide graph:
+//   update_fft1_slowsum (fft1.c:4526-4605) + new_fft1_averages (wide_graph.c:1003-1051):
+//       fft1_slowsum = sliding sum of the latest wg_fft_avg2num rows, kept by add-new/subtract-old
+//       with a moving window of bins recomputed from scratch each time, clamped at FFT1_SMALL
+//   fft1_waterfall (fft1.c:115-223) + update_wg_waterf (fft1.c:104-113):
+//       wg_waterf_sum += row; every wg.waterfall_avgnum transforms one line of
+//       short = clamp(1000*log10(sum*wg_waterf_yfac)) in one of three pixel mappings.
+// Both are sequential over rows and independent over bins, so one thread owns one bin (or one
+// pixel) and walks the new rows in order with its running value in a register: the arithmetic
+// order per bin is the reference's.  The scalar state machines (recalc window, line counter,
+// line pointer) are cheap recurrences every thread repeats; the host repeats them once more to
+// hand the updated state back.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lb {
+
+#define LB_FFT1_SMALL 1.0e-20f      /* fft1def.h: FFT1_SMALL */
+
+struct WgK {
+  const float* sumsq;       // fft1_sumsq ring
+  uint32_t sumsq_mask;      // floats
+  uint32_t pa0;             // first new completed row
+  int nrows;
+  int N;
+  // slowsum
+  float* slowsum;
+  int first_point, last_point;          // fft1_first_point, fft1_last_point
+  int wg_first_point, wg_last_point;
+  int avg2num, xpoints, fresh_recalc;
+  int recalc0, change_flag0;
+  // waterfall
+  float* wsum;
+  const float* yfac;
+  short* waterf;
+  int waterf_size, waterf_ptr0, counter0, avg1num, waterfall_avgnum;
+  int first_xpoint, xpixels, xpp, ppx;  // wg.xpoints_per_pixel, wg.pixels_per_xpoint
+  uint32_t pwg0;            // fft1_sumsq_pwg on entry
+  int wrows;                // rows the waterfall drains
+};
+
+__device__ __forceinline__ float wg_fresh(const WgK& p, uint32_t pa, int i)
+{
+  uint32_t p0 = (pa - (uint32_t)(p.avg2num - 1) * (uint32_t)p.N) & p.sumsq_mask;    // wide_graph.c:1016
+  float s = p.sumsq[p0 + i];
+  for (int m = 1; m < p.avg2num; m++) {
+    p0 = (p0 + p.N) & p.sumsq_mask;
+    s = __fadd_rn(s, p.sumsq[p0 + i]);
+    if (s < LB_FFT1_SMALL) s = LB_FFT1_SMALL;
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(256) slowsum_kernel(const WgK p)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N) return;
+  float s = p.slowsum[i];
+  int recalc = p.recalc0;
+  bool change = p.change_flag0 != 0;
+  for (int r = 0; r < p.nrows; r++) {
+    const uint32_t pa = (p.pa0 + (uint32_t)r * (uint32_t)p.N) & p.sumsq_mask;
+    if (change) {                                     // fft1.c:4541-4546
+      change = false;
+      if (i >= p.wg_first_point && i <= p.wg_last_point) s = wg_fresh(p, pa, i);
+      continue;
+    }
+    const uint32_t pb = (pa - (uint32_t)p.avg2num * (uint32_t)p.N) & p.sumsq_mask;   // fft1.c:4568
+    if (recalc == p.last_point) recalc = p.first_point;
+    const int ia = recalc;
+    recalc += p.xpoints / p.fresh_recalc;
+    if (recalc > p.last_point) recalc = p.last_point;
+    if (i >= ia && i <= recalc) {
+      s = wg_fresh(p, pa, i);
+    } else if (i >= p.first_point && i <= p.last_point) {
+      s = __fadd_rn(s, __fsub_rn(p.sumsq[pa + i], p.sumsq[pb + i]));                 // fft1.c:4576,4581
+      if (s < LB_FFT1_SMALL) s = LB_FFT1_SMALL;
+    }
+  }
+  p.slowsum[i] = s;
+}
+
+__device__ __forceinline__ float wg_log(float v)      // 1000*(float)log10(v), fft1.c:141
+{
+  return 1000.0f * (float)log10((double)v);
+}
+__device__ __forceinline__ short wg_clamp(float y)    // fft1.c:142-144
+{
+  if (y < -32767.0f) y = -32767.0f;
+  if (y > 32767.0f) y = 32767.0f;
+  return (short)y;
+}
+__device__ __forceinline__ short wg_clamp_interp(float y)   // fft1.c:169-171: low values go to +32767
+{
+  if (y < -32767.0f) y = 32767.0f;
+  if (y > 32767.0f) y = 32767.0f;
+  return (short)y;
+}
+
+// One thread per unit u.  mode 0 (1:1): unit = bin u.  mode 1 (xpoints_per_pixel > 1): unit =
+// pixel u = bins first_xpoint + u*xpp ...  mode 2 (interpolation, pixels_per_xpoint > 1): unit =
+// bin first_xpoint + u; it owns wsum of that bin and the ppx pixels that end on it.
+__global__ void __launch_bounds__(256) waterfall_kernel(const WgK p, int mode, int nunits)
+{
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nunits) return;
+  int b0, nb;                       // bins whose wsum this thread carries
+  if (mode == 0) { b0 = u; nb = 1; }
+  else if (mode == 1) { b0 = p.first_xpoint + u * p.xpp; nb = p.xpp; }
+  else { b0 = p.first_xpoint + u - 1; nb = 2; }     // [previous bin, own bin]
+  float acc[2];
+  float accmax = 0.f;
+  (void)accmax;
+  // mode 1 carries up to xpp sums; they live in global memory between rows only when xpp > 2,
+  // so keep it simple: recompute from the global wsum per line segment (see below)
+  int counter = p.counter0;
+  int ptr = p.waterf_ptr0;
+  auto in_wg = [&](int b) { return b >= p.wg_first_point && b <= p.wg_last_point && b < p.N && b >= 0; };
+  auto src = [&](uint32_t row, int b) { return p.sumsq[row + (uint32_t)(p.first_xpoint + (b - p.wg_first_point))]; };   // fft1.c:121-126
+  if (mode != 1) {
+    for (int k = 0; k < nb; k++) acc[k] = (b0 + k >= 0 && b0 + k < p.N) ? p.wsum[b0 + k] : 0.f;
+  }
+  uint32_t row = p.pwg0;
+  int seg_start = 0;                // first row of the current (unfinished) line, mode 1
+  for (int r = 0; r < p.wrows; r++) {
+    if (mode != 1) {
+      for (int k = 0; k < nb; k++)
+        if (in_wg(b0 + k)) acc[k] = __fadd_rn(acc[k], src(row, b0 + k));
+    }
+    row = (row + p.N) & p.sumsq_mask;
+    counter += p.avg1num;
+    if (counter >= p.waterfall_avgnum) {
+      if (mode == 0) {
+        const int ix = u - p.first_xpoint;
+        if (ix >= 0 && ix < p.xpixels) p.waterf[ptr + ix] = wg_clamp(wg_log(acc[0] * p.yfac[u]));
+        if (in_wg(u)) acc[0] = 0.00001f;
+      } else if (mode == 1) {
+        float t1 = 0.f;
+        for (int k = 0; k < nb; k++) {
+          const int b = b0 + k;
+          if (b >= p.N) break;
+          float v = p.wsum[b];
+          if (in_wg(b)) {
+            if (seg_start > 0) v = 0.00001f;          // reset by the previous line of this call
+            uint32_t rr = (p.pwg0 + (uint32_t)seg_start * (uint32_t)p.N) & p.sumsq_mask;
+            for (int q = seg_start; q <= r; q++) { v = __fadd_rn(v, src(rr, b)); rr = (rr + p.N) & p.sumsq_mask; }
+          }
+          const float t2 = v * p.yfac[b];
+          if (t2 > t1) t1 = t2;
+        }
+        if (u < p.xpixels) p.waterf[ptr + u] = wg_clamp(wg_log(t1));
+        seg_start = r + 1;
+      } else {
+        // fft1.c:158-205: pixel 0 from the first bin; then ppx pixels per further bin, a running
+        // float sum from the previous bin's level to this bin's
+        const int m = p.xpixels - p.ppx;
+        if (u == 0) {
+          p.waterf[ptr] = wg_clamp(wg_log(acc[1] * p.yfac[p.first_xpoint]));
+        } else {
+          const int ix = (u - 1) * p.ppx;
+          const int i = p.first_xpoint + u;
+          const bool regular = ix < m;
+          const int groups = (m + p.ppx - 1) / p.ppx;            // iterations of the ix loop
+          const bool tail = (u - 1 == (groups > 0 ? groups : 0)) && i < p.N;     // fft1.c:190
+          if ((regular || tail) && i < p.N) {
+            float yval = wg_log(acc[0] * p.yfac[i - 1]);
+            const float t1 = wg_log(acc[1] * p.yfac[i]);
+            const float der = (t1 - yval) / (float)p.ppx;
+            for (int k = ix + 1; k <= ix + p.ppx; k++) {
+              yval = __fadd_rn(yval, der);
+              p.waterf[ptr + k] = wg_clamp_interp(yval);
+            }
+          }
+        }
+        for (int k = 0; k < nb; k++)
+          if (in_wg(b0 + k)) acc[k] = 0.00001f;
+      }
+      counter = 0;                                              // update_wg_waterf, fft1.c:104-113
+      ptr -= p.xpixels;
+      if (ptr < 0) ptr += p.waterf_size;
+    }
+  }
+  // hand the running sums back
+  if (mode == 0) {
+    if (in_wg(u)) p.wsum[u] = acc[0];
+  } else if (mode == 2) {
+    const int b = p.first_xpoint + u;
+    if (in_wg(b)) p.wsum[b] = acc[1];
+  } else {
+    for (int k = 0; k < nb; k++) {
+      const int b = b0 + k;
+      if (b >= p.N || !in_wg(b)) continue;
+      float v = p.wsum[b];
+      if (seg_start > 0) v = 0.00001f;
+      uint32_t rr = (p.pwg0 + (uint32_t)seg_start * (uint32_t)p.N) & p.sumsq_mask;
+      for (int q = seg_start; q < p.wrows; q++) { v = __fadd_rn(v, src(rr, b)); rr = (rr + p.N) & p.sumsq_mask; }
+      p.wsum[b] = v;
+    }
+  }
+}
+
+}  // namespace lb

@@ -85,6 +85,14 @@ int ref_sumsq_bufsize(void) { return fft1_sumsq_bufsize; }
 int ref_sumsq_pa(void) { return fft1_sumsq_pa; }
 int ref_sumsq_counter(void) { return fft1_sumsq_counter; }
 int ref_waterf_ptr(void) { return wg_waterf_ptr; }
+int ref_waterf_sum_counter(void) { return wg_waterf_sum_counter; }
+int ref_sumsq_recalc(void) { return fft1_sumsq_recalc; }
+int ref_sumsq_pwg(void) { return fft1_sumsq_pwg; }
+int ref_latest_wg_spectrum(void) { return latest_wg_spectrum; }
+int ref_wg_first_point(void) { return wg_first_point; }
+int ref_wg_last_point(void) { return wg_last_point; }
+int ref_first_fft_bandwidth(void) { return genparm[FIRST_FFT_BANDWIDTH]; }
+void ref_set_change_fft1_flag(int v) { change_fft1_flag = v; }      /* wide_graph.c:648 sets it on every redraw */
 int ref_waterf_size(void) { return wg_waterf_size; }
 int ref_first_point(void) { return fft1_first_point; }
 int ref_last_point(void) { return fft1_last_point; }

@@ -148,6 +148,17 @@ class RefOracle:
     def waterf_ptr(self):
         return self.lib.ref_waterf_ptr()
 
+    def wg_state(self):
+        """the scalar wide-graph globals (fft1.c:104-223, 4526-4605)"""
+        L = self.lib
+        return dict(fft1_sumsq_pwg=L.ref_sumsq_pwg(), fft1_sumsq_recalc=L.ref_sumsq_recalc(),
+                    wg_waterf_sum_counter=L.ref_waterf_sum_counter(), wg_waterf_ptr=L.ref_waterf_ptr(),
+                    latest_wg_spectrum=L.ref_latest_wg_spectrum(), wg_first_point=L.ref_wg_first_point(),
+                    wg_last_point=L.ref_wg_last_point(), first_fft_bandwidth=L.ref_first_fft_bandwidth())
+
+    def set_change_fft1_flag(self, v):
+        self.lib.ref_set_change_fft1_flag(int(v))
+
     def waterf_yfac(self):
         return self._arr("ref_waterf_yfac", self.fft1_size)
 

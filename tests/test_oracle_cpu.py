@@ -172,6 +172,7 @@ def test_struct_layouts_match_header():
 #include "linrad_b200.h"
 int main(void){
   printf("%zu %zu %zu %zu %zu\n", sizeof(lb200_config), sizeof(lb200_ring), sizeof(lb200_fft1_args), sizeof(lb200_mix1_state), sizeof(lb200_mix1_args));
+  printf("%zu %zu %zu %zu %zu\n", sizeof(lb200_wg_config), sizeof(lb200_wg_state), sizeof(lb200_wg_args), offsetof(lb200_wg_args, wg_waterf_size), offsetof(lb200_wg_args, state));
   printf("%zu %zu %zu %zu\n", offsetof(lb200_config, fft1_window), offsetof(lb200_config, max_batch), offsetof(lb200_fft1_args, power_rows), offsetof(lb200_mix1_args, timf3_pa));
   return 0; }'''
     exe = os.path.join(HERE, "golden", "_abi_probe")
@@ -184,7 +185,9 @@ int main(void){
         os.remove(exe)
     sizes = [C.sizeof(api.Config), C.sizeof(api.Ring), C.sizeof(api.Fft1Args), C.sizeof(api.Mix1State), C.sizeof(api.Mix1Args)]
     offs = [api.Config.fft1_window.offset, api.Config.max_batch.offset, api.Fft1Args.power_rows.offset, api.Mix1Args.timf3_pa.offset]
-    assert [int(v) for v in out] == sizes + offs
+    wg = [C.sizeof(api.WgConfig), C.sizeof(api.WgState), C.sizeof(api.WgArgs), api.WgArgs.wg_waterf_size.offset, api.WgArgs.state.offset]
+    got = [int(v) for v in out]
+    assert got[:5] == sizes and got[5:10] == wg and got[10:] == offs
 
 
 def test_create_fails_loudly_without_gpu():
