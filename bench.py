@@ -35,11 +35,48 @@ WORKLOADS = {
     # name: (PathSetup kwargs, reference fft_cntrl row, selections (bins), batch per step)
     "cfg1": (dict(input_mode=IQ, rf_channels=1, ad_speed=96000, fft1_n=13, mix1_red_n=4), 6, [3000.37], 5920),
     "cfg2": (dict(input_mode=IQ | DW | TWO, rf_channels=2, ad_speed=192000, fft1_n=14, mix1_red_n=4), 7, [6000.74], 740),
+    "cfg3": (dict(input_mode=0, rf_channels=1, ad_speed=2400000, fft1_n=15, mix1_red_n=5), 2, [], 740),
+    "cfg4": (dict(input_mode=IQ, rf_channels=1, ad_speed=20000000, fft1_n=18, mix1_red_n=6), 20,
+             [8192.0 * (1 + c) + 0.25 * c for c in range(16)], 60),
 }
 WORKLOAD_TEXT = {
     "cfg1": "configs[0]: 1-ch complex IQ 96 kS/s int16, fft1 N=8192 sin^2 window, mix1 M=512 one signal",
     "cfg2": "configs[1]: 2-ch complex IQ 192 kS/s 24-bit (int32), fft1 N=16384 sin^2 window, mix1 M=1024 one signal",
+    "cfg3": "configs[2]: real 1-ch int16 2.4 MS/s, fft1_re N=32768 bins (65536 reals), power-spectrum averaging, no mix1",
+    "cfg4": "configs[3]: 1-ch complex IQ 20 MS/s int16, fft1 N=262144 four-step, mix1 M=4096 x 16 selections",
 }
+
+
+# cfg4's N = 2^18 exceeds every float CPU version of the reference (N <= 65536, buf.c:285-290) and its
+# double-precision version 20 is 2-channel only: the CPU arm times the nearest legal size instead
+# (version 6, N = 65536, same M = 4096 and 16 selections) and says so.
+CPU_OVERRIDE = {
+    "cfg4": (dict(input_mode=IQ, rf_channels=1, ad_speed=20000000, fft1_n=16, mix1_red_n=4), 6,
+             "reference float path stops at N=65536: timed at N=65536 (version 6), M=4096, 16 selections"),
+}
+
+
+def cpu_workload(name):
+    kw, version, selbins, _ = WORKLOADS[name]
+    note = ""
+    if name in CPU_OVERRIDE:
+        kw, version, note = CPU_OVERRIDE[name]
+        scale = (1 << kw["fft1_n"]) / (1 << WORKLOADS[name][0]["fft1_n"])
+        selbins = [b * scale for b in selbins]
+    return kw, version, selbins, note
+
+
+def samples_per_transform(s):
+    """new input samples per transform (real input: 2P real samples)"""
+    return s.fft1_new_points * (1 if s.input_mode & IQ else 2)
+
+
+def kernel_name(s):
+    if not s.input_mode & IQ:
+        return "fft1 real input: packed transform kernel(s) + fft1_real_post_kernel (one lb200_fft1_dev call)"
+    if s.fft1_n > 14:
+        return "fft1_large_cols_kernel + fft1_large_rows_kernel (four-step, one lb200_fft1_dev call)"
+    return "fft1_fused_kernel" if s.fft1_n >= 10 else "fft1_small_kernel"
 
 
 def pow2_at_least(x):
@@ -52,7 +89,7 @@ def pow2_at_least(x):
 def alg_bytes(s, nsel):
     """algorithmic bytes per transform, split by kernel."""
     N, C = s.fft1_size, s.rf_channels
-    b_in = s.fft1_new_points * s.frame_bytes
+    b_in = s.timf1_blockbytes
     b_fft1 = 8 * C * N
     b_pow = 4.0 * N / s.avg1num
     M, Mi, Mn = s.mix1_size, s.mix1_interleave_points, s.mix1_new_points
@@ -118,7 +155,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     import multiprocessing as mp
-    kw, version, selbins, _ = WORKLOADS[args.workload]
+    kw, version, selbins, note = cpu_workload(args.workload)
     s = sizing.PathSetup(**kw)
     cores = args.cpu_procs or max(1, (os.cpu_count() or 2))
     blocks = args.cpu_blocks or max(8, int(48 * 8192 * 13 / (s.fft1_size * s.fft1_n * s.rf_channels)))
@@ -160,7 +197,7 @@ def reference_arm(args, rank, world):
     for p, qi, _ in procs:
         qi.put(None)
     tot = sum(times)
-    samples = blocks * s.fft1_new_points * cores * len(times)
+    samples = blocks * samples_per_transform(s) * cores * len(times)
     value = samples / tot / 1e6
     line = {
         "impl": "reference", "metric": "fft1+mix1 IQ Msamples/s", "value": value, "unit": "Msamples/s",
@@ -170,7 +207,8 @@ def reference_arm(args, rank, world):
                    "reference_fft1_version": version},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference",
                          "sample": f"{blocks} transforms per core per step, {cores} independent pipelines, "
-                                   f"fft1_b(v{version})+fft1_c+fft1_waterfall+fft1_mix1_fixed compiled from the reference C files (-O2 -ffast-math)"},
+                                   f"fft1_b(v{version})+fft1_c+fft1_waterfall+fft1_mix1_fixed compiled from the reference C files (-O2 -ffast-math)"
+                                   + (f"; {note}" if note else "")},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -183,7 +221,7 @@ def cpu_baseline_quick(workload, seconds=12.0):
         from oracle import refwrap
         if not refwrap.available():
             return None
-        kw, version, selbins, _ = WORKLOADS[workload]
+        kw, version, selbins, note = cpu_workload(workload)
         s = sizing.PathSetup(**kw)
         r = refwrap.RefOracle(fft1_version=version, n_sel=len(selbins), **kw)
         for i, fb in enumerate(selbins):
@@ -197,9 +235,10 @@ def cpu_baseline_quick(workload, seconds=12.0):
             r.process_timed(raw, blocks)
             n += blocks
         dt = time.perf_counter() - t0
-        return {"value": n * s.fft1_new_points / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "reference",
+        return {"value": n * samples_per_transform(s) / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "reference",
                 "sample": f"{n} transforms in {dt:.1f} s, one thread: fft1_b(v{version})+fft1_c+fft1_waterfall+"
-                          f"fft1_mix1_fixed from the reference C files (-O2 -ffast-math); nproc={os.cpu_count()}"}
+                          f"fft1_mix1_fixed from the reference C files (-O2 -ffast-math); nproc={os.cpu_count()}"
+                          + (f"; {note}" if note else "")}
     except Exception as e:  # the baseline must never take the GPU line down
         return {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
@@ -259,7 +298,7 @@ def main():
     d_sumsq = torch.zeros(sumsq_floats, dtype=torch.float32, device=dev)
     timf3_size = pow2_at_least((B + 2) * s.timf3_block + 2 * C * s.mix1_size)
     nsel = len(selbins)
-    d_timf3 = torch.zeros(nsel * 2 * timf3_size, dtype=torch.float32, device=dev)
+    d_timf3 = torch.zeros(max(nsel, 1) * 2 * timf3_size, dtype=torch.float32, device=dev)
     states = api.new_states([s.selfreq_for_bin(b) for b in selbins])
     torch.cuda.synchronize()
 
@@ -277,8 +316,9 @@ def main():
         if record:
             e1.record(stream)
             ev_pairs.append((e0, e1))
-        plan.mix1_dev(fft1=d_fft1.data_ptr(), fft1_floats=fft1_floats, fft1_px=0, nblocks=B, states=states,
-                      timf3=d_timf3.data_ptr(), timf3_floats=timf3_size, timf3_pa=0)
+        if nsel:
+            plan.mix1_dev(fft1=d_fft1.data_ptr(), fft1_floats=fft1_floats, fft1_px=0, nblocks=B, states=states,
+                          timf3=d_timf3.data_ptr(), timf3_floats=timf3_size, timf3_pa=0)
         if world > 1:
             # the averaged power spectrum is the only thing that crosses GPUs
             with torch.cuda.stream(stream):
@@ -309,7 +349,8 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    samples = B * s.fft1_new_points * args.steps * world
+    spt = samples_per_transform(s)
+    samples = B * spt * args.steps * world
     value = samples / (ms * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (fft1_small_kernel) -----------------------------------
@@ -322,20 +363,20 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = ab["fft1"] * B / (fft1_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fft1_small_kernel", "kernel_ms": fft1_ms,
+                "traffic": None, "kernel": kernel_name(s), "kernel_ms": fft1_ms,
                 "algorithmic_bytes_per_launch": ab["fft1"] * B, "peak_source": peak_src,
                 "whole_step_frac": ab["total"] * B * args.steps / (ms * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the host-buffer C ABI ------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        Be = args.e2e_batch
+        Be = min(args.e2e_batch, B)
         h_timf1 = torch.zeros(pow2_at_least((Be + 2) * s.timf1_blockbytes), dtype=torch.uint8).pin_memory()
         h_timf1[: Be * s.timf1_blockbytes].copy_(torch.from_numpy(host_in[: Be * s.timf1_blockbytes]))
         h_fft1 = torch.zeros(pow2_at_least(Be * s.fft1_block), dtype=torch.float32).pin_memory()
         h_sumsq = torch.zeros(pow2_at_least((Be // s.avg1num + 2) * N), dtype=torch.float32).pin_memory()
         t3s = pow2_at_least((Be + 2) * s.timf3_block + 2 * C * s.mix1_size)
-        h_timf3 = torch.zeros(nsel * 2 * t3s, dtype=torch.float32).pin_memory()
+        h_timf3 = torch.zeros(max(nsel, 1) * 2 * t3s, dtype=torch.float32).pin_memory()
         plan2 = api.Plan(s, device=local_rank)
         st2 = api.new_states([s.selfreq_for_bin(b) for b in selbins])
         os.environ["LB200_NO_HOSTREGISTER"] = "1"      # buffers are already pinned
@@ -344,8 +385,9 @@ def main():
         def e2e_step():
             plan2.fft1_host(timf1=h_timf1.numpy(), ref=0, nblocks=Be, fft1=h_fft1.numpy(), fft1_pa=0, apply_fc=True,
                             sumsq=h_sumsq.numpy(), sumsq_pa=0, counter=0)
-            plan2.mix1_host(fft1=h_fft1.numpy(), fft1_px=0, nblocks=Be, states=st2, timf3=h_timf3.numpy(),
-                            timf3_floats=t3s, timf3_pa=0)
+            if nsel:
+                plan2.mix1_host(fft1=h_fft1.numpy(), fft1_px=0, nblocks=Be, states=st2, timf3=h_timf3.numpy(),
+                                timf3_floats=t3s, timf3_pa=0)
 
         for _ in range(3):
             e2e_step()
@@ -362,7 +404,7 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": Be * s.fft1_new_points * nrep * world / dt / 1e6, "unit": "Msamples/s",
+        e2e = {"value": Be * spt * nrep * world / dt / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": (plan2.h2d_bytes() - h0) // nrep, "d2h_bytes_per_step": (plan2.d2h_bytes() - d0) // nrep,
                "batch": Be, "api": "lb200_fft1 + lb200_mix1 on pinned host rings"}
         plan2.close()

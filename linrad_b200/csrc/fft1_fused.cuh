@@ -47,6 +47,18 @@ LB_D void l2_prefetch_span(const uint8_t* ring, uint32_t mask, uint32_t start, u
 #endif
 }
 
+// fft1_float is written once and not read again by this kernel: stream it through L2
+// (evict-first) so that it does not push the input span and the channel-0 scratch row out
+#ifndef LB_NO_STREAM_HINTS
+LB_D void lb_store_stream(float2* p, float2 v) { __stcs(p, v); }
+LB_D void lb_store_stream(float4* p, float4 v) { __stcs(p, v); }
+LB_D float2 lb_load_last(const float2* p) { return __ldcs(p); }
+#else
+LB_D void lb_store_stream(float2* p, float2 v) { *p = v; }
+LB_D void lb_store_stream(float4* p, float4 v) { *p = v; }
+LB_D float2 lb_load_last(const float2* p) { return *p; }
+#endif
+
 template <int FMT>
 LB_D float2 cvt_iq(const uint8_t* p)
 {
@@ -199,7 +211,7 @@ fft1_fused_kernel(const Fft1K p)
         if (NCH == 1) {
           float* oc = outb;
 #pragma unroll
-          for (int e = 0; e < 32; e++) *reinterpret_cast<float2*>(oc + (size_t)e * (T * MM)) = make_float2(v[e].y, v[e].x);
+          for (int e = 0; e < 32; e++) lb_store_stream(reinterpret_cast<float2*>(oc + (size_t)e * (T * MM)), make_float2(v[e].y, v[e].x));
         } else {
           // two channels share every 16-byte output slot: channel 0 waits in an L2-resident
           // scratch row of this CTA so that the slot is written once, whole (a half-written
@@ -213,10 +225,10 @@ fft1_fused_kernel(const Fft1K p)
             for (int e0 = 0; e0 < 32; e0 += 8) {
               float2 o0[8];
 #pragma unroll
-              for (int e = 0; e < 8; e++) o0[e] = sc[(e0 + e) * T];
+              for (int e = 0; e < 8; e++) o0[e] = lb_load_last(sc + (e0 + e) * T);
 #pragma unroll
               for (int e = 0; e < 8; e++)
-                *reinterpret_cast<float4*>(outb + (size_t)(e0 + e) * (T * MM)) = make_float4(o0[e].x, o0[e].y, v[e0 + e].y, v[e0 + e].x);
+                lb_store_stream(reinterpret_cast<float4*>(outb + (size_t)(e0 + e) * (T * MM)), make_float4(o0[e].x, o0[e].y, v[e0 + e].y, v[e0 + e].x));
               asm volatile("" ::: "memory");     // keep the next chunk's loads from being hoisted (registers)
             }
           }

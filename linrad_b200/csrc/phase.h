@@ -50,6 +50,8 @@ LBP_HD double lb_pow2(int k)          /* 2^k as a double, -1022 <= k <= 1023 */
 
 LBP_HD float lb_phase_advance(float x, float d, int n)
 {
+  if ((lb_f2u(d) & 0x7fffffffu) == 0u)      /* d = +-0 (a selection on an exact bin): x never moves */
+    return (n > 0) ? lb_float_add(x, d) : x;   /* one add settles the sign of a zero x */
   while (n > 0) {
     bool jumped = false;
     const uint32_t bx = lb_f2u(x), bd = lb_f2u(d);
@@ -130,6 +132,7 @@ struct lb_phase_stepper {
   }
   float advance(float x, int n)
   {
+    if ((lb_f2u(d) & 0x7fffffffu) == 0u) return (n > 0) ? lb_float_add(x, d) : x;
     while (n > 0) {
       const uint32_t bx = lb_f2u(x);
       const int key = (int)(bx >> 23);
