@@ -252,7 +252,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="transforms per step per GPU (0 = workload default)")
-    ap.add_argument("--e2e-batch", type=int, default=64)
+    ap.add_argument("--e2e-batch", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
@@ -380,7 +380,6 @@ def main():
         plan2 = api.Plan(s, device=local_rank)
         st2 = api.new_states([s.selfreq_for_bin(b) for b in selbins])
         os.environ["LB200_NO_HOSTREGISTER"] = "1"      # buffers are already pinned
-        os.environ["LB200_MIX1_TRUST_MIRROR"] = "1"    # mix1 runs on the plan that produced fft1_float
 
         def e2e_step():
             plan2.fft1_host(timf1=h_timf1.numpy(), ref=0, nblocks=Be, fft1=h_fft1.numpy(), fft1_pa=0, apply_fc=True,

@@ -29,6 +29,25 @@ cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k);
 cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k);
 bool lb_fft1_large_supported(int log2n);
 
+// fft1_sumsq rows from per-transform power rows (small-batch path of lb200_fft1_dev): one thread
+// per bin and averaging group, transforms added in time order like fft1_c does (fft1.c:4115-4200)
+__global__ void __launch_bounds__(256) sumsq_rows_kernel(const Fft1K p, const float* __restrict__ pw, int N)
+{
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  const int g = blockIdx.y;
+  if (k >= N || k < p.first_point || k > p.last_point) return;
+  int b0 = g * p.avg1num - p.counter0;
+  int b1 = b0 + p.avg1num;
+  if (b0 < 0) b0 = 0;
+  if (b1 > p.nblocks) b1 = p.nblocks;
+  if (b1 <= b0) return;
+  float acc = pw[(size_t)b0 * N + k];
+  for (int b = b0 + 1; b < b1; b++) acc += pw[(size_t)b * N + k];
+  float* row = p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask);
+  if (g == 0 && p.counter0 > 0) acc = row[k] + acc;
+  row[k] = acc;
+}
+
 static int env_int(const char* name, int dflt)
 {
   const char* s = getenv(name);
@@ -221,7 +240,7 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   for (auto& kv : plan->registered) cudaHostUnregister(const_cast<void*>(kv.first));
   void* ptrs[] = {plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
                   plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wn1, plan->d_Wn2,
-                  plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2, plan->d_zbuf, plan->d_Wre};
+                  plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2, plan->d_zbuf, plan->d_Wre, plan->d_powtmp};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < lb200_plan::kJobSlots; i++) {
     if (plan->d_mixjobs[i]) cudaFree(plan->d_mixjobs[i]);
@@ -232,6 +251,9 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   free_mirror(plan->m_timf3); free_mirror(plan->m_power);
   free_mirror(plan->m_wg_sumsq); free_mirror(plan->m_wg_slowsum); free_mirror(plan->m_wg_wsum); free_mirror(plan->m_wg_yfac);
   free_mirror(plan->m_wg_waterf); free_mirror(plan->m_codec_in); free_mirror(plan->m_codec_out);
+  for (cudaEvent_t e : plan->events) cudaEventDestroy(e);
+  if (plan->s_in) cudaStreamDestroy(plan->s_in);
+  if (plan->s_out) cudaStreamDestroy(plan->s_out);
   if (plan->stream) cudaStreamDestroy(plan->stream);
   delete plan;
 }
@@ -312,6 +334,37 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   }
   int threads = 0;
   size_t smem = 0;
+  // Small batches: one CTA per averaging group would leave most SMs idle (a Linrad-sized call of
+  // a few transforms, or one sub-batch of the pipelined host path).  Then every transform gets
+  // its own CTA, writes its |z|^2 row to an L2-resident temporary, and sumsq_rows_kernel folds
+  // the rows into fft1_sumsq in the same order the group-per-CTA kernel uses.
+  bool split = false;
+  Fft1K kfold = k;
+  if (k.sumsq && !k.power_rows && k.avg1num > 1 && k.nblocks > 1) {
+    const int ngroups_all = (k.counter0 + k.nblocks + k.avg1num - 1) / k.avg1num;
+    if (ngroups_all < plan->sm_count && !env_int("LB200_NO_SPLIT", 0)) {
+      const size_t need = (size_t)k.nblocks * plan->N * sizeof(float);
+      if (plan->powtmp_bytes < need) {
+        if (plan->d_powtmp) cudaFree(plan->d_powtmp);
+        plan->d_powtmp = nullptr;
+        plan->powtmp_bytes = 0;
+        LB_CUDA(cudaMalloc((void**)&plan->d_powtmp, need));
+        plan->powtmp_bytes = need;
+      }
+      split = true;
+      k.power_rows = plan->d_powtmp;
+      k.sumsq = nullptr;
+    }
+  }
+  auto fold = [&]() -> int {
+    if (!split) return 0;
+    const int ngroups_all = (kfold.counter0 + kfold.nblocks + kfold.avg1num - 1) / kfold.avg1num;
+    dim3 grid((plan->N + 255) / 256, ngroups_all);
+    sumsq_rows_kernel<<<grid, 256, 0, plan->stream>>>(kfold, plan->d_powtmp, plan->N);
+    LB_CUDA(cudaGetLastError());
+    plan->launches++;
+    return 0;
+  };
   const int group = k.power_rows ? 1 : k.avg1num;
   if (plan->cfg.fft1_n >= 10 && !env_int("LB200_FFT1_LEGACY", 0)) {
     // fused 32-points-per-thread kernel
@@ -334,7 +387,7 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
     if (grid > cap) grid = cap;
     LB_CUDA(fn(k, grid, plan->stream));
     plan->launches++;
-    return LB200_OK;
+    return fold();
   }
   fft1_small_launch_t fn = lb_get_fft1_small(plan->cfg.fft1_n, plan->fmt, env_int("LB200_FFT1_VARIANT", 0), &threads, &smem);
   if (!fn) return LB200_ERR_UNSUPPORTED;
@@ -348,7 +401,7 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   if (grid > cap) grid = cap;
   LB_CUDA(fn(k, grid, plan->stream));
   plan->launches++;
-  return LB200_OK;
+  return fold();
 }
 
 // ---- host-ring staging helpers -----------------------------------------------------------
@@ -369,17 +422,17 @@ static int ensure_mirror(lb200_plan* plan, HostMirror& m, const void* host, size
 }
 
 // copy [off, off+len) of a power-of-two ring of `size` bytes, wrapping, H2D or D2H
-static int ring_copy(lb200_plan* plan, void* dev, void* host, size_t size, size_t off, size_t len, bool h2d)
+static int ring_copy_on(lb200_plan* plan, cudaStream_t st, void* dev, void* host, size_t size, size_t off, size_t len, bool h2d)
 {
   off &= size - 1;
   while (len > 0) {
     size_t n = size - off;
     if (n > len) n = len;
     if (h2d) {
-      LB_CUDA(cudaMemcpyAsync((char*)dev + off, (const char*)host + off, n, cudaMemcpyHostToDevice, plan->stream));
+      LB_CUDA(cudaMemcpyAsync((char*)dev + off, (const char*)host + off, n, cudaMemcpyHostToDevice, st));
       plan->h2d += n;
     } else {
-      LB_CUDA(cudaMemcpyAsync((char*)host + off, (const char*)dev + off, n, cudaMemcpyDeviceToHost, plan->stream));
+      LB_CUDA(cudaMemcpyAsync((char*)host + off, (const char*)dev + off, n, cudaMemcpyDeviceToHost, st));
       plan->d2h += n;
     }
     len -= n;
@@ -387,7 +440,46 @@ static int ring_copy(lb200_plan* plan, void* dev, void* host, size_t size, size_
   }
   return 0;
 }
+static int ring_copy(lb200_plan* plan, void* dev, void* host, size_t size, size_t off, size_t len, bool h2d)
+{
+  return ring_copy_on(plan, plan->stream, dev, host, size, off, len, h2d);
+}
 
+// copy-engine streams and the event pool of the pipelined host path
+static int ensure_pipeline(lb200_plan* plan, size_t nevents)
+{
+  if (!plan->s_in) LB_CUDA(cudaStreamCreateWithFlags(&plan->s_in, cudaStreamNonBlocking));
+  if (!plan->s_out) LB_CUDA(cudaStreamCreateWithFlags(&plan->s_out, cudaStreamNonBlocking));
+  while (plan->events.size() < nevents) {
+    cudaEvent_t e;
+    LB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    plan->events.push_back(e);
+  }
+  return 0;
+}
+
+// which blocks of the fft1_float mirror hold what this plan itself produced for the host ring
+static void mark_fft1_valid(lb200_plan* plan, const void* host, size_t ring_floats, size_t pa, int nblocks, bool valid)
+{
+  const size_t nb = ring_floats / plan->fft1_block;
+  if (plan->fft1_valid_host != host || plan->fft1_valid.size() != nb) {
+    plan->fft1_valid.assign(nb, 0);
+    plan->fft1_valid_host = host;
+  }
+  for (int b = 0; b < nblocks; b++) plan->fft1_valid[((pa / plan->fft1_block) + b) % nb] = valid ? 1 : 0;
+}
+static bool fft1_mirror_valid(const lb200_plan* plan, const void* host, size_t ring_floats, size_t px, int nblocks)
+{
+  const size_t nb = ring_floats / plan->fft1_block;
+  if (plan->fft1_valid_host != host || plan->fft1_valid.size() != nb || px % plan->fft1_block) return false;
+  for (int b = 0; b < nblocks; b++)
+    if (!plan->fft1_valid[((px / plan->fft1_block) + b) % nb]) return false;
+  return true;
+}
+
+// Host rings.  The call is cut into sub-batches that flow through three streams -- input copy,
+// kernels, output copy -- so that the H2D of sub-batch i+1, the kernels of i and the D2H of i-1
+// overlap (PCIe is full duplex and fft1_float going back is twice the size of timf1 coming in).
 extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
 {
   if (!plan || !a || !a->timf1.base || !a->fft1_float.base) return LB200_ERR_BAD_ARG;
@@ -395,44 +487,91 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
   if (!is_pow2(a->timf1.size) || !is_pow2(a->fft1_float.size)) return LB200_ERR_BAD_ARG;
   cudaSetDevice(plan->device);
   int rc;
-  lb200_fft1_args d = *a;
   const size_t pre = plan->pre_bytes;
   const size_t span = pre + (size_t)plan->blockbytes * a->nblocks;
   if (span > a->timf1.size) return LB200_ERR_BAD_ARG;
+  if ((size_t)plan->fft1_block * a->nblocks > a->fft1_float.size) return LB200_ERR_BAD_ARG;
   if ((rc = ensure_mirror(plan, plan->m_timf1, a->timf1.base, a->timf1.size))) return rc;
   if ((rc = ensure_mirror(plan, plan->m_fft1, a->fft1_float.base, a->fft1_float.size * sizeof(float)))) return rc;
-  if ((rc = ring_copy(plan, plan->m_timf1.d, a->timf1.base, a->timf1.size, (size_t)a->timf1p_ref - pre + a->timf1.size, span, true))) return rc;
-  d.timf1.base = plan->m_timf1.d;
-  d.fft1_float.base = plan->m_fft1.d;
-  size_t rows = 0;
-  if (a->apply_filtercorr && a->power_rows) {
+  const bool want_power = a->apply_filtercorr && a->power_rows;
+  const bool want_sumsq = a->apply_filtercorr && !a->power_rows && a->fft1_sumsq.base;
+  const int avg = plan->cfg.fft_avg1num;
+  if (want_power) {
     const size_t bytes = sizeof(float) * (size_t)plan->N * a->nblocks;
     if (!plan->m_power.d || plan->m_power.bytes < bytes) {
       if (plan->m_power.d) cudaFree(plan->m_power.d);
+      plan->m_power.d = nullptr;
       LB_CUDA(cudaMalloc(&plan->m_power.d, bytes));
       plan->m_power.bytes = bytes;
     }
-    d.power_rows = (float*)plan->m_power.d;
-  } else if (a->apply_filtercorr && a->fft1_sumsq.base) {
+  } else if (want_sumsq) {
     if (!is_pow2(a->fft1_sumsq.size)) return LB200_ERR_BAD_ARG;
     if ((rc = ensure_mirror(plan, plan->m_sumsq, a->fft1_sumsq.base, a->fft1_sumsq.size * sizeof(float)))) return rc;
-    d.fft1_sumsq.base = plan->m_sumsq.d;
-    rows = ((size_t)a->fft1_sumsq_counter + a->nblocks + plan->cfg.fft_avg1num - 1) / plan->cfg.fft_avg1num;
-    if (a->fft1_sumsq_counter > 0)   // a row in progress: bring the host's partial sums over
-      if ((rc = ring_copy(plan, plan->m_sumsq.d, a->fft1_sumsq.base, a->fft1_sumsq.size * 4, (size_t)a->fft1_sumsq_pa * 4, (size_t)plan->N * 4, true))) return rc;
   }
-  if ((rc = lb200_fft1_dev(plan, &d))) return rc;
-  if ((rc = ring_copy(plan, plan->m_fft1.d, a->fft1_float.base, a->fft1_float.size * 4, (size_t)a->fft1_pa * 4,
-                      (size_t)plan->fft1_block * a->nblocks * 4, false))) return rc;
-  if (d.power_rows && a->power_rows) {
-    const size_t bytes = sizeof(float) * (size_t)plan->N * a->nblocks;
-    LB_CUDA(cudaMemcpyAsync(a->power_rows, d.power_rows, bytes, cudaMemcpyDeviceToHost, plan->stream));
-    plan->d2h += bytes;
-  } else if (rows) {
-    if ((rc = ring_copy(plan, plan->m_sumsq.d, a->fft1_sumsq.base, a->fft1_sumsq.size * 4, (size_t)a->fft1_sumsq_pa * 4,
-                        rows * plan->N * 4, false))) return rc;
+  // sub-batch size: about 16 MB of fft1_float each (a sub-batch costs ~10 driver calls), whole averaging groups once the group that
+  // is open on entry has been completed
+  int sub = (int)((16u << 20) / ((size_t)plan->fft1_block * 4));
+  if (sub < 1) sub = 1;
+  if (want_sumsq && sub >= avg) sub -= sub % avg;
+  sub = env_int("LB200_HOST_SUBBATCH", sub);
+  if (sub < 1) sub = 1;
+  const int nsub_max = a->nblocks / sub + 2;
+  if ((rc = ensure_pipeline(plan, 2 * (size_t)nsub_max))) return rc;
+  // the setup work queued on the compute stream (mirror clears) comes first
+  LB_CUDA(cudaEventRecord(plan->events[0], plan->stream));
+  LB_CUDA(cudaStreamWaitEvent(plan->s_in, plan->events[0], 0));
+  LB_CUDA(cudaStreamWaitEvent(plan->s_out, plan->events[0], 0));
+  mark_fft1_valid(plan, a->fft1_float.base, a->fft1_float.size, a->fft1_pa, a->nblocks, false);
+  int done = 0, counter = a->fft1_sumsq_counter, ev = 1;
+  uint32_t sumsq_pa = a->fft1_sumsq_pa;
+  while (done < a->nblocks) {
+    int n = sub;
+    if (want_sumsq && counter > 0 && sub >= avg) n = avg - counter;       // close the open group first
+    if (n > a->nblocks - done) n = a->nblocks - done;
+    // ---- input: the overlap span rides with the first sub-batch only
+    const size_t in_off = (size_t)a->timf1p_ref + (size_t)done * plan->blockbytes + a->timf1.size - (done == 0 ? pre : 0);
+    const size_t in_len = (size_t)n * plan->blockbytes + (done == 0 ? pre : 0);
+    if ((rc = ring_copy_on(plan, plan->s_in, plan->m_timf1.d, a->timf1.base, a->timf1.size, in_off, in_len, true))) return rc;
+    if (want_sumsq && done == 0 && counter > 0)   // a row in progress: bring the host's partial sums over
+      if ((rc = ring_copy_on(plan, plan->s_in, plan->m_sumsq.d, a->fft1_sumsq.base, a->fft1_sumsq.size * 4, (size_t)sumsq_pa * 4, (size_t)plan->N * 4, true))) return rc;
+    if ((rc = ensure_pipeline(plan, (size_t)ev + 2))) return rc;
+    cudaEvent_t e_in = plan->events[ev++], e_k = plan->events[ev++];
+    LB_CUDA(cudaEventRecord(e_in, plan->s_in));
+    LB_CUDA(cudaStreamWaitEvent(plan->stream, e_in, 0));
+    // ---- kernels
+    lb200_fft1_args d = *a;
+    d.timf1.base = plan->m_timf1.d;
+    d.fft1_float.base = plan->m_fft1.d;
+    d.timf1p_ref = (uint32_t)((a->timf1p_ref + (size_t)done * plan->blockbytes) & (a->timf1.size - 1));
+    d.fft1_pa = (uint32_t)((a->fft1_pa + (size_t)done * plan->fft1_block) & (a->fft1_float.size - 1));
+    d.nblocks = n;
+    d.power_rows = want_power ? (float*)plan->m_power.d + (size_t)done * plan->N : nullptr;
+    d.fft1_sumsq.base = want_sumsq ? plan->m_sumsq.d : nullptr;
+    d.fft1_sumsq_pa = sumsq_pa;
+    d.fft1_sumsq_counter = counter;
+    if ((rc = lb200_fft1_dev(plan, &d))) return rc;
+    LB_CUDA(cudaEventRecord(e_k, plan->stream));
+    LB_CUDA(cudaStreamWaitEvent(plan->s_out, e_k, 0));
+    // ---- output
+    if ((rc = ring_copy_on(plan, plan->s_out, plan->m_fft1.d, a->fft1_float.base, a->fft1_float.size * 4, (size_t)d.fft1_pa * 4,
+                           (size_t)plan->fft1_block * n * 4, false))) return rc;
+    if (want_power) {
+      const size_t bytes = sizeof(float) * (size_t)plan->N * n;
+      LB_CUDA(cudaMemcpyAsync(a->power_rows + (size_t)done * plan->N, d.power_rows, bytes, cudaMemcpyDeviceToHost, plan->s_out));
+      plan->d2h += bytes;
+    } else if (want_sumsq) {
+      const size_t rows = ((size_t)counter + n + avg - 1) / avg;           // rows touched, the last may stay open
+      if ((rc = ring_copy_on(plan, plan->s_out, plan->m_sumsq.d, a->fft1_sumsq.base, a->fft1_sumsq.size * 4, (size_t)sumsq_pa * 4,
+                             rows * plan->N * 4, false))) return rc;
+      const int tot = counter + n;
+      sumsq_pa = (uint32_t)((sumsq_pa + (size_t)(tot / avg) * plan->N) & (a->fft1_sumsq.size - 1));
+      counter = tot % avg;
+    }
+    done += n;
   }
+  LB_CUDA(cudaStreamSynchronize(plan->s_out));
   LB_CUDA(cudaStreamSynchronize(plan->stream));
+  if (a->apply_filtercorr) mark_fft1_valid(plan, a->fft1_float.base, a->fft1_float.size, a->fft1_pa, a->nblocks, true);
   return LB200_OK;
 }
 
@@ -600,7 +739,9 @@ extern "C" int lb200_mix1(lb200_plan* plan, const lb200_mix1_args* a)
   // only needs M bins but the blocks are usually already there from lb200_fft1 on this plan)
   if ((rc = ensure_mirror(plan, plan->m_fft1, a->fft1_float.base, a->fft1_float.size * 4))) return rc;
   if ((rc = ensure_mirror(plan, plan->m_timf3, a->timf3_float.base, (size_t)K * 2 * a->timf3_float.size * 4))) return rc;
-  if (!env_int("LB200_MIX1_TRUST_MIRROR", 0))
+  // spectra this plan's own lb200_fft1 produced (filter-corrected, i.e. final) are still in the
+  // mirror; anything else is brought over from the host ring
+  if (env_int("LB200_MIX1_ALWAYS_UPLOAD", 0) || !fft1_mirror_valid(plan, a->fft1_float.base, a->fft1_float.size, a->fft1_px, a->nblocks))
     if ((rc = ring_copy(plan, plan->m_fft1.d, a->fft1_float.base, a->fft1_float.size * 4, (size_t)a->fft1_px * 4,
                         (size_t)plan->fft1_block * a->nblocks * 4, true))) return rc;
   // parked tails of the previous call (mix1.c:188-194): carry samples per selection

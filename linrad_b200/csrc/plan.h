@@ -53,6 +53,8 @@ struct lb200_plan {
   // large-N (four-step) scratch
   float2* d_scratch = nullptr;
   size_t scratch_elems = 0;
+  float* d_powtmp = nullptr;   // small-batch path: per-transform |z|^2 rows
+  size_t powtmp_bytes = 0;
   float2* d_zbuf = nullptr;    // real input: packed spectrum Z of one sub-batch
   size_t zbuf_elems = 0;
   float2* d_Wre = nullptr;     // real input: exp(-i pi k / N), k = 0..N
@@ -70,6 +72,11 @@ struct lb200_plan {
   HostMirror m_timf1, m_fft1, m_sumsq, m_timf3, m_power;
   HostMirror m_wg_sumsq, m_wg_slowsum, m_wg_wsum, m_wg_yfac, m_wg_waterf, m_codec_in, m_codec_out;
   std::map<const void*, size_t> registered;
+  // pipelined host path: copy streams, event pool, validity of the fft1_float mirror per block
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> events;
+  std::vector<uint8_t> fft1_valid;
+  const void* fft1_valid_host = nullptr;
   // counters
   uint64_t launches = 0, h2d = 0, d2h = 0;
   int last_cuda_error = 0;
