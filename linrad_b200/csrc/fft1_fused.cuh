@@ -17,10 +17,10 @@
 //     real gain except on the 16 outermost bins at each end; the gain is folded into the window
 //     table and the edge bins are corrected by their ratio to it.
 //
-// Work decomposition: one CTA owns one averaging group (the wg.fft_avg1num consecutive
-// transforms summed into one fft1_sumsq row, fft1.c:4507-4520) and walks through its transforms
-// and channels in time order, so the row is accumulated on chip in the reference's own order
-// and written exactly once.  While transform b is computed the new timf1 bytes of transform
+// Work decomposition: one CTA owns one channel of one averaging group (the wg.fft_avg1num
+// consecutive transforms summed into one fft1_sumsq row, fft1.c:4507-4520) and walks through its
+// transforms in time order, so the row is accumulated on chip in the reference's own order; with
+// two channels the two CTAs of a group add their shares into the (host-zeroed) row.  While transform b is computed the new timf1 bytes of transform
 // b+1 are pulled into L2 with one TMA bulk prefetch (cp.async.bulk.prefetch.L2).
 #pragma once
 #include "fft32_core.cuh"
@@ -98,29 +98,36 @@ fft1_fused_kernel(const Fft1K p)
   const int c0 = p.power_rows ? 0 : p.counter0;
   const int ngroups = (c0 + p.nblocks + group_size - 1) / group_size;
   const uint32_t span = (uint32_t)N * FRAME;
-  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+  // work item = (averaging group, channel).  The two channels of a group go to neighbouring CTAs:
+  // they read the same timf1 frames at the same time (one DRAM fetch, the second CTA hits L2) and
+  // each writes its own 8-byte half of every output slot; the halves of a 32-byte sector arrive
+  // within microseconds of each other and leave L2 as whole sectors.
+  const int nwork = ngroups * NCH;
+  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int g = w / NCH;
+    const int c = w - g * NCH;
     int b0 = g * group_size - c0;
     int b1 = b0 + group_size;
     if (b0 < 0) b0 = 0;
     if (b1 > p.nblocks) b1 = p.nblocks;
     for (int b = b0; b < b1; b++) {
       const uint32_t start = (p.ref0 + (uint32_t)b * p.blockbytes - p.pre_bytes) & p.ring_mask;
-      if (t == 0) {
-        // what this CTA reads next: the new bytes of b+1, or the whole span of its next group
+      if (t == 0 && c == 0) {
+        // what this CTA (and its sibling) reads next: the new bytes of b+1, or the whole span of
+        // its next group
         if (b + 1 < b1) {
           l2_prefetch_span(p.timf1, p.ring_mask, start + span, p.blockbytes);
         } else {
-          const int gn = g + gridDim.x;
+          const int gn = (w + (int)gridDim.x) / NCH;
           int bn = gn * group_size - c0;
           if (bn < 0) bn = 0;
           if (gn < ngroups && bn < p.nblocks)
             l2_prefetch_span(p.timf1, p.ring_mask, p.ref0 + (uint32_t)bn * p.blockbytes - p.pre_bytes, span);
         }
       }
-      float* outb = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask) + (size_t)t * MM;
+      float* outb = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask) + (size_t)t * MM + 2 * c;
       const bool wraps = start + span > p.ring_mask + 1u;
-#pragma unroll 1
-      for (int c = 0; c < NCH; c++) {
+      {
         float2 v[32];
         // ---- load, int -> float, window (sign and, for FC_FOLDED, gain are in the table)
         if (!wraps) {
@@ -174,7 +181,7 @@ fft1_fused_kernel(const Fft1K p)
         radix32_gen(v, wb);
         __syncthreads();                         // exchange buffer is free for the next transform
         // ---- epilogue: bin k = t + T*e; v holds (im, re) of the output value
-        const bool first = (b == b0 && c == 0);
+        const bool first = (b == b0);
         float* ac = acc + t;
         if (FC == FC_FOLDED) {                   // host guarantees the full bin range here
           if (t < 16) {                          // bins 0..15 and N-16..N-1 carry the taper of fft1.c:4703-4722
@@ -208,38 +215,17 @@ fft1_fused_kernel(const Fft1K p)
             }
           }
         }
-        if (NCH == 1) {
-          float* oc = outb;
 #pragma unroll
-          for (int e = 0; e < 32; e++) lb_store_stream(reinterpret_cast<float2*>(oc + (size_t)e * (T * MM)), make_float2(v[e].y, v[e].x));
-        } else {
-          // two channels share every 16-byte output slot: channel 0 waits in an L2-resident
-          // scratch row of this CTA so that the slot is written once, whole (a half-written
-          // 32-byte sector costs a DRAM fill read)
-          float2* sc = p.scratch2 + (size_t)blockIdx.x * N + t;
-          if (c == 0) {
-#pragma unroll
-            for (int e = 0; e < 32; e++) sc[e * T] = make_float2(v[e].y, v[e].x);
-          } else {
-#pragma unroll
-            for (int e0 = 0; e0 < 32; e0 += 8) {
-              float2 o0[8];
-#pragma unroll
-              for (int e = 0; e < 8; e++) o0[e] = lb_load_last(sc + (e0 + e) * T);
-#pragma unroll
-              for (int e = 0; e < 8; e++)
-                lb_store_stream(reinterpret_cast<float4*>(outb + (size_t)(e0 + e) * (T * MM)), make_float4(o0[e].x, o0[e].y, v[e0 + e].y, v[e0 + e].x));
-              asm volatile("" ::: "memory");     // keep the next chunk's loads from being hoisted (registers)
-            }
-          }
-        }
+        for (int e = 0; e < 32; e++) lb_store_stream(reinterpret_cast<float2*>(outb + (size_t)e * (T * MM)), make_float2(v[e].y, v[e].x));
       }
       if (p.power_rows && FC != FC_RAW) {
 #pragma unroll
         for (int e = 0; e < 32; e++) {
           const int k = t + T * e;
           const bool inr = (k >= p.first_point) && (k <= p.last_point);
-          p.power_rows[(size_t)b * N + k] = inr ? acc[k] : 0.0f;
+          // two channels: the host has zeroed the row, each channel's CTA adds its share
+          if (NCH == 1) p.power_rows[(size_t)b * N + k] = inr ? acc[k] : 0.0f;
+          else if (inr) atomicAdd(&p.power_rows[(size_t)b * N + k], acc[k]);
         }
       }
     }
@@ -250,9 +236,13 @@ fft1_fused_kernel(const Fft1K p)
       for (int e = 0; e < 32; e++) {
         const int k = t + T * e;
         if (k >= p.first_point && k <= p.last_point) {
-          float val = acc[k];
-          if (continuing) val = row[k] + val;
-          row[k] = val;
+          if (NCH == 1) {
+            float val = acc[k];
+            if (continuing) val = row[k] + val;
+            row[k] = val;
+          } else {
+            atomicAdd(&row[k], acc[k]);          // row zeroed by the host unless it is being continued
+          }
         }
       }
     }

@@ -184,10 +184,6 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
         if ((rc = upload(plan, (void**)&plan->d_edge, edge.data(), sizeof(float2) * 32))) return fail(rc);
       }
     }
-    if (plan->nch == 2) {
-      const size_t rows = (size_t)plan->sm_count * (512 / (N / 32)) * 4;   // grid cap incl. LB200_GRID_WAVES <= 4
-      if (cudaMalloc((void**)&plan->d_scratch2, rows * N * sizeof(float2)) != cudaSuccess) return fail(LB200_ERR_CUDA);
-    }
     if (cfg->fft1_n > 10) {
       const int R0 = N >> 10;
       std::vector<float4> tab((size_t)16 * R0);
@@ -375,11 +371,28 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
     k.wtab = fc == FC_FOLDED ? plan->d_wsign_g : plan->d_wsign;
     k.edge = plan->d_edge;
     k.tab1 = plan->d_tab1;
-    k.scratch2 = plan->d_scratch2;
     fft1_small_launch_t fn = lb_get_fft1_fused(plan->cfg.fft1_n, plan->fmt, fc, &threads, &smem);
     if (!fn) return LB200_ERR_UNSUPPORTED;
     const int ngroups = (k.counter0 + k.nblocks + group - 1) / group;
-    int grid = ngroups;
+    if (plan->nch == 2 && fc != FC_RAW) {
+      // the two channels of a group are separate CTAs that ADD their power into the row
+      if (k.power_rows) {
+        LB_CUDA(cudaMemsetAsync(k.power_rows, 0, sizeof(float) * (size_t)plan->N * k.nblocks, plan->stream));
+      } else if (k.sumsq) {
+        const int g0 = k.counter0 > 0 ? 1 : 0;                       // a row being continued keeps its partial sums
+        size_t off = (k.sumsq_pa + (size_t)g0 * plan->N) & k.sumsq_mask;
+        size_t len = (size_t)(ngroups - g0) * plan->N;
+        const size_t size = (size_t)k.sumsq_mask + 1;
+        while (len > 0) {                                            // at most two pieces: the rows are consecutive on the ring
+          size_t n = size - off;
+          if (n > len) n = len;
+          LB_CUDA(cudaMemsetAsync(k.sumsq + off, 0, sizeof(float) * n, plan->stream));
+          len -= n;
+          off = 0;
+        }
+      }
+    }
+    int grid = ngroups * plan->nch;
     int waves = env_int("LB200_GRID_WAVES", 1);
     if (waves < 1) waves = 1;
     if (waves > 4) waves = 4;
