@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblinrad_b200.so")
+LIB_PATH = os.environ.get("LB200_LIB") or os.path.join(_HERE, "liblinrad_b200.so")   # LB200_LIB: A/B builds of the same ABI
 
 LB200_ABI_VERSION = 1
 ERR = {0: "OK", 3100: "NO_DEVICE", 3101: "CUDA", 3102: "BAD_CONFIG", 3103: "UNSUPPORTED", 3104: "BAD_ARG",

@@ -21,6 +21,13 @@
 
 namespace lb {
 
+// tile widths (log2): adjacent columns per CTA in step A, adjacent rows per CTA in step B.  Eight
+// float2 = 64 bytes = two full sectors per run; small tiles keep several CTAs resident per SM so
+// that the load, exchange and store phases of different CTAs overlap.
+#ifndef LB_LARGE_LT
+#define LB_LARGE_LT 3
+#endif
+
 struct Fft1LargeK {
   Fft1K k;               // same parameter block as the single-CTA kernel
   float2* scratch;       // Y: [slot][channel][N]
@@ -35,7 +42,7 @@ struct Fft1LargeK {
 
 // ------------------------------------------------------------------------------ step A
 template <int LOG2N1, int LOG2N2, int LOG2E, int LOG2TA, int FMT>
-__global__ void __launch_bounds__(1 << (LOG2N1 - LOG2E + LOG2TA))
+__global__ void __launch_bounds__(1 << (LOG2N1 - LOG2E + LOG2TA), (1 << (LOG2N1 - LOG2E + LOG2TA)) <= 256 ? 3 : 1)
 fft1_large_cols_kernel(const Fft1LargeK q)
 {
   using P = Plan<LOG2N1, LOG2E>;
@@ -92,7 +99,7 @@ fft1_large_cols_kernel(const Fft1LargeK q)
 
 // ------------------------------------------------------------------------------ step B
 template <int LOG2N1, int LOG2N2, int LOG2E, int LOG2TB, int NCH>
-__global__ void __launch_bounds__(1 << (LOG2N2 - LOG2E + LOG2TB))
+__global__ void __launch_bounds__(1 << (LOG2N2 - LOG2E + LOG2TB), (1 << (LOG2N2 - LOG2E + LOG2TB)) <= 256 ? 3 : 1)
 fft1_large_rows_kernel(const Fft1LargeK q)
 {
   using P = Plan<LOG2N2, LOG2E>;
@@ -163,7 +170,7 @@ fft1_large_rows_kernel(const Fft1LargeK q)
             if (b == b0 && c == 0) acc[o] = pw;
             else acc[o] += pw;
           }
-          *reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c) = ov;
+          __stcs(reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c), ov);
         }
       }
       if (p.power_rows && p.fc_mode != 0) {

@@ -106,7 +106,7 @@ cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k)
   q.Wn2 = plan->d_Wn2;
   q.Wbig = plan->d_Wn;
   large_fn_t fn = large_fn(plan->fmt);
-  const int tilesA = (1 << ln2) / 16, tilesB = (1 << ln1) / 16;
+  const int tilesA = (1 << ln2) >> LB_LARGE_LT, tilesB = (1 << ln1) >> LB_LARGE_LT;
   for (int g0 = 0; g0 < ngroups; g0 += gps) {
     const int g1 = g0 + gps < ngroups ? g0 + gps : ngroups;
     int b_first = g0 * group - c0;
@@ -119,7 +119,7 @@ cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k)
     q.g_count = g1 - g0;
     int gridA = q.b_count * nch * tilesA;
     int gridB = q.g_count * tilesB;
-    const int cap = plan->sm_count * 8;
+    const int cap = plan->sm_count * 16;
     if (gridA > cap) gridA = cap;
     if (gridB > cap) gridB = cap;
     cudaError_t e = fn(log2n, 0, q, gridA, plan->stream);
@@ -214,7 +214,7 @@ cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k)
       q.b_count = b_count;
       q.g_first = b_first;          // groups of one transform (avg1num = 1, counter0 = 0)
       q.g_count = b_count;
-      const int tilesA = (1 << ln2) / 16, tilesB = (1 << ln1) / 16;
+      const int tilesA = (1 << ln2) >> LB_LARGE_LT, tilesB = (1 << ln1) >> LB_LARGE_LT;
       int gridA = b_count * nch * tilesA, gridB = b_count * tilesB;
       const int cap = plan->sm_count * 8;
       if (gridA > cap) gridA = cap;

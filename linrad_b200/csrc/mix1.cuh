@@ -45,6 +45,18 @@ struct Mix1K {
   int mode;               // 0 none, 1 sin^2 (Mi==Mn), 2 crossover
 };
 
+// sin/cos of a mixer phase (the reference takes sin()/cos() in double of the float phase,
+// mix1.c:147-148): two-constant reduction to [-pi, pi], then the SFU approximations, absolute
+// error below 5e-7 -- far inside the 2e-5 baseband tolerance.
+LB_D void mix1_sincos(float x, float* s, float* c)
+{
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831854820251465f, x);           // float(2 pi)
+  r = fmaf(-k, -1.7484555e-7f, r);                      // 2 pi - float(2 pi)
+  *s = __sinf(r);
+  *c = __cosf(r);
+}
+
 // taper index of do_mix1 (mix1.c:113-135 / 455-491, including the doubled factors of the
 // two-channel loop at i==M-1 and i==M/2)
 template <int NCH>
@@ -139,14 +151,17 @@ mix1_kernel(const Mix1K p)
       }
       // ---- exact float phase chains for this transform (mix1.c:143-153,164-186)
       if (emit && job.point >= 0) {
-        const int chunk_t = (nt + LANE_THREADS - 1) / LANE_THREADS;
+        // one closed-form jump per 16 samples (it costs ~300 instructions), then plain float adds
+        int chunk_t = (nt + LANE_THREADS - 1) / LANE_THREADS;
+        if (chunk_t < 16) chunk_t = 16;
         int i0 = lt * chunk_t;
         if (i0 < nt) {
           float x = lb_phase_advance(job.t1, job.t2, i0);
           int i1 = i0 + chunk_t; if (i1 > nt) i1 = nt;
           for (int i = i0; i < i1; i++) { ph_t[i] = x; x = lb_float_add(x, job.t2); }
         }
-        const int chunk_r = (nr + LANE_THREADS - 1) / LANE_THREADS;
+        int chunk_r = (nr + LANE_THREADS - 1) / LANE_THREADS;
+        if (chunk_r < 16 && nr > 0) chunk_r = 16;
         i0 = lt * chunk_r;
         if (chunk_r > 0 && i0 < nr) {
           float x = lb_phase_advance(job.r1, job.r2, i0);
@@ -165,9 +180,9 @@ mix1_kernel(const Mix1K p)
         } else {
           for (int s = lt; s < nt; s += LANE_THREADS) {
             float st, ct;
-            sincosf(ph_t[s], &st, &ct);
+            mix1_sincos(ph_t[s], &st, &ct);
             float sr = 0.f, cr = 1.f;
-            if (s < nr) sincosf(ph_r[s], &sr, &cr);
+            if (s < nr) mix1_sincos(ph_r[s], &sr, &cr);
             const uint32_t o = (job.dst + (uint32_t)s * MM) & p.timf3_mask;
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
