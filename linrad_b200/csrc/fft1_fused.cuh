@@ -59,6 +59,27 @@ LB_D void lb_store_stream(float4* p, float4 v) { *p = v; }
 LB_D float2 lb_load_last(const float2* p) { return *p; }
 #endif
 
+// Split-phase CTA barrier on an mbarrier in shared memory: a thread ARRIVES as soon as it has
+// finished reading an exchange buffer and only WAITS right before it overwrites that buffer, so
+// the write-after-read hand-over costs no stall when the other warps are already past it.
+LB_D void mbar_init(uint64_t* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+LB_D void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+LB_D void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+
 template <int FMT>
 LB_D float2 cvt_iq(const uint8_t* p)
 {
@@ -92,6 +113,14 @@ fft1_fused_kernel(const Fft1K p)
 #pragma unroll
   for (int j = 0; j < 5; j++) wb[j] = p.Wn[t << j];
   const float* wtab = p.wtab + t;
+  __shared__ uint64_t war_bar[2];            // [0]: exchange 1 has been read, [1]: exchange 2 (or the only one) has been read
+  if (t == 0) {
+    mbar_init(&war_bar[0], T);
+    mbar_init(&war_bar[1], T);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t par0 = 0, par1 = 0;
+  bool first_xch = true;
   __syncthreads();
 
   const int group_size = p.power_rows ? 1 : p.avg1num;
@@ -158,10 +187,13 @@ fft1_fused_kernel(const Fft1K p)
         }
         // ---- transform
         pass0<P::R0>(v);
+        if (!first_xch) { mbar_wait(&war_bar[1], par1); par1 ^= 1; }   // the previous transform's last reads are done
+        first_xch = false;
         exch1_store<LOG2N>(v, xch, t);
         __syncthreads();
         exch1_load<LOG2N>(v, xch, t);
         if (P::NPASS == 3) {
+          mbar_arrive(&war_bar[0]);
           {
             float2 w[32];
             const float4* tp = tab1 + (t & (P::R0 - 1));
@@ -173,13 +205,14 @@ fft1_fused_kernel(const Fft1K p)
             }
             radix32_table(v, w);
           }
-          __syncthreads();                       // everybody has read exchange 1
+          mbar_wait(&war_bar[0], par0);          // everybody has read exchange 1
+          par0 ^= 1;
           exch2_store<LOG2N>(v, xch, t);
           __syncthreads();
           exch2_load<LOG2N>(v, xch, t);
         }
+        mbar_arrive(&war_bar[1]);                // my reads of the exchange buffer are done
         radix32_gen(v, wb);
-        __syncthreads();                         // exchange buffer is free for the next transform
         // ---- epilogue: bin k = t + T*e; v holds (im, re) of the output value
         const bool first = (b == b0);
         float* ac = acc + t;
