@@ -34,7 +34,7 @@ IQ, DW, TWO = sizing.IQ_DATA, sizing.DWORD_INPUT, sizing.TWO_CHANNELS
 WORKLOADS = {
     # name: (PathSetup kwargs, reference fft_cntrl row, selections (bins), batch per step)
     "cfg1": (dict(input_mode=IQ, rf_channels=1, ad_speed=96000, fft1_n=13, mix1_red_n=4), 6, [3000.37], 5920),
-    "cfg2": (dict(input_mode=IQ | DW | TWO, rf_channels=2, ad_speed=192000, fft1_n=14, mix1_red_n=4), 7, [6000.74], 740),
+    "cfg2": (dict(input_mode=IQ | DW | TWO, rf_channels=2, ad_speed=192000, fft1_n=14, mix1_red_n=4), 7, [6000.74], 2960),
     "cfg3": (dict(input_mode=0, rf_channels=1, ad_speed=2400000, fft1_n=15, mix1_red_n=5), 2, [], 740),
     "cfg4": (dict(input_mode=IQ, rf_channels=1, ad_speed=20000000, fft1_n=18, mix1_red_n=6), 20,
              [8192.0 * (1 + c) + 0.25 * c for c in range(16)], 60),

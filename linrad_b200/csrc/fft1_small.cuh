@@ -67,6 +67,7 @@ struct Fft1K {
   float2* zbuf;
   int zb_first;
   const float2* Wre;        // exp(-i pi k / N), k = 0..N
+  uint32_t stagger_ns;      // fft1_fused_kernel: CTAs start spread over this many ns (0 = together)
 };
 
 template <int FMT>

@@ -398,6 +398,12 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
     if (waves > 4) waves = 4;
     const int cap = plan->sm_count * (512 / threads) * waves;
     if (grid > cap) grid = cap;
+    // long launches: spread the CTAs' start times so that their store phases do not coincide
+    k.stagger_ns = 0;
+    {
+      const long per_cta = ((long)ngroups * plan->nch * group + grid - 1) / grid;      // transforms per CTA
+      if (per_cta >= 8) k.stagger_ns = (uint32_t)env_int("LB200_STAGGER_NS", 0);
+    }
     LB_CUDA(fn(k, grid, plan->stream));
     plan->launches++;
     return fold();
