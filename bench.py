@@ -38,12 +38,17 @@ WORKLOADS = {
     "cfg3": (dict(input_mode=0, rf_channels=1, ad_speed=2400000, fft1_n=15, mix1_red_n=5), 2, [], 740),
     "cfg4": (dict(input_mode=IQ, rf_channels=1, ad_speed=20000000, fft1_n=18, mix1_red_n=6), 20,
              [8192.0 * (1 + c) + 0.25 * c for c in range(16)], 60),
+    # configs[4]: 64 independent cfg4 streams on 8 GPUs = 8 streams per GPU (any --gpus N runs 8 per GPU)
+    "cfg5": (dict(input_mode=IQ, rf_channels=1, ad_speed=20000000, fft1_n=18, mix1_red_n=6), 20,
+             [8192.0 * (1 + c) + 0.25 * c for c in range(16)], 60),
 }
+STREAMS_PER_GPU = {"cfg5": 8}
 WORKLOAD_TEXT = {
     "cfg1": "configs[0]: 1-ch complex IQ 96 kS/s int16, fft1 N=8192 sin^2 window, mix1 M=512 one signal",
     "cfg2": "configs[1]: 2-ch complex IQ 192 kS/s 24-bit (int32), fft1 N=16384 sin^2 window, mix1 M=1024 one signal",
     "cfg3": "configs[2]: real 1-ch int16 2.4 MS/s, fft1_re N=32768 bins (65536 reals), power-spectrum averaging, no mix1",
     "cfg4": "configs[3]: 1-ch complex IQ 20 MS/s int16, fft1 N=262144 four-step, mix1 M=4096 x 16 selections",
+    "cfg5": "configs[4]: 8 independent 20 MS/s IQ streams per GPU (64 on 8 GPUs), each as configs[3]; per-GPU sum + all-reduce of the averaged power spectra",
 }
 
 
@@ -54,6 +59,7 @@ CPU_OVERRIDE = {
     "cfg4": (dict(input_mode=IQ, rf_channels=1, ad_speed=20000000, fft1_n=16, mix1_red_n=4), 6,
              "reference float path stops at N=65536: timed at N=65536 (version 6), M=4096, 16 selections"),
 }
+CPU_OVERRIDE["cfg5"] = CPU_OVERRIDE["cfg4"]
 
 
 def cpu_workload(name):
@@ -283,46 +289,60 @@ def main():
     plan = api.Plan(s, device=local_rank)
     stream = torch.cuda.ExternalStream(plan.stream, device=dev)
 
-    # ---- device-resident rings (same layouts as Linrad's host rings) -------------------------
-    raw = make_timf1(s.input_mode, C, N, 64, s.fft1_new_points, seed=100 + rank)
-    raw_bytes = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+    # ---- device-resident rings (same layouts as Linrad's host rings), one set per receiver stream
+    S = STREAMS_PER_GPU.get(args.workload, 1)
     timf1_bytes = pow2_at_least((B + 2) * s.timf1_blockbytes)
-    reps = (B * s.timf1_blockbytes + raw_bytes.size - 1) // raw_bytes.size
-    host_in = np.tile(raw_bytes, reps)[: B * s.timf1_blockbytes]
-    d_timf1 = torch.zeros(timf1_bytes, dtype=torch.uint8, device=dev)
-    d_timf1[: host_in.size].copy_(torch.from_numpy(host_in))
     fft1_floats = pow2_at_least(B * s.fft1_block)
-    d_fft1 = torch.empty(fft1_floats, dtype=torch.float32, device=dev)
     rows = (B + s.avg1num - 1) // s.avg1num
     sumsq_floats = pow2_at_least((rows + 1) * N)
-    d_sumsq = torch.zeros(sumsq_floats, dtype=torch.float32, device=dev)
     timf3_size = pow2_at_least((B + 2) * s.timf3_block + 2 * C * s.mix1_size)
     nsel = len(selbins)
-    d_timf3 = torch.zeros(max(nsel, 1) * 2 * timf3_size, dtype=torch.float32, device=dev)
-    states = api.new_states([s.selfreq_for_bin(b) for b in selbins])
+    d_timf1, d_fft1, d_sumsq, d_timf3, states = [], [], [], [], []
+    host_in = None
+    for si in range(S):
+        raw = make_timf1(s.input_mode, C, N, 64, s.fft1_new_points, seed=100 + rank * S + si)
+        raw_bytes = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+        reps = (B * s.timf1_blockbytes + raw_bytes.size - 1) // raw_bytes.size
+        hin = np.tile(raw_bytes, reps)[: B * s.timf1_blockbytes]
+        if host_in is None:
+            host_in = hin
+        t1 = torch.zeros(timf1_bytes, dtype=torch.uint8, device=dev)
+        t1[: hin.size].copy_(torch.from_numpy(hin))
+        d_timf1.append(t1)
+        d_fft1.append(torch.empty(fft1_floats, dtype=torch.float32, device=dev))
+        d_sumsq.append(torch.zeros(sumsq_floats, dtype=torch.float32, device=dev))
+        d_timf3.append(torch.zeros(max(nsel, 1) * 2 * timf3_size, dtype=torch.float32, device=dev))
+        states.append(api.new_states([s.selfreq_for_bin(b) for b in selbins]))
+    d_specsum = torch.zeros(rows * N, dtype=torch.float32, device=dev) if (S > 1 or world > 1) else None
     torch.cuda.synchronize()
 
     ev_pairs = []
 
     def step(record=False):
         # block 0 of the batch starts at byte 0; its overlap half is the ring's tail (zeros/old data)
-        if record:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-        plan.fft1_dev(timf1=d_timf1.data_ptr(), timf1_bytes=timf1_bytes, ref=0, nblocks=B, fft1=d_fft1.data_ptr(),
-                      fft1_floats=fft1_floats, fft1_pa=0, apply_fc=True, sumsq=d_sumsq.data_ptr(),
-                      sumsq_floats=sumsq_floats, sumsq_pa=0, counter=0)
-        if record:
-            e1.record(stream)
-            ev_pairs.append((e0, e1))
-        if nsel:
-            plan.mix1_dev(fft1=d_fft1.data_ptr(), fft1_floats=fft1_floats, fft1_px=0, nblocks=B, states=states,
-                          timf3=d_timf3.data_ptr(), timf3_floats=timf3_size, timf3_pa=0)
-        if world > 1:
-            # the averaged power spectrum is the only thing that crosses GPUs
+        for si in range(S):
+            if record:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            plan.fft1_dev(timf1=d_timf1[si].data_ptr(), timf1_bytes=timf1_bytes, ref=0, nblocks=B, fft1=d_fft1[si].data_ptr(),
+                          fft1_floats=fft1_floats, fft1_pa=0, apply_fc=True, sumsq=d_sumsq[si].data_ptr(),
+                          sumsq_floats=sumsq_floats, sumsq_pa=0, counter=0)
+            if record:
+                e1.record(stream)
+                ev_pairs.append((e0, e1))
+            if nsel:
+                plan.mix1_dev(fft1=d_fft1[si].data_ptr(), fft1_floats=fft1_floats, fft1_px=0, nblocks=B, states=states[si],
+                              timf3=d_timf3[si].data_ptr(), timf3_floats=timf3_size, timf3_pa=0)
+        if d_specsum is not None:
+            # the averaged power spectrum is the only thing that crosses GPUs:
+            # per-GPU sum over its streams, then one all-reduce
             with torch.cuda.stream(stream):
-                dist.all_reduce(d_sumsq[: rows * N])
+                d_specsum.copy_(d_sumsq[0][: rows * N])
+                for si in range(1, S):
+                    d_specsum.add_(d_sumsq[si][: rows * N])
+                if world > 1:
+                    dist.all_reduce(d_specsum)
 
     for _ in range(args.warmup):
         step()
@@ -350,7 +370,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     spt = samples_per_transform(s)
-    samples = B * spt * args.steps * world
+    samples = B * S * spt * args.steps * world
     value = samples / (ms * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (fft1_small_kernel) -----------------------------------
@@ -362,10 +382,19 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = ab["fft1"] * B / (fft1_ms * 1e-3) / 1e9
+    # DRAM bytes of the same launch from the committed `ncu --set full` capture (per transform,
+    # scaled to this launch's batch); null when no capture exists for the workload
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get("cfg4" if args.workload == "cfg5" else args.workload)
+        if tj:
+            traffic = tj["dram_bytes_per_transform"] * B
+            traffic_src = tj["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": kernel_name(s), "kernel_ms": fft1_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name(s), "kernel_ms": fft1_ms,
                 "algorithmic_bytes_per_launch": ab["fft1"] * B, "peak_source": peak_src,
-                "whole_step_frac": ab["total"] * B * args.steps / (ms * 1e-3) / 1e9 / peak}
+                "whole_step_frac": ab["total"] * B * S * args.steps / (ms * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the host-buffer C ABI ------------------------------------------------
     e2e = None
@@ -419,9 +448,10 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[args.workload], "transforms_per_step_per_gpu": B,
-                       "l2": f"working set per step {(B * (s.timf1_blockbytes + 4 * s.fft1_block)) >> 20} MiB > 126 MiB L2, no flush needed",
+                       "l2": f"working set per step {(S * B * (s.timf1_blockbytes + 4 * s.fft1_block)) >> 20} MiB > 126 MiB L2, no flush needed",
                        "mix1_selections": nsel, "fft_avg1num": s.avg1num,
-                       "parallelism": f"{world} independent receiver streams, one per GPU"},
+                       "streams_per_gpu": S,
+                       "parallelism": f"{world * S} independent receiver streams, {S} per GPU; only the averaged power spectrum is all-reduced"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clk.summary(),
         }

@@ -92,108 +92,58 @@ LB_D float2 cvt_iq(const uint8_t* p)
   }
 }
 
-// ---- asynchronous staging of the raw timf1 frames through the exchange buffer ----------------
-// The slots of the exchange buffer a thread reads in the LAST exchange of a transform are its own
-// (nobody else reads or writes them until the next transform's first exchange store).  Right after
-// that read the thread issues cp.async (LDGSTS) copies of its 32 raw frames of the NEXT transform
-// into those very slots: the global-load latency then runs under the last radix-32 pass, the
-// epilogue and the stores of the current transform, and costs neither registers nor LSU stalls.
-// 8-byte channels (int32 I/Q) use one slot per frame, 4-byte channels (int16 I/Q) share a slot
-// between frames e and e+1.
-LB_D void cp_async_8(void* smem, const void* gmem)
+// ---- asynchronous output: results leave through the exchange buffer and the TMA unit ---------
+// STG costs the SM one 32-byte sector per clock (measured: 4.2 cycles per 128-byte line), the
+// issuing warps stall on the LSU queue meanwhile, and a two-channel transform fills only half of
+// every sector (8 bytes of each 16-byte [re1,im1,re2,im2] slot).  So once the last exchange has
+// been read the threads write their results into the exchange buffer in the layout of fft1_float
+// and one thread hands the block to the TMA unit (cp.async.bulk shared -> global).
+// The copy drains while the CTA loads and starts the next transform.  Two-channel formats keep
+// direct stores (see the comment at the store).
+LB_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+LB_D void bulk_store(void* gdst, const void* ssrc, uint32_t bytes)
 {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 }
-LB_D void cp_async_4(void* smem, const void* gmem)
-{
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-LB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-LB_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+LB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+LB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+LB_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// float2 slot index (relative to the thread's base slot) of element e in the last exchange's load pattern
-template <int LOG2N>
-LB_HD constexpr int last_xch_stride()
+// |z|^2 of elements [E0, E1) -> fft1_sumsq row / power row, after the filtercorr multiply (fft1_c,
+// fft1.c:4115-4200).  v holds (im, re).
+template <int FC, int NCH, int T, int E0, int E1>
+LB_D void fused_epilogue(float2 (&v)[32], const Fft1K& p, float* prow, bool plain, bool rows, int t, int c)
 {
-  using P = Plan32<LOG2N>;
-  return P::NPASS == 3 ? (P::T + P::T / 32) : (P::T + (P::T >> P::SH1) * 2);
-}
-template <int LOG2N>
-LB_HD int last_xch_base(int t)
-{
-  using P = Plan32<LOG2N>;
-  return P::NPASS == 3 ? pad1(t) : pad2<P::SH1>(t);
-}
-
-template <int LOG2N, int FMT>
-LB_D void raw_issue(float2* slot0, const uint8_t* ring, uint32_t mask, uint32_t start, int t, int c)
-{
-  using P = Plan32<LOG2N>;
-  constexpr int T = P::T;
-  constexpr int FRAME = FmtInfo<FMT>::FRAME, NCH = FmtInfo<FMT>::NCH, CHB = FRAME / NCH;
-  constexpr int STR = last_xch_stride<LOG2N>();
-  const uint32_t span = (uint32_t)P::N * FRAME;
-  if (start + span <= mask + 1u) {
-#if defined(LB_EXP) && (LB_EXP & 8)
-    const uint8_t* srcx = ring + start + (uint32_t)t * CHB + c * (P::N * CHB);
+  constexpr int MM = 2 * NCH;
+  if (FC == FC_FOLDED) {                     // host guarantees the full bin range here
+    if (prow) {
+      if (plain) {
 #pragma unroll
-    for (int e = 0; e < 32; e++) {
-      if (CHB == 8) cp_async_8(slot0 + e * STR, srcx + (size_t)e * (T * CHB));
-      else cp_async_4(reinterpret_cast<uint32_t*>(slot0 + (e >> 1) * STR) + (e & 1), srcx + (size_t)e * (T * CHB));
+        for (int e = E0; e < E1; e++) prow[e * T] = fmaf(v[e].x, v[e].x, v[e].y * v[e].y);
+      } else {
+#pragma unroll
+        for (int e = E0; e < E1; e++) atomicAdd(prow + e * T, fmaf(v[e].x, v[e].x, v[e].y * v[e].y));
+      }
     }
-    cp_async_commit();
-    return;
-#endif
-    const uint8_t* src = ring + start + (uint32_t)t * FRAME + c * CHB;
+  } else if (FC == FC_TABLE) {
+    // general path: full filtercorr table and/or a limited bin range (fft1.c:4115-4131)
+    const float* fcp = p.filtercorr + (size_t)t * MM + 2 * c;
 #pragma unroll
-    for (int e = 0; e < 32; e++) {
-      if (CHB == 8) cp_async_8(slot0 + e * STR, src + (size_t)e * (T * FRAME));
-      else cp_async_4(reinterpret_cast<uint32_t*>(slot0 + (e >> 1) * STR) + (e & 1), src + (size_t)e * (T * FRAME));
-    }
-  } else {
-#pragma unroll
-    for (int e = 0; e < 32; e++) {
-      const uint32_t off = (start + (uint32_t)(t + T * e) * FRAME) & mask;
-      if (CHB == 8) cp_async_8(slot0 + e * STR, ring + off + c * CHB);
-      else cp_async_4(reinterpret_cast<uint32_t*>(slot0 + (e >> 1) * STR) + (e & 1), ring + off + c * CHB);
-    }
-  }
-  cp_async_commit();
-}
-
-// raw frames -> float, window (sign and, for FC_FOLDED, gain are in the table), conj/direction swap
-template <int LOG2N, int FMT>
-LB_D void raw_take(float2 (&v)[32], const float2* slot0, const float* wtab, int direction)
-{
-  using P = Plan32<LOG2N>;
-  constexpr int T = P::T;
-  constexpr int FRAME = FmtInfo<FMT>::FRAME, NCH = FmtInfo<FMT>::NCH, CHB = FRAME / NCH;
-  constexpr int STR = last_xch_stride<LOG2N>();
-  if (CHB == 8) {
-#pragma unroll
-    for (int e = 0; e < 32; e++) {
-      const int2 r = *reinterpret_cast<const int2*>(slot0 + e * STR);
-      v[e] = make_float2((float)r.x, (float)r.y);
-    }
-  } else {
-#pragma unroll
-    for (int h = 0; h < 16; h++) {
-      const uint2 r = *reinterpret_cast<const uint2*>(slot0 + h * STR);
-      v[2 * h] = make_float2((float)(short)(r.x & 0xffffu), (float)(short)(r.x >> 16));
-      v[2 * h + 1] = make_float2((float)(short)(r.y & 0xffffu), (float)(short)(r.y >> 16));
-    }
-  }
-  if (direction > 0) {
-#pragma unroll
-    for (int e = 0; e < 32; e++) {
-      const float w = wtab[e * T];
-      v[e] = make_float2(v[e].y * -w, v[e].x * w);
-    }
-  } else {
-#pragma unroll
-    for (int e = 0; e < 32; e++) {
-      const float w = wtab[e * T];
-      v[e] = make_float2(v[e].x * w, v[e].y * -w);
+    for (int e = E0; e < E1; e++) {
+      const int k = t + T * e;
+      if (k >= p.first_point && k <= p.last_point) {
+        const float2 f = *reinterpret_cast<const float2*>(fcp + (size_t)e * (T * MM));
+        const float re = v[e].y * f.x - v[e].x * f.y;
+        const float im = v[e].x * f.x + v[e].y * f.y;
+        v[e] = make_float2(im, re);
+        const float pw = re * re + im * im;
+        if (prow) {
+          if (plain) prow[e * T] = pw;
+          else atomicAdd(prow + e * T, pw);
+        }
+      } else if (rows && NCH == 1) {
+        prow[e * T] = 0.0f;
+      }
     }
   }
 }
@@ -205,7 +155,8 @@ fft1_fused_kernel(const Fft1K p)
   using P = Plan32<LOG2N>;
   constexpr int N = P::N, T = P::T;
   constexpr int FRAME = FmtInfo<FMT>::FRAME, NCH = FmtInfo<FMT>::NCH, MM = 2 * NCH;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int CHB = FRAME / NCH;                         // bytes of one channel's IQ pair
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* xch = reinterpret_cast<float2*>(smem_raw);
   float4* tab1 = reinterpret_cast<float4*>(smem_raw + sizeof(float2) * P::XCH);
   float* wsm = reinterpret_cast<float*>(smem_raw + sizeof(float2) * P::XCH + sizeof(float4) * P::TAB1);
@@ -220,26 +171,20 @@ fft1_fused_kernel(const Fft1K p)
 #pragma unroll
   for (int j = 0; j < 5; j++) wb[j] = p.Wn[t << j];
   const float* wtab = wsm + t;
-  __shared__ uint64_t war_bar[2];            // [0]: exchange 1 has been read, [1]: the staged raw frames have been read
+  // split-phase barriers (arrive when done with a buffer, wait right before it is overwritten):
+  // [0] exchange 1 has been read, [1] the last exchange has been read, [2] a staging round has
+  // been written (consumer: thread 0), [3] the TMA unit has read the staged round (producer: thread 0)
+  __shared__ uint64_t bars[4];
   if (t == 0) {
-    mbar_init(&war_bar[0], T);
-    mbar_init(&war_bar[1], T);
+    mbar_init(&bars[0], T);
+    mbar_init(&bars[1], T);
+    mbar_init(&bars[2], T);
+    mbar_init(&bars[3], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  uint32_t par0 = 0, par1 = 0;
-  // All CTAs of a launch run the same load / transform / store cycle with the same period.  Started
-  // together they stay in step for the whole launch: the memory system sees every SM storing at
-  // once, then nothing.  A pseudo-random start offset per work pair spreads the phases.
-  if (t == 0 && p.stagger_ns) {
-    const uint32_t h = (((uint32_t)blockIdx.x / NCH) * 2654435761u) >> 22;      // 10 bits
-    const uint64_t d = ((uint64_t)p.stagger_ns * h) >> 10;
-    uint64_t t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do {
-      __nanosleep(256);
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    } while (t1 - t0 < d);
-  }
+  uint32_t par0 = 0, par1 = 0, par2 = 0, par3 = 0;
+  bool staged = false;                       // the TMA unit may still be reading the exchange buffer
+  bool first_xch = true;
   __syncthreads();
 
   const int group_size = p.power_rows ? 1 : p.avg1num;
@@ -247,56 +192,81 @@ fft1_fused_kernel(const Fft1K p)
   const int ngroups = (c0 + p.nblocks + group_size - 1) / group_size;
   const uint32_t span = (uint32_t)N * FRAME;
   // work item = (averaging group, channel).  The two channels of a group go to neighbouring CTAs:
-  // they read the same timf1 frames at the same time (one DRAM fetch, the second CTA hits L2) and
-  // each writes its own 8-byte half of every output slot; the halves of a 32-byte sector arrive
-  // within microseconds of each other and leave L2 as whole sectors.
+  // they read the same timf1 frames at the same time (one DRAM fetch, the second CTA hits L2).
   const int nwork = ngroups * NCH;
-  int w = blockIdx.x;
-  if (w >= nwork) return;
-  // block range [b0, b1) of work item w
-  auto range_of = [&](int ww, int& bb0, int& bb1) {
-    const int gg = ww / NCH;
-    bb0 = gg * group_size - c0;
-    bb1 = bb0 + group_size;
-    if (bb0 < 0) bb0 = 0;
-    if (bb1 > p.nblocks) bb1 = p.nblocks;
-  };
-  auto start_of = [&](int bb) { return (p.ref0 + (uint32_t)bb * p.blockbytes - p.pre_bytes) & p.ring_mask; };
-  int b0, b1;
-  range_of(w, b0, b1);
-  int b = b0;
-  float2* slot0 = xch + last_xch_base<LOG2N>(t);
-  raw_issue<LOG2N, FMT>(slot0, p.timf1, p.ring_mask, start_of(b), t, w % NCH);
-
-  while (true) {
+  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int g = w / NCH;
     const int c = w - g * NCH;
-    // the transform after this one (same group, or the first of this CTA's next work item)
-    int nw = w, nb = b + 1, nb0 = b0, nb1 = b1;
-    bool have_next = true;
-    if (nb >= b1) {
-      nw = w + (int)gridDim.x;
-      have_next = nw < nwork;
-      if (have_next) {
-        range_of(nw, nb0, nb1);
-        nb = nb0;
+    int b0 = g * group_size - c0;
+    int b1 = b0 + group_size;
+    if (b0 < 0) b0 = 0;
+    if (b1 > p.nblocks) b1 = p.nblocks;
+    for (int b = b0; b < b1; b++) {
+      const uint32_t start = (p.ref0 + (uint32_t)b * p.blockbytes - p.pre_bytes) & p.ring_mask;
+      if (t == 0 && c == 0) {
+        // what this CTA (and its sibling) reads next: the new bytes of b+1, or the whole span of
+        // its next group
+        if (b + 1 < b1) {
+          l2_prefetch_span(p.timf1, p.ring_mask, start + span, p.blockbytes);
+        } else {
+          const int gn = (w + (int)gridDim.x) / NCH;
+          int bn = gn * group_size - c0;
+          if (bn < 0) bn = 0;
+          if (gn < ngroups && bn < p.nblocks)
+            l2_prefetch_span(p.timf1, p.ring_mask, p.ref0 + (uint32_t)bn * p.blockbytes - p.pre_bytes, span);
+        }
       }
-    }
-    float* outb = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask) + (size_t)t * MM + 2 * c;
-    {
+      float* out_block = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
+      const bool wraps = start + span > p.ring_mask + 1u;
       float2 v[32];
-      cp_async_wait_all();                       // my own raw frames have landed in my own slots
-      raw_take<LOG2N, FMT>(v, slot0, wtab, p.direction);
-      mbar_arrive(&war_bar[1]);                  // my slots may be overwritten by the first exchange
+      // ---- load, int -> float, window (sign and, for FC_FOLDED, gain are in the table)
+      if (!wraps) {
+        const uint8_t* src = p.timf1 + start + (uint32_t)t * FRAME + c * CHB;
+        if (p.direction > 0) {
+#pragma unroll
+          for (int e = 0; e < 32; e++) {
+            const float2 s = cvt_iq<FMT>(src + (size_t)e * (T * FRAME));
+            const float wv = wtab[e * T];
+            v[e] = make_float2(s.y * -wv, s.x * wv);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e++) {
+            const float2 s = cvt_iq<FMT>(src + (size_t)e * (T * FRAME));
+            const float wv = wtab[e * T];
+            v[e] = make_float2(s.x * wv, s.y * -wv);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          const uint32_t off = (start + (uint32_t)(t + T * e) * FRAME) & p.ring_mask;
+          const float2 s = cvt_iq<FMT>(p.timf1 + off + c * CHB);
+          const float wv = wtab[e * T];
+          v[e] = p.direction > 0 ? make_float2(s.y * -wv, s.x * wv) : make_float2(s.x * wv, s.y * -wv);
+        }
+      }
       // ---- transform
       pass0<P::R0>(v);
-      mbar_wait(&war_bar[1], par1);              // everybody has taken their raw frames
-      par1 ^= 1;
+      if (NCH == 2 && !first_xch) {            // the previous transform's last exchange has been read by everybody
+        mbar_wait(&bars[1], par1);
+        par1 ^= 1;
+      }
+      first_xch = false;
+      if (staged) {                            // the previous transform's output has left the exchange buffer
+        if (t == 0) {
+          bulk_wait_read();
+          mbar_arrive(&bars[3]);
+        }
+        mbar_wait(&bars[3], par3);
+        par3 ^= 1;
+        staged = false;
+      }
       exch1_store<LOG2N>(v, xch, t);
       __syncthreads();
       exch1_load<LOG2N>(v, xch, t);
       if (P::NPASS == 3) {
-        mbar_arrive(&war_bar[0]);
+        mbar_arrive(&bars[0]);
         {
           float2 w32[32];
           const float4* tp = tab1 + (t & (P::R0 - 1));
@@ -308,101 +278,66 @@ fft1_fused_kernel(const Fft1K p)
           }
           radix32_table(v, w32);
         }
-        mbar_wait(&war_bar[0], par0);            // everybody has read exchange 1
+        mbar_wait(&bars[0], par0);             // everybody has read exchange 1
         par0 ^= 1;
         exch2_store<LOG2N>(v, xch, t);
         __syncthreads();
         exch2_load<LOG2N>(v, xch, t);
       }
-      // ---- the slots just read are free: stage the next transform's raw frames into them
-      if (have_next) {
-        raw_issue<LOG2N, FMT>(slot0, p.timf1, p.ring_mask, start_of(nb), t, nw % NCH);
-        if (t == 0 && (nw % NCH) == 0) {
-          // pull what comes after that into L2: the new bytes of the following transform of the
-          // same group, or the whole span of the first transform of the work item after it
-          if (nb + 1 < nb1) {
-            l2_prefetch_span(p.timf1, p.ring_mask, start_of(nb) + span, p.blockbytes);
-          } else if (nw + (int)gridDim.x < nwork) {
-            int fb0, fb1;
-            range_of(nw + (int)gridDim.x, fb0, fb1);
-            if (fb0 < fb1) l2_prefetch_span(p.timf1, p.ring_mask, start_of(fb0), span);
-          }
-        }
-      }
+      mbar_arrive(&bars[1]);                   // my reads of the exchange buffer are done
       radix32_gen(v, wb);
       // ---- epilogue: bin k = t + T*e; v holds (im, re) of the output value.  |z|^2 goes
       // straight to the fft1_sumsq row in L2 (fft1.c:4507-4520 sums the transforms of a group in
       // time order; so do the reductions of one thread on one address): the first transform of a
       // one-channel group stores, everything else is a fire-and-forget RED.ADD.  Two-channel rows
       // are zeroed by the host because the two channel CTAs of a group add into the same row.
+      const bool rows = p.power_rows != nullptr;
+      float* prow = nullptr;
       if (FC != FC_RAW) {
-        const bool rows = p.power_rows != nullptr;
-        float* prow = rows ? p.power_rows + (size_t)b * N + t
-                           : (p.sumsq ? p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask) + t : nullptr);
-        const bool plain = (NCH == 1) && (rows || (b == b0 && !(g == 0 && p.counter0 > 0)));
-        if (FC == FC_FOLDED) {                   // host guarantees the full bin range here
-          if (t < 16) {                          // bins 0..15 and N-16..N-1 carry the taper of fft1.c:4703-4722
-            const float2 f = p.edge[t];
-            v[0] = make_float2(v[0].x * f.x + v[0].y * f.y, v[0].y * f.x - v[0].x * f.y);
-          }
-          if (t >= T - 16) {
-            const float2 f = p.edge[16 + t - (T - 16)];
-            v[31] = make_float2(v[31].x * f.x + v[31].y * f.y, v[31].y * f.x - v[31].x * f.y);
-          }
-#if defined(LB_EXP) && (LB_EXP & 4)
-          if (prow && v[3].x == 1.2345f) {
-#else
-          if (prow) {
-#endif
-            if (plain) {
-#pragma unroll
-              for (int e = 0; e < 32; e++) prow[e * T] = fmaf(v[e].x, v[e].x, v[e].y * v[e].y);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; e++) atomicAdd(prow + e * T, fmaf(v[e].x, v[e].x, v[e].y * v[e].y));
-            }
-          }
-        } else {
-          // general path: full filtercorr table and/or a limited bin range (fft1.c:4115-4131)
-          const float* fcp = p.filtercorr + (size_t)t * MM + 2 * c;
-#pragma unroll
-          for (int e = 0; e < 32; e++) {
-            const int k = t + T * e;
-            if (k >= p.first_point && k <= p.last_point) {
-              const float2 f = *reinterpret_cast<const float2*>(fcp + (size_t)e * (T * MM));
-              const float re = v[e].y * f.x - v[e].x * f.y;
-              const float im = v[e].x * f.x + v[e].y * f.y;
-              v[e] = make_float2(im, re);
-              const float pw = re * re + im * im;
-              if (prow) {
-                if (plain) prow[e * T] = pw;
-                else atomicAdd(prow + e * T, pw);
-              }
-            } else if (rows && NCH == 1) {
-              prow[e * T] = 0.0f;
-            }
-          }
+        prow = rows ? p.power_rows + (size_t)b * N + t
+                    : (p.sumsq ? p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask) + t : nullptr);
+      }
+      const bool plain = (NCH == 1) && (rows || (b == b0 && !(g == 0 && p.counter0 > 0)));
+      if (FC == FC_FOLDED) {
+        if (t < 16) {                          // bins 0..15 and N-16..N-1 carry the taper of fft1.c:4703-4722
+          const float2 f = p.edge[t];
+          v[0] = make_float2(v[0].x * f.x + v[0].y * f.y, v[0].y * f.x - v[0].x * f.y);
+        }
+        if (t >= T - 16) {
+          const float2 f = p.edge[16 + t - (T - 16)];
+          v[31] = make_float2(v[31].x * f.x + v[31].y * f.y, v[31].y * f.x - v[31].x * f.y);
         }
       }
-#if defined(LB_EXP) && (LB_EXP & 2)
-      if (v[0].x == 1.2345f) outb[0] = v[5].y;
-#elif defined(LB_EXP) && (LB_EXP & 1)
-      {
-        float* ob = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask) + (size_t)t * 2 + (size_t)c * N * 2;
+      if (NCH == 1) {
+        // one round: bin k at byte 8k of the exchange buffer
+        fused_epilogue<FC, NCH, T, 0, 32>(v, p, prow, plain, rows, t, c);
+        mbar_wait(&bars[1], par1);             // everybody has read the last exchange
+        par1 ^= 1;
 #pragma unroll
-        for (int e = 0; e < 32; e++) lb_store_stream(reinterpret_cast<float2*>(ob + (size_t)e * (T * 2)), make_float2(v[e].y, v[e].x));
+        for (int e = 0; e < 32; e++) xch[t + T * e] = make_float2(v[e].y, v[e].x);
+        fence_async_smem();
+        mbar_arrive(&bars[2]);
+        if (t == 0) {
+          mbar_wait(&bars[2], par2);
+#pragma unroll
+          for (int q = 0; q < 4; q++) bulk_store(out_block + q * (N / 2), xch + q * (N / 4), N * 2);
+          bulk_commit();
+        }
+        par2 ^= 1;
+        staged = true;
+      } else {
+        // two channels: this CTA owns 8 bytes of every 16-byte slot.  The masked TMA copy
+        // (cp.async.bulk ... .cp_mask) was measured: like STG it moves one half-used sector per
+        // clock, and with room for only N/2 staged bins the second round has to wait for the
+        // first, so plain streaming stores are faster here (profiles/r1_v4_notes.txt).
+        fused_epilogue<FC, NCH, T, 0, 32>(v, p, prow, plain, rows, t, c);
+        float* outb = out_block + (size_t)t * MM + 2 * c;
+#pragma unroll
+        for (int e = 0; e < 32; e++) lb_store_stream(reinterpret_cast<float2*>(outb + (size_t)e * (T * MM)), make_float2(v[e].y, v[e].x));
       }
-#else
-#pragma unroll
-      for (int e = 0; e < 32; e++) lb_store_stream(reinterpret_cast<float2*>(outb + (size_t)e * (T * MM)), make_float2(v[e].y, v[e].x));
-#endif
     }
-    if (!have_next) break;
-    w = nw;
-    b = nb;
-    b0 = nb0;
-    b1 = nb1;
   }
+  if (t == 0) bulk_wait_all();                 // the exchange buffer must outlive the last copy
 }
 
 template <int LOG2N>

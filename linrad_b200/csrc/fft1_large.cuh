@@ -109,9 +109,9 @@ fft1_large_rows_kernel(const Fft1LargeK q)
   constexpr int NTHREADS = TB * T;
   constexpr int XCH = N2 + N2 / 32 + 32;          // per-row exchange slice
   constexpr int TILE_PTS = TB * N2;
+  constexpr int TP = TB + 1;                      // padded row of the transpose tile (conflict-free scatter)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* xch_all = reinterpret_cast<float2*>(smem_raw);      // TB rows; reused as the transpose tile
-  float* acc = reinterpret_cast<float*>(smem_raw + sizeof(float2) * (size_t)TB * XCH);
   const Fft1K& p = q.k;
   const int t = threadIdx.x & (T - 1);
   const int row = threadIdx.x / T;
@@ -120,44 +120,47 @@ fft1_large_rows_kernel(const Fft1LargeK q)
   Twiddles<P> tw;
   load_twiddles<P>(tw, q.Wn2, t);
 
+  // work item = (transform, tile of TB rows).  |z|^2 is added straight into the fft1_sumsq row
+  // (host-zeroed unless it continues a partial group): the transforms of a group are spread over
+  // many CTAs, which keeps every SM busy even when a sub-batch holds only a few groups.
   const int group_size = p.power_rows ? 1 : p.avg1num;
   const int c0 = p.power_rows ? 0 : p.counter0;
-  const int nwork = q.g_count * TILES;
+  const int nwork = q.b_count * TILES;
   for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int tile = w % TILES;
-    const int g = q.g_first + w / TILES;
-    int b0 = g * group_size - c0;
-    int b1 = b0 + group_size;
-    if (b0 < 0) b0 = 0;
-    if (b1 > p.nblocks) b1 = p.nblocks;
+    const int slot = w / TILES;
+    const int b = q.b_first + slot;
+    const int g = (b + c0) / group_size;
     const int k1 = tile * TB + row;
-    for (int b = b0; b < b1; b++) {
-      const int slot = b - q.b_first;
-      float* outb = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
+    float* outb = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
+    float* rowp = (p.sumsq && !p.power_rows) ? p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask) : nullptr;
+    float* prow = p.power_rows ? p.power_rows + (size_t)b * N : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < NCH; c++) {
-        const float2* Y = q.scratch + ((size_t)slot * NCH + c) * N + (size_t)k1 * N2;
-        float2 v[E];
+    for (int c = 0; c < NCH; c++) {
+      const float2* Y = q.scratch + ((size_t)slot * NCH + c) * N + (size_t)k1 * N2;
+      float2 v[E];
 #pragma unroll
-        for (int e = 0; e < E; e++) v[e] = Y[t + T * e];
-        __syncthreads();                   // the transpose tile of the previous pass is consumed
-        fft_forward<P>(v, xch, t, tw);
-        __syncthreads();
-        // transpose: tile[k2][row]
+      for (int e = 0; e < E; e++) v[e] = Y[t + T * e];
+      __syncthreads();                   // the transpose tile of the previous pass is consumed
+      fft_forward<P>(v, xch, t, tw);
+      __syncthreads();
+      // transpose: tile[k2][row]
 #pragma unroll
-        for (int e = 0; e < E; e++) xch_all[(t + T * e) * TB + row] = v[e];
-        __syncthreads();
-        for (int o = threadIdx.x; o < TILE_PTS; o += NTHREADS) {
-          const int r = o & (TB - 1), k2 = o >> LOG2TB;
-          const int k = tile * TB + r + N1 * k2;
-          const float2 z = xch_all[o];
-          if (p.zbuf) {                    // real input: plain Z, finished by fft1_real_post_kernel
-            p.zbuf[((size_t)(b - p.zb_first) * NCH + c) * N + k] = z;
-            continue;
-          }
-          float2 ov = p.direction < 0 ? make_float2(z.y, z.x) : make_float2(z.x, -z.y);
-          const bool inr = (k >= p.first_point) && (k <= p.last_point);
-          if (p.fc_mode != 0 && inr) {
+      for (int e = 0; e < E; e++) xch_all[(t + T * e) * TP + row] = v[e];
+      __syncthreads();
+#pragma unroll 4
+      for (int o = threadIdx.x; o < TILE_PTS; o += NTHREADS) {
+        const int r = o & (TB - 1), k2 = o >> LOG2TB;
+        const int k = tile * TB + r + N1 * k2;
+        const float2 z = xch_all[k2 * TP + r];
+        if (p.zbuf) {                    // real input: plain Z, finished by fft1_real_post_kernel
+          p.zbuf[((size_t)(b - p.zb_first) * NCH + c) * N + k] = z;
+          continue;
+        }
+        float2 ov = p.direction < 0 ? make_float2(z.y, z.x) : make_float2(z.x, -z.y);
+        const bool inr = (k >= p.first_point) && (k <= p.last_point);
+        if (p.fc_mode != 0) {
+          if (inr) {
             float2 f;
             if (p.fc_mode == 2 || k < p.fc_edge || k >= N - p.fc_edge)
               f = *reinterpret_cast<const float2*>(p.filtercorr + (size_t)k * MM + 2 * c);
@@ -167,32 +170,17 @@ fft1_large_rows_kernel(const Fft1LargeK q)
             const float im = ov.y * f.x + ov.x * f.y;
             ov = make_float2(re, im);
             const float pw = re * re + im * im;
-            if (b == b0 && c == 0) acc[o] = pw;
-            else acc[o] += pw;
+            if (prow) {                  // the same thread owns bin k for both channels
+              if (c == 0) prow[k] = pw;
+              else prow[k] += pw;
+            } else if (rowp) {
+              atomicAdd(rowp + k, pw);
+            }
+          } else if (prow && c == 0) {
+            prow[k] = 0.0f;
           }
-          __stcs(reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c), ov);
         }
-      }
-      if (p.power_rows && p.fc_mode != 0) {
-        for (int o = threadIdx.x; o < TILE_PTS; o += NTHREADS) {
-          const int r = o & (TB - 1), k2 = o >> LOG2TB;
-          const int k = tile * TB + r + N1 * k2;
-          const bool inr = (k >= p.first_point) && (k <= p.last_point);
-          p.power_rows[(size_t)b * N + k] = inr ? acc[o] : 0.0f;
-        }
-      }
-    }
-    if (p.sumsq && !p.power_rows && p.fc_mode != 0 && b1 > b0) {
-      float* rowp = p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask);
-      const bool continuing = (g == 0 && p.counter0 > 0);
-      for (int o = threadIdx.x; o < TILE_PTS; o += NTHREADS) {
-        const int r = o & (TB - 1), k2 = o >> LOG2TB;
-        const int k = tile * TB + r + N1 * k2;
-        if (k >= p.first_point && k <= p.last_point) {
-          float val = acc[o];
-          if (continuing) val = rowp[k] + val;
-          rowp[k] = val;
-        }
+        __stcs(reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c), ov);
       }
     }
   }
@@ -203,8 +191,9 @@ constexpr size_t fft1_large_cols_smem() { return sizeof(float2) * ((size_t)1 << 
 template <int LOG2N2, int LOG2TB>
 constexpr size_t fft1_large_rows_smem()
 {
-  return sizeof(float2) * ((size_t)(1 << LOG2TB) * ((1 << LOG2N2) + (1 << LOG2N2) / 32 + 32)) +
-         sizeof(float) * ((size_t)1 << (LOG2N2 + LOG2TB));
+  const size_t xch = (size_t)(1 << LOG2TB) * ((1 << LOG2N2) + (1 << LOG2N2) / 32 + 32);
+  const size_t tile = (size_t)((1 << LOG2TB) + 1) << LOG2N2;
+  return sizeof(float2) * (xch > tile ? xch : tile);
 }
 
 }  // namespace lb

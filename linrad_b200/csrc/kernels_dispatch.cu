@@ -66,6 +66,25 @@ static large_fn_t large_fn(int fmt)
   return (fmt >= 0 && fmt < 8) ? t[fmt] : nullptr;
 }
 
+// zero the fft1_sumsq rows a launch will ADD into (all but a row that continues a partial group)
+cudaError_t lb_zero_sumsq_rows(lb200_plan* plan, const Fft1K& k, int ngroups)
+{
+  const int g0 = k.counter0 > 0 ? 1 : 0;
+  const size_t N = (size_t)plan->N;
+  size_t off = (k.sumsq_pa + (size_t)g0 * N) & k.sumsq_mask;
+  size_t len = (size_t)(ngroups - g0) * N;
+  const size_t size = (size_t)k.sumsq_mask + 1;
+  while (len > 0) {                                            // at most two pieces: the rows are consecutive on the ring
+    size_t n = size - off;
+    if (n > len) n = len;
+    cudaError_t e = cudaMemsetAsync(k.sumsq + off, 0, sizeof(float) * n, plan->stream);
+    if (e != cudaSuccess) return e;
+    len -= n;
+    off = 0;
+  }
+  return cudaSuccess;
+}
+
 bool lb_fft1_large_supported(int log2n) { return log2n >= 15 && log2n <= 20; }
 
 static void large_split(int log2n, int* ln1, int* ln2)
@@ -107,6 +126,10 @@ cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k)
   q.Wbig = plan->d_Wn;
   large_fn_t fn = large_fn(plan->fmt);
   const int tilesA = (1 << ln2) >> LB_LARGE_LT, tilesB = (1 << ln1) >> LB_LARGE_LT;
+  if (k.sumsq && !k.power_rows && k.fc_mode != 0) {
+    cudaError_t e = lb_zero_sumsq_rows(plan, k, ngroups);    // step B adds |z|^2 into the rows
+    if (e != cudaSuccess) return e;
+  }
   for (int g0 = 0; g0 < ngroups; g0 += gps) {
     const int g1 = g0 + gps < ngroups ? g0 + gps : ngroups;
     int b_first = g0 * group - c0;
@@ -118,7 +141,7 @@ cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k)
     q.g_first = g0;
     q.g_count = g1 - g0;
     int gridA = q.b_count * nch * tilesA;
-    int gridB = q.g_count * tilesB;
+    int gridB = q.b_count * tilesB;
     const int cap = plan->sm_count * 16;
     if (gridA > cap) gridA = cap;
     if (gridB > cap) gridB = cap;
