@@ -701,11 +701,24 @@ static int launch_mix1(lb200_plan* plan, const lb200_mix1_args* a, const float* 
   if (ctas_per_sm > 2048 / threads) ctas_per_sm = 2048 / threads;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int target = plan->sm_count * ctas_per_sm;
-  int chunks = (int)(((size_t)K * B + (size_t)target * par - 1) / ((size_t)target * par));
-  if (chunks < 1) chunks = 1;
-  if (chunks > 8) chunks = 8;
-  int runlen = chunks * par - (mix1_mode(plan) != 0 ? 1 : 0);
-  if (runlen < 1) runlen = 1;
+  // cost of a choice = (waves of CTAs) x (chunks each CTA walks through): a run length that leaves
+  // a nearly empty last wave is as slow as a full one
+  const int pre = mix1_mode(plan) != 0 ? 1 : 0;
+  int runlen = 1;
+  {
+    long best = -1;
+    for (int chunks = 1; chunks <= 16; chunks++) {
+      const int rl = chunks * par - pre;
+      if (rl < 1) continue;
+      const long nr = (long)((B + rl - 1) / rl) * K;
+      const long waves = (nr + target - 1) / target;
+      const long cost = waves * chunks;
+      if (best < 0 || cost < best) {
+        best = cost;
+        runlen = rl;
+      }
+    }
+  }
   runlen = env_int("LB200_MIX1_RUNLEN", runlen);
   k.runlen = runlen;
   const int nruns = ((B + runlen - 1) / runlen) * K;
