@@ -258,7 +258,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="transforms per step per GPU (0 = workload default)")
-    ap.add_argument("--e2e-batch", type=int, default=0, help="transforms per host-ring call (0 = four 16 MB sub-batches)")
+    ap.add_argument("--e2e-batch", type=int, default=0, help="transforms per host-ring call (0 = sixteen 16 MB sub-batches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
@@ -399,7 +399,7 @@ def main():
     # ---- end to end through the host-buffer C ABI ------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        Be = args.e2e_batch or 4 * max(1, (16 << 20) // (4 * s.fft1_block))
+        Be = args.e2e_batch or 16 * max(1, (16 << 20) // (4 * s.fft1_block))
         Be = min(Be, B)
         h_timf1 = torch.zeros(pow2_at_least((Be + 2) * s.timf1_blockbytes), dtype=torch.uint8).pin_memory()
         h_timf1[: Be * s.timf1_blockbytes].copy_(torch.from_numpy(host_in[: Be * s.timf1_blockbytes]))

@@ -20,26 +20,6 @@
 
 namespace lb {
 
-// e' = e + W*o, o' = e - W*o with W = exp(-2 pi i k32/32), k32 in [0,16)
-LB_HD void bfly32(float2& e, float2& o, int k32)
-{
-  if (k32 == 0) {
-    const float2 t = e;
-    e = make_float2(t.x + o.x, t.y + o.y);
-    o = make_float2(t.x - o.x, t.y - o.y);
-  } else if (k32 == 8) {                 // W = -i:  W*o = (o.y, -o.x)
-    const float2 t = e, u = o;
-    e = make_float2(t.x + u.y, t.y - u.x);
-    o = make_float2(t.x - u.y, t.y + u.x);
-  } else {                               // W = c - i s:  W*o = (o.x c + o.y s, o.y c - o.x s)
-    const float c = cos32(k32), s = sin32(k32);
-    const float lx = fmaf(o.y, s, fmaf(o.x, c, e.x));
-    const float ly = fmaf(-o.x, s, fmaf(o.y, c, e.y));
-    o = make_float2(fmaf(2.0f, e.x, -lx), fmaf(2.0f, e.y, -ly));
-    e = make_float2(lx, ly);
-  }
-}
-
 // lo = a + w*b, hi = 2a - lo for a run-time twiddle w
 LB_HD void bfly_w(float2& a, float2& b, float2 w)
 {

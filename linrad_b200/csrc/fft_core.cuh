@@ -76,6 +76,26 @@ LB_HD float2 rot32(float2 a, int k32)
   }
 }
 
+// e' = e + W*o, o' = e - W*o with W = exp(-2 pi i k32/32), k32 in [0,16)
+LB_HD void bfly32(float2& e, float2& o, int k32)
+{
+  if (k32 == 0) {
+    const float2 t = e;
+    e = make_float2(t.x + o.x, t.y + o.y);
+    o = make_float2(t.x - o.x, t.y - o.y);
+  } else if (k32 == 8) {                 // W = -i:  W*o = (o.y, -o.x)
+    const float2 t = e, u = o;
+    e = make_float2(t.x + u.y, t.y - u.x);
+    o = make_float2(t.x - u.y, t.y + u.x);
+  } else {                               // W = c - i s:  W*o = (o.x c + o.y s, o.y c - o.x s)
+    const float c = cos32(k32), s = sin32(k32);
+    const float lx = fmaf(o.y, s, fmaf(o.x, c, e.x));
+    const float ly = fmaf(-o.x, s, fmaf(o.y, c, e.y));
+    o = make_float2(fmaf(2.0f, e.x, -lx), fmaf(2.0f, e.y, -ly));
+    e = make_float2(lx, ly);
+  }
+}
+
 // ---------------------------------------------------------------- DFT_R on registers
 // In-place forward DFT of the R points x[0], x[S], ..., x[(R-1)S]; natural order in and out.
 // Radix-2 decimation in time; every index is a compile-time constant after unrolling so the
@@ -89,10 +109,10 @@ struct DftS {
     float2 lo[R / 2], hi[R / 2];
 #pragma unroll
     for (int k = 0; k < R / 2; k++) {
-      const float2 e = x[2 * S * k];
-      const float2 o = rot32(x[S + 2 * S * k], k * (32 / R));
-      lo[k] = cadd(e, o);
-      hi[k] = csub(e, o);
+      float2 e = x[2 * S * k], o = x[S + 2 * S * k];
+      bfly32(e, o, k * (32 / R));            // lo = e + W o (4 FFMA), hi = 2e - lo (2 FFMA)
+      lo[k] = e;
+      hi[k] = o;
     }
 #pragma unroll
     for (int k = 0; k < R / 2; k++) {
