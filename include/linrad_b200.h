@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LB200_ABI_VERSION 1
+#define LB200_ABI_VERSION 2
 
 /* ui.rx_input_mode bits used by the path (globdef.h:277-279) */
 #define LB200_DWORD_INPUT 1
@@ -55,7 +55,9 @@ typedef struct lb200_config {
   /* --- input format ------------------------------------------------------------- */
   int rx_input_mode;            /* ui.rx_input_mode (DWORD_INPUT|TWO_CHANNELS|IQ_DATA) */
   int rx_rf_channels;           /* ui.rx_rf_channels: 1 or 2 */
-  int sample_shift;             /* ui.sample_shift (Q delay in samples, fft1.c:778-787) */
+  int sample_shift;             /* ui.sample_shift (I/Q skew in samples, IQ input only: < 0 takes Q
+                                   from |shift| frames earlier, > 0 takes I from shift frames
+                                   earlier, fft1.c:770-790, 2041-2247) */
   /* --- fft1 geometry -------------------------------------------------------------- */
   int fft1_n;                   /* fft1_n;  fft1_size = 1 << fft1_n (bins) */
   int fft1_interleave_points;   /* fft1_interleave_points (buf.c:303,327) */
@@ -67,7 +69,9 @@ typedef struct lb200_config {
                                    input); NULL when genparm[FIRST_FFT_SINPOW]==0.  Use
                                    lb200_window_to_natural() to convert a make_window() table. */
   const float *fft1_filtercorr; /* twice_rxchan*fft1_size floats, layout of fft1.c:4691-4692 */
-  const float *fft1_foldcorr;   /* twice_rxchan*fft1_size floats or NULL (CALIQ off) */
+  const float *fft1_foldcorr;   /* twice_rxchan*fft1_size floats, layout of fft1_filtercorr, or NULL
+                                   when (fft1_calibrate_flag & CALIQ) == 0: the I/Q mirror-image
+                                   correction of fft1_b (fft1.c:3607-3657, 3941-4026), IQ input only */
   /* --- power spectra --------------------------------------------------------------- */
   int fft_avg1num;              /* wg.fft_avg1num */
   /* --- mix1 ------------------------------------------------------------------------- */
@@ -83,6 +87,10 @@ typedef struct lb200_config {
   float mix1_highest_fq;        /* mix1_highest_fq */
   /* --- bulk-mode capacity ------------------------------------------------------------ */
   int max_batch;                /* largest nblocks per call (sizes staging buffers) */
+  /* --- channel-2 phasing (ABI 2) ---------------------------------------------------- */
+  float pg_ch2_c1, pg_ch2_c2;   /* pol_graph.c:165-173; (1, 0) = off.  Two-channel IQ input only:
+                                   ch2 *= (c1 - i c2) on bins [first_sym_point, N - first_sym_point)
+                                   (fft1.c:4064-4080) */
 } lb200_config;
 
 /* Ring-buffer descriptor: base pointer + power-of-two size (the reference's xxx_mask+1). */

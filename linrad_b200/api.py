@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LB200_LIB") or os.path.join(_HERE, "liblinrad_b200.so")   # LB200_LIB: A/B builds of the same ABI
 
-LB200_ABI_VERSION = 1
+LB200_ABI_VERSION = 2
 ERR = {0: "OK", 3100: "NO_DEVICE", 3101: "CUDA", 3102: "BAD_CONFIG", 3103: "UNSUPPORTED", 3104: "BAD_ARG",
        1211: "MIX1_RANGE_LOW", 1212: "MIX1_RANGE_HIGH"}
 
@@ -44,6 +44,7 @@ class Config(C.Structure):
         ("mix1_sin2win", C.c_void_p),
         ("fftx_points_per_hz", C.c_float), ("mix1_lowest_fq", C.c_float), ("mix1_highest_fq", C.c_float),
         ("max_batch", C.c_int),
+        ("pg_ch2_c1", C.c_float), ("pg_ch2_c2", C.c_float),
     ]
 
 
@@ -144,13 +145,15 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
-def make_config(setup, device=0, window=None, filtercorr=None, max_batch=0):
+def make_config(setup, device=0, window=None, filtercorr=None, max_batch=0, foldcorr=None, sample_shift=0,
+                pg_ch2=(1.0, 0.0)):
     """Build an lb200_config from a sizing.PathSetup.  `window`/`filtercorr` override the tables
     (e.g. with the reference's own, taken from the oracle in the parity tests).  Returns
     (Config, keepalive) -- keepalive holds the numpy tables until lb200_create has copied them."""
     keep = dict(
         window=_f32(window if window is not None else setup.window),
         filtercorr=_f32(filtercorr if filtercorr is not None else setup.filtercorr),
+        foldcorr=_f32(foldcorr),
         fqwin=_f32(setup.mix1_fqwin), mwin=_f32(setup.mix1_window),
         cos2=_f32(setup.mix1_cos2win), sin2=_f32(setup.mix1_sin2win))
     cfg = Config()
@@ -158,7 +161,7 @@ def make_config(setup, device=0, window=None, filtercorr=None, max_batch=0):
     cfg.device = device
     cfg.rx_input_mode = setup.input_mode
     cfg.rx_rf_channels = setup.rf_channels
-    cfg.sample_shift = 0
+    cfg.sample_shift = sample_shift
     cfg.fft1_n = setup.fft1_n
     cfg.fft1_interleave_points = setup.fft1_interleave_points
     cfg.fft1_direction = setup.direction
@@ -166,7 +169,7 @@ def make_config(setup, device=0, window=None, filtercorr=None, max_batch=0):
     cfg.fft1_last_point = setup.fft1_last_point
     cfg.fft1_window = _ptr(keep["window"])
     cfg.fft1_filtercorr = _ptr(keep["filtercorr"])
-    cfg.fft1_foldcorr = None
+    cfg.fft1_foldcorr = _ptr(keep["foldcorr"])
     cfg.fft_avg1num = setup.avg1num
     cfg.mix1_n = setup.mix1_n
     cfg.mix1_interleave_points = setup.mix1_interleave_points
@@ -179,16 +182,18 @@ def make_config(setup, device=0, window=None, filtercorr=None, max_batch=0):
     cfg.mix1_lowest_fq = setup.mix1_lowest_fq
     cfg.mix1_highest_fq = setup.mix1_highest_fq
     cfg.max_batch = max_batch
+    cfg.pg_ch2_c1, cfg.pg_ch2_c2 = float(pg_ch2[0]), float(pg_ch2[1])
     return cfg, keep
 
 
 class Plan:
     """Thin handle around lb200_plan."""
 
-    def __init__(self, setup, device=0, window=None, filtercorr=None, max_batch=0):
+    def __init__(self, setup, device=0, window=None, filtercorr=None, max_batch=0, foldcorr=None, sample_shift=0,
+                 pg_ch2=(1.0, 0.0)):
         self.lib = load_library()
         self.setup = setup
-        self.cfg, keep = make_config(setup, device, window, filtercorr, max_batch)
+        self.cfg, keep = make_config(setup, device, window, filtercorr, max_batch, foldcorr, sample_shift, pg_ch2)
         h = C.c_void_p()
         rc = self.lib.lb200_create(C.byref(self.cfg), C.byref(h))
         if rc:

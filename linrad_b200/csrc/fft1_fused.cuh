@@ -217,7 +217,7 @@ fft1_fused_kernel(const Fft1K p)
         }
       }
       float* out_block = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
-      const bool wraps = start + span > p.ring_mask + 1u;
+      const bool wraps = (start + span > p.ring_mask + 1u) || (p.skew_i | p.skew_q);
       float2 v[32];
       // ---- load, int -> float, window (sign and, for FC_FOLDED, gain are in the table)
       if (!wraps) {
@@ -238,10 +238,15 @@ fft1_fused_kernel(const Fft1K p)
           }
         }
       } else {
+        // ring wrap inside the span, or ui.sample_shift (I and Q words from different frames)
 #pragma unroll
         for (int e = 0; e < 32; e++) {
           const uint32_t off = (start + (uint32_t)(t + T * e) * FRAME) & p.ring_mask;
-          const float2 s = cvt_iq<FMT>(p.timf1 + off + c * CHB);
+          float2 s;
+          if ((FMT == FMT_I16_1CH || FMT == FMT_I32_1CH) && (p.skew_i | p.skew_q))
+            s = load_iq_skew<FMT>(p.timf1, p.ring_mask, off, p.skew_i, p.skew_q);
+          else
+            s = cvt_iq<FMT>(p.timf1 + off + c * CHB);
           const float wv = wtab[e * T];
           v[e] = p.direction > 0 ? make_float2(s.y * -wv, s.x * wv) : make_float2(s.x * wv, s.y * -wv);
         }

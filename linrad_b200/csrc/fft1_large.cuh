@@ -79,7 +79,11 @@ fft1_large_cols_kernel(const Fft1LargeK q)
     for (int e = 0; e < E; e++) {
       const int n = (t + T * e) * N2 + n2;
       const uint32_t off = (start + (uint32_t)n * FRAME) & p.ring_mask;
-      const float2 s = load_iq<FMT>(p.timf1, off, c);
+      float2 s;
+      if ((FMT == FMT_I16_1CH || FMT == FMT_I32_1CH) && (p.skew_i | p.skew_q))
+        s = load_iq_skew<FMT>(p.timf1, p.ring_mask, off, p.skew_i, p.skew_q);
+      else
+        s = load_iq<FMT>(p.timf1, off, c);
       if (FmtInfo<FMT>::REAL) {            // packed real pair, plain transform (fft1_re.c)
         const float2 wv = p.window ? reinterpret_cast<const float2*>(p.window)[n] : make_float2(1.0f, 1.0f);
         v[e] = make_float2(s.x * wv.x, s.y * wv.y);

@@ -68,7 +68,20 @@ struct Fft1K {
   int zb_first;
   const float2* Wre;        // exp(-i pi k / N), k = 0..N
   uint32_t stagger_ns;      // fft1_fused_kernel: CTAs start spread over this many ns (0 = together)
+  // ui.sample_shift (one-channel IQ only, fft1.c:770-790): byte offsets of the frame the I word
+  // and the frame the Q word of sample n are taken from, relative to frame n (both 0 = off)
+  int skew_i, skew_q;
 };
+
+// I from the frame at off + skew_i, Q from the frame at off + skew_q (one-channel IQ formats)
+template <int FMT>
+LB_D float2 load_iq_skew(const uint8_t* ring, uint32_t mask, uint32_t off, int skew_i, int skew_q)
+{
+  const uint32_t oi = (off + (uint32_t)skew_i) & mask, oq = (off + (uint32_t)skew_q) & mask;
+  if (FMT == FMT_I16_1CH)
+    return make_float2((float)*reinterpret_cast<const short*>(ring + oi), (float)*reinterpret_cast<const short*>(ring + oq + 2));
+  return make_float2((float)*reinterpret_cast<const int*>(ring + oi), (float)*reinterpret_cast<const int*>(ring + oq + 4));
+}
 
 template <int FMT>
 LB_D float2 load_iq(const uint8_t* ring, uint32_t off, int c)
@@ -137,7 +150,11 @@ fft1_small_kernel(const Fft1K p)
         for (int e = 0; e < E; e++) {
           const int idx = t + T * e;
           const uint32_t off = (start + (uint32_t)idx * FRAME) & p.ring_mask;
-          const float2 s = load_iq<FMT>(p.timf1, off, c);
+          float2 s;
+          if ((FMT == FMT_I16_1CH || FMT == FMT_I32_1CH) && (p.skew_i | p.skew_q))
+            s = load_iq_skew<FMT>(p.timf1, p.ring_mask, off, p.skew_i, p.skew_q);
+          else
+            s = load_iq<FMT>(p.timf1, off, c);
           if (REAL) {
             const float2 w = p.window ? reinterpret_cast<const float2*>(p.window)[idx] : make_float2(1.0f, 1.0f);
             v[e] = make_float2(s.x * w.x, s.y * w.y);

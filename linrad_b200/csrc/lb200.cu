@@ -11,6 +11,7 @@
 #include "plan.h"
 #include "fft1_small.cuh"
 #include "fft1_fused.cuh"
+#include "fft1_post.cuh"
 #include "fft1_large.cuh"
 #include "mix1.cuh"
 
@@ -108,8 +109,19 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
   if (cfg->fft1_first_point < 0 || cfg->fft1_last_point >= plan->N || cfg->fft1_first_point > cfg->fft1_last_point)
     return fail(LB200_ERR_BAD_CONFIG);
   if (cfg->fft_avg1num < 1) return fail(LB200_ERR_BAD_CONFIG);
-  if (cfg->sample_shift != 0) return fail(LB200_ERR_UNSUPPORTED);
-  if (cfg->fft1_foldcorr != nullptr) return fail(LB200_ERR_UNSUPPORTED);
+  // ui.sample_shift exists only in the one-channel IQ window functions of the reference
+  // (fft1.c:225-1028); the two-channel and real-input ones ignore it, and so does this library
+  if (plan->iq && plan->nch == 1 && cfg->sample_shift != 0) {
+    if (cfg->sample_shift <= -plan->N || cfg->sample_shift >= plan->N) return fail(LB200_ERR_BAD_CONFIG);
+    if (cfg->sample_shift < 0) plan->shift_q = cfg->sample_shift;       // fft1.c:778-782
+    else plan->shift_i = -cfg->sample_shift;                             // fft1.c:784-787
+  }
+  // the mirror-image correction and the channel-2 phasing belong to IQ input (fft1.c:3607, 4064)
+  if (cfg->fft1_foldcorr != nullptr && !plan->iq) return fail(LB200_ERR_UNSUPPORTED);
+  plan->phasing = (cfg->pg_ch2_c1 != 1.0f || cfg->pg_ch2_c2 != 0.0f);
+  if (plan->phasing && !(plan->iq && plan->nch == 2)) return fail(LB200_ERR_UNSUPPORTED);
+  plan->first_sym = plan->N - 1 - cfg->fft1_last_point;                 // fft1.c:4647-4649
+  if (plan->first_sym > cfg->fft1_first_point) plan->first_sym = cfg->fft1_first_point;
   if (cfg->fft1_n > 14 && !lb_fft1_large_supported(cfg->fft1_n)) return fail(LB200_ERR_UNSUPPORTED);
   if (cfg->fft1_n < 7) return fail(LB200_ERR_UNSUPPORTED);
 
@@ -140,6 +152,7 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
     }
     if ((rc = upload(plan, (void**)&plan->d_Wre, w.data(), sizeof(float2) * w.size()))) return fail(rc);
   }
+  if (cfg->fft1_foldcorr && (rc = upload(plan, (void**)&plan->d_foldcorr, cfg->fft1_foldcorr, sizeof(float) * plan->fft1_block))) return fail(rc);
   if (cfg->fft1_filtercorr) {
     const float* fc = cfg->fft1_filtercorr;
     if ((rc = upload(plan, (void**)&plan->d_filtercorr, fc, sizeof(float) * plan->fft1_block))) return fail(rc);
@@ -234,7 +247,7 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   cudaSetDevice(plan->device);
   if (plan->stream) cudaStreamSynchronize(plan->stream);
   for (auto& kv : plan->registered) cudaHostUnregister(const_cast<void*>(kv.first));
-  void* ptrs[] = {plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
+  void* ptrs[] = {plan->d_foldcorr, plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
                   plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wn1, plan->d_Wn2,
                   plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2, plan->d_zbuf, plan->d_Wre, plan->d_powtmp};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -319,14 +332,50 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   k.last_point = plan->cfg.fft1_last_point;
   k.direction = plan->cfg.fft1_direction;
 
+  k.skew_i = plan->shift_i * plan->frame;
+  k.skew_q = plan->shift_q * plan->frame;
+
   if (!plan->iq) {
     k.Wre = plan->d_Wre;
     LB_CUDA(lb_launch_fft1_real(plan, k));    // counts its own launches
     return LB200_OK;
   }
+  // Calibrated I/Q balance or channel-2 phasing: the transform kernels deliver the plain fft1_b
+  // spectrum and fft1_iqpost_kernel does the rest of fft1_b and all of fft1_c (fft1_post.cuh)
+  const bool need_post = plan->d_foldcorr != nullptr || plan->phasing;
+  Fft1PostK pk;
+  if (need_post) {
+    memset(&pk, 0, sizeof(pk));
+    pk.k = k;
+    pk.foldcorr = plan->d_foldcorr;
+    pk.flip = (plan->d_foldcorr != nullptr && k.direction < 0) ? 1 : 0;
+    pk.first_sym = plan->first_sym;
+    pk.c1 = plan->cfg.pg_ch2_c1;
+    pk.c2 = plan->cfg.pg_ch2_c2;
+    pk.phasing = plan->phasing ? 1 : 0;
+    pk.N = plan->N;
+    k.fc_mode = 0;
+    k.sumsq = nullptr;
+    k.power_rows = nullptr;
+    if (plan->d_foldcorr) k.direction = 1;    // the reversal is fused with the correction (fft1.c:3628-3655)
+  }
+  auto post = [&]() -> int {
+    if (!need_post) return 0;
+    const int gsz = pk.k.power_rows ? 1 : pk.k.avg1num;
+    const int c0 = pk.k.power_rows ? 0 : pk.k.counter0;
+    const int ngr = (c0 + pk.k.nblocks + gsz - 1) / gsz;
+    const int chunks = (plan->N / 2 + 1 + 255) / 256;
+    long grid = (long)ngr * chunks;
+    if (grid > (long)plan->sm_count * 32) grid = (long)plan->sm_count * 32;
+    if (plan->nch == 1) fft1_iqpost_kernel<1><<<(int)grid, 256, 0, plan->stream>>>(pk);
+    else fft1_iqpost_kernel<2><<<(int)grid, 256, 0, plan->stream>>>(pk);
+    LB_CUDA(cudaGetLastError());
+    plan->launches++;
+    return 0;
+  };
   if (plan->cfg.fft1_n > 14) {
     LB_CUDA(lb_launch_fft1_large(plan, k));   // counts its own launches
-    return LB200_OK;
+    return post();
   }
   int threads = 0;
   size_t smem = 0;
@@ -406,7 +455,8 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
     }
     LB_CUDA(fn(k, grid, plan->stream));
     plan->launches++;
-    return fold();
+    if (int r = fold()) return r;
+    return post();
   }
   fft1_small_launch_t fn = lb_get_fft1_small(plan->cfg.fft1_n, plan->fmt, env_int("LB200_FFT1_VARIANT", 0), &threads, &smem);
   if (!fn) return LB200_ERR_UNSUPPORTED;
@@ -420,7 +470,8 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   if (grid > cap) grid = cap;
   LB_CUDA(fn(k, grid, plan->stream));
   plan->launches++;
-  return fold();
+  if (int r = fold()) return r;
+  return post();
 }
 
 // ---- host-ring staging helpers -----------------------------------------------------------

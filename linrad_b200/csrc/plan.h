@@ -35,6 +35,10 @@ struct lb200_plan {
   float* d_window = nullptr;
   float2* d_Wn = nullptr;      // fft1 twiddles, N entries
   float* d_filtercorr = nullptr;
+  float* d_foldcorr = nullptr; // CALIQ mirror-image correction table (mm*N floats) or nullptr
+  bool phasing = false;        // pg_ch2_c1/c2 != (1, 0)
+  int first_sym = 0;           // fft1_first_sym_point (fft1.c:4647-4650)
+  int shift_i = 0, shift_q = 0; // ui.sample_shift as frame offsets of the I and the Q word
   int fc_mode = 2;
   float fc_gain = 0.f;
   int fc_edge = 0;

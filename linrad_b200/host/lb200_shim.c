@@ -83,6 +83,8 @@ c.fftx_points_per_hz=fftx_points_per_hz;
 c.mix1_lowest_fq=mix1_lowest_fq;
 c.mix1_highest_fq=mix1_highest_fq;
 c.max_batch=1;
+c.pg_ch2_c1=pg_ch2_c1;
+c.pg_ch2_c2=pg_ch2_c2;
 shim_power=malloc((size_t)(fft1n_mask+1)*(size_t)fft1_size*sizeof(float));
 if(shim_power == NULL){shim_fail(LB200_ERR_BAD_CONFIG); return -1;}
 for(i=0; i<no_of_threads && i<LB200_SHIM_MAX_THREADS; i++)

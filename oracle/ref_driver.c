@@ -141,6 +141,19 @@ static void free_all(void)
   free(wg_waterf); wg_waterf = NULL;
 }
 
+/* I/Q mirror-image calibration (fft1.c:3607-3657, 3941-4026): install a foldcorr table and raise
+ * CALIQ; NULL switches it off again.  Channel-2 phasing (fft1.c:4064-4080, pol_graph.c:165-173). */
+void ref_set_foldcorr(const float *table)
+{
+  if (table) {
+    memcpy(fft1_foldcorr, table, sizeof(float) * twice_rxchan * fft1_size);
+    fft1_calibrate_flag |= CALIQ;
+  } else {
+    fft1_calibrate_flag &= ~CALIQ;
+  }
+}
+void ref_set_ch2_phasing(float c1, float c2) { pg_ch2_c1 = c1; pg_ch2_c2 = c2; }
+
 void ref_set_selfreq(int ss, double hz)
 {
   SEL[ss].selfreq = hz;

@@ -39,6 +39,8 @@ class RefOracle:
         L.ref_init.argtypes = [C.POINTER(RefCfg), C.c_int, C.c_int]
         L.ref_process.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_set_selfreq.argtypes = [C.c_int, C.c_double]
+        L.ref_set_foldcorr.argtypes = [C.c_void_p]
+        L.ref_set_ch2_phasing.argtypes = [C.c_float, C.c_float]
         L.ref_sel_state.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.ref_make_window.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_fftback.argtypes = [C.c_int, C.c_int, C.c_void_p]
@@ -90,6 +92,17 @@ class RefOracle:
         ptr = getattr(self.lib, fn)()
         buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
         return np.frombuffer(buf, dtype=dtype).copy()
+
+    def set_foldcorr(self, table):
+        """install fft1_foldcorr (twice_rxchan*fft1_size floats) and raise CALIQ; None = off"""
+        if table is None:
+            self.lib.ref_set_foldcorr(None)
+        else:
+            t = np.ascontiguousarray(table, np.float32)
+            self.lib.ref_set_foldcorr(t.ctypes.data)
+
+    def set_ch2_phasing(self, c1, c2):
+        self.lib.ref_set_ch2_phasing(float(c1), float(c2))
 
     def set_selfreq(self, ss, hz):
         self.lib.ref_set_selfreq(ss, float(hz))

@@ -32,11 +32,15 @@ def pow2_at_least(x):
     return p
 
 
-def run_reference(kw, raw, selbins, nblocks, want_raw=False, **extra):
+def run_reference(kw, raw, selbins, nblocks, want_raw=False, foldcorr=None, pg_ch2=None, **extra):
     from oracle.refwrap import RefOracle
     kw = dict(kw)
     version = kw.pop("version")
     r = RefOracle(fft1_version=version, n_sel=len(selbins), max_fft1n=8, **kw, **extra)
+    if foldcorr is not None:
+        r.set_foldcorr(foldcorr)
+    if pg_ch2 is not None:
+        r.set_ch2_phasing(*pg_ch2)
     hz = kw["ad_speed"] / (1 << kw["fft1_n"]) / (1 if kw["input_mode"] & IQ_DATA else 2)
     for i, fb in enumerate(selbins):
         r.set_selfreq(i, fb * hz if fb >= 0 else -1.0)
@@ -59,9 +63,10 @@ class CudaStream:
     fft1_mix1_fixed."""
 
     def __init__(self, setup, selbins, window=None, filtercorr=None, max_fft1n=8, sumsq_rows=16,
-                 timf3_size=None, timf1_bytes=None):
+                 timf3_size=None, timf1_bytes=None, foldcorr=None, sample_shift=0, pg_ch2=(1.0, 0.0)):
         self.s = setup
-        self.plan = api.Plan(setup, window=window, filtercorr=filtercorr)
+        self.plan = api.Plan(setup, window=window, filtercorr=filtercorr, foldcorr=foldcorr, sample_shift=sample_shift,
+                             pg_ch2=pg_ch2)
         N = setup.fft1_size
         # 8 transforms' worth of input (a real-input transform covers 2N frames)
         self.timf1_bytes = timf1_bytes or pow2_at_least(8 * N * setup.frame_bytes * (1 if setup.input_mode & IQ_DATA else 2))

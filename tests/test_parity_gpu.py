@@ -58,13 +58,15 @@ def _setup(kw, **over):
     return sizing.PathSetup(**k)
 
 
-def _compare(kw, nblocks, selbins, chunk, seed=1, **over):
+def _compare(kw, nblocks, selbins, chunk, seed=1, ext=None, **over):
+    """ext: the rarely used fft1_b options (foldcorr table, sample_shift, pg_ch2), given to both sides"""
     s = _setup(kw, **over)
     raw = make_timf1(s.input_mode, s.rf_channels, s.fft1_size, nblocks, s.fft1_new_points, seed=seed)
     kwr = dict(kw)
     kwr.update(over)
-    ref = run_reference(kwr, raw, selbins, nblocks, want_raw=True)
-    cs = CudaStream(s, selbins)
+    ext = ext or {}
+    ref = run_reference(kwr, raw, selbins, nblocks, want_raw=True, **ext)
+    cs = CudaStream(s, selbins, **ext)
     try:
         got = cs.process(raw, nblocks, chunk=chunk)
         # fft1_float
@@ -93,6 +95,53 @@ def _compare(kw, nblocks, selbins, chunk, seed=1, **over):
         return e
     finally:
         cs.close()
+
+
+def _foldcorr_table(n, channels, seed):
+    """a plausible calibration table: mirror coefficients of a few percent, smooth over frequency"""
+    rng = np.random.default_rng(seed)
+    N = 1 << n
+    k = np.arange(N)
+    t = np.zeros((N, 2 * channels), np.float32)
+    for c in range(channels):
+        a, b = rng.uniform(0.005, 0.03, 2)
+        ph = rng.uniform(0, 2 * np.pi, 2)
+        t[:, 2 * c] = a * np.cos(2 * np.pi * k / N + ph[0]) + 0.01
+        t[:, 2 * c + 1] = b * np.sin(4 * np.pi * k / N + ph[1])
+    return t.reshape(-1)
+
+
+@pytest.mark.parametrize("direction", [1, -1])
+@pytest.mark.parametrize("mode,ch,ver,n", [(IQ_DATA, 1, 6, 11), (IQ_DATA | TWO_CHANNELS, 2, 7, 11),
+                                            (IQ_DATA | DWORD_INPUT, 1, 7, 9), (IQ_DATA, 1, 6, 15)])
+def test_iq_mirror_correction(mode, ch, ver, n, direction):
+    """fft1_calibrate_flag & CALIQ: fft1.c:3607-3657 / 3941-4026, with the reversal of direction < 0"""
+    kw = dict(input_mode=mode, rf_channels=ch, ad_speed=96000, fft1_n=n, mix1_red_n=3, version=ver)
+    _compare(kw, 7, [300.37 * (1 << n) / 2048], chunk=3, direction=direction,
+             ext=dict(foldcorr=_foldcorr_table(n, ch, seed=n + ch)))
+
+
+def test_iq_mirror_correction_limited_range():
+    kw = dict(input_mode=IQ_DATA, rf_channels=1, ad_speed=96000, fft1_n=11, mix1_red_n=3, version=6)
+    _compare(kw, 6, [700.0], chunk=6, first_xpoint=300, xpoints=1200, ext=dict(foldcorr=_foldcorr_table(11, 1, seed=5)))
+
+
+@pytest.mark.parametrize("direction", [1, -1])
+def test_channel2_phasing(direction):
+    """pg_ch2_c1 / pg_ch2_c2 (pol_graph.c:165-173, fft1.c:4064-4080), alone and on top of CALIQ"""
+    kw = dict(input_mode=IQ_DATA | TWO_CHANNELS, rf_channels=2, ad_speed=96000, fft1_n=11, mix1_red_n=3, version=7)
+    c1, c2 = 1.07 * np.cos(0.4), -1.07 * np.sin(0.4)
+    _compare(kw, 7, [300.37], chunk=4, direction=direction, ext=dict(pg_ch2=(c1, c2)))
+    _compare(kw, 7, [300.37], chunk=4, direction=direction,
+             ext=dict(pg_ch2=(c1, c2), foldcorr=_foldcorr_table(11, 2, seed=9)))
+
+
+@pytest.mark.parametrize("shift", [-3, -1, 2])
+@pytest.mark.parametrize("mode,ver,n", [(IQ_DATA, 6, 11), (IQ_DATA, 7, 8), (IQ_DATA | DWORD_INPUT, 6, 12), (IQ_DATA, 6, 15)])
+def test_sample_shift(mode, ver, n, shift):
+    """ui.sample_shift: I and Q words taken from different frames (fft1.c:770-790, 472-483)"""
+    kw = dict(input_mode=mode, rf_channels=1, ad_speed=96000, fft1_n=n, mix1_red_n=3, version=ver)
+    _compare(kw, 7, [], chunk=3, ext=dict(sample_shift=shift))
 
 
 def test_cfg1_iq16_8192():
