@@ -218,6 +218,43 @@ int lb200_expand_rawdat(lb200_plan *plan, const void *packed, void *out, size_t 
 int lb200_widen_24bit_dev(lb200_plan *plan, const void *pcm24, void *out, size_t nsamples);
 int lb200_widen_24bit(lb200_plan *plan, const void *pcm24, void *out, size_t nsamples);
 
+/* ---- Linrad .raw recordings (modesub.c:656-733 reader, 1519-1640 writer) -------------------
+ * Little-endian, no padding:
+ *   int32 first          >= 0: this IS rx_input_mode (old format; time 0, centre 0, direction +1)
+ *                        <  0: REMEMBER_* tag (-1 unknown, -2 nothing, -3 Perseus, -4 SDR-14; the
+ *                              last two are followed by int32 chunk_size + chunk), then
+ *                              double diskread_time, double passband_center,
+ *                              int32 passband_direction (+1/-1 -> fft1_direction), int32 rx_input_mode
+ *   int32 rx_rf_channels (2 sets TWO_CHANNELS in rx_input_mode), int32 rx_ad_channels (1..4, equal to
+ *   or twice rx_rf_channels), int32 rx_ad_speed, uint8 save_init_flag (bit 0: filter calibration
+ *   follows, bit 1: I/Q calibration follows; fft1.c:5203, 4780)
+ * Payload: blocks of timf1 frames; int16 verbatim, DWORD_INPUT recordings 18-bit packed
+ * (18*block_bytes/32 bytes per block, buf.c:599, rxin.c:1643) for lb200_expand_rawdat. */
+#define LB200_REMEMBER_UNKNOWN (-1)
+#define LB200_REMEMBER_NOTHING (-2)
+#define LB200_REMEMBER_PERSEUS (-3)
+#define LB200_REMEMBER_SDR14 (-4)
+typedef struct lb200_raw_header {
+  int remember_tag;             /* remember_proprietery_chunk[0]; NOTHING for old-format files */
+  int chunk_size;               /* remember_proprietery_chunk[1] (Perseus / SDR-14), else 0 */
+  uint64_t chunk_offset;        /* file offset of that chunk, 0 when there is none */
+  double diskread_time;
+  double passband_center;       /* fg.passband_center */
+  int passband_direction;       /* fg.passband_direction == fft1_direction */
+  int rx_input_mode;            /* ui.rx_input_mode, TWO_CHANNELS or-ed in like the reader does */
+  int rx_rf_channels;
+  int rx_ad_channels;
+  int rx_ad_speed;
+  int save_init_flag;
+  uint64_t payload_offset;      /* first byte behind save_init_flag */
+} lb200_raw_header;
+/* open_savefile's header logic on a memory image of the file head.  LB200_OK, or
+ * LB200_ERR_BAD_ARG where the reference says "File corrupted" (short file, unknown tag,
+ * direction not +-1, rx_input_mode >= MODEPARM_MAX, bad channel counts). */
+int lb200_raw_header_parse(const void *bytes, size_t nbytes, lb200_raw_header *out);
+/* bytes one block of `block_bytes` timf1 bytes occupies in the file (save_rw_bytes, buf.c:599) */
+size_t lb200_raw_block_bytes(const lb200_raw_header *h, size_t block_bytes);
+
 /* Host helpers shared by the shim and the tests (pure integer / scalar logic) */
 /* set_mix1_phases (mix1.c:781-861) for one selection and one transform; returns 0 or 1211/1212 */
 int lb200_set_mix1_phases(const lb200_config *cfg, lb200_mix1_state *s, float fq);

@@ -22,7 +22,7 @@ EXPORTS = ["lb200_create", "lb200_destroy", "lb200_strerror", "lb200_abi_version
            "lb200_phase_advance", "lb200_window_to_natural",
            "lb200_update_fft1_slowsum_dev", "lb200_update_fft1_slowsum", "lb200_fft1_waterfall_dev",
            "lb200_fft1_waterfall", "lb200_expand_rawdat_dev", "lb200_expand_rawdat", "lb200_widen_24bit_dev",
-           "lb200_widen_24bit"]
+           "lb200_widen_24bit", "lb200_raw_header_parse", "lb200_raw_block_bytes"]
 
 
 class Lb200Error(RuntimeError):
@@ -45,6 +45,15 @@ class Config(C.Structure):
         ("fftx_points_per_hz", C.c_float), ("mix1_lowest_fq", C.c_float), ("mix1_highest_fq", C.c_float),
         ("max_batch", C.c_int),
         ("pg_ch2_c1", C.c_float), ("pg_ch2_c2", C.c_float),
+    ]
+
+
+class RawHeader(C.Structure):
+    _fields_ = [
+        ("remember_tag", C.c_int), ("chunk_size", C.c_int), ("chunk_offset", C.c_uint64),
+        ("diskread_time", C.c_double), ("passband_center", C.c_double), ("passband_direction", C.c_int),
+        ("rx_input_mode", C.c_int), ("rx_rf_channels", C.c_int), ("rx_ad_channels", C.c_int),
+        ("rx_ad_speed", C.c_int), ("save_init_flag", C.c_int), ("payload_offset", C.c_uint64),
     ]
 
 
@@ -133,6 +142,9 @@ def load_library():
         getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(WgConfig), C.POINTER(WgArgs)]
     for f in ("lb200_expand_rawdat_dev", "lb200_expand_rawdat", "lb200_widen_24bit_dev", "lb200_widen_24bit"):
         getattr(lib, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.lb200_raw_header_parse.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(RawHeader)]
+    lib.lb200_raw_block_bytes.argtypes = [C.POINTER(RawHeader), C.c_size_t]
+    lib.lb200_raw_block_bytes.restype = C.c_size_t
     _lib = lib
     return lib
 

@@ -82,3 +82,73 @@ extern "C" void lb200_window_to_natural(int mo, int size, const float* win, floa
     memcpy(natural, win, sizeof(float) * (size_t)size);
   }
 }
+
+// ---- Linrad .raw header (open_savefile, modesub.c:656-733) -----------------------------------
+namespace {
+struct Cursor {
+  const unsigned char* p;
+  size_t n, at;
+  bool get(void* dst, size_t k)
+  {
+    if (at + k > n) return false;
+    memcpy(dst, p + at, k);
+    at += k;
+    return true;
+  }
+};
+}  // namespace
+
+extern "C" int lb200_raw_header_parse(const void* bytes, size_t nbytes, lb200_raw_header* out)
+{
+  if (!bytes || !out) return LB200_ERR_BAD_ARG;
+  Cursor c{(const unsigned char*)bytes, nbytes, 0};
+  lb200_raw_header h;
+  memset(&h, 0, sizeof(h));
+  int first;
+  if (!c.get(&first, 4)) return LB200_ERR_BAD_ARG;
+  if (first < 0) {
+    h.remember_tag = first;
+    switch (first) {
+      case LB200_REMEMBER_UNKNOWN:
+      case LB200_REMEMBER_NOTHING:
+        break;
+      case LB200_REMEMBER_PERSEUS:
+      case LB200_REMEMBER_SDR14:
+        if (!c.get(&h.chunk_size, 4)) return LB200_ERR_BAD_ARG;
+        if (h.chunk_size < 0 || c.at + (size_t)h.chunk_size > c.n) return LB200_ERR_BAD_ARG;
+        h.chunk_offset = c.at;
+        c.at += (size_t)h.chunk_size;
+        break;
+      default:
+        return LB200_ERR_BAD_ARG;             // "This Linrad version is too old"
+    }
+    if (!c.get(&h.diskread_time, 8)) return LB200_ERR_BAD_ARG;
+    if (!c.get(&h.passband_center, 8)) return LB200_ERR_BAD_ARG;
+    if (!c.get(&h.passband_direction, 4)) return LB200_ERR_BAD_ARG;
+    if (h.passband_direction != 1 && h.passband_direction != -1) return LB200_ERR_BAD_ARG;
+    if (!c.get(&h.rx_input_mode, 4)) return LB200_ERR_BAD_ARG;
+  } else {
+    h.remember_tag = LB200_REMEMBER_NOTHING;
+    h.rx_input_mode = first;
+    h.passband_direction = 1;
+  }
+  if (h.rx_input_mode >= 256) return LB200_ERR_BAD_ARG;          // MODEPARM_MAX, globdef.h:285
+  if (!c.get(&h.rx_rf_channels, 4)) return LB200_ERR_BAD_ARG;
+  if (h.rx_rf_channels == 2) h.rx_input_mode |= LB200_TWO_CHANNELS;
+  if (!c.get(&h.rx_ad_channels, 4)) return LB200_ERR_BAD_ARG;
+  if (h.rx_ad_channels > 4 || h.rx_ad_channels < 1) return LB200_ERR_BAD_ARG;
+  if (h.rx_ad_channels != h.rx_rf_channels && h.rx_ad_channels != 2 * h.rx_rf_channels) return LB200_ERR_BAD_ARG;
+  if (!c.get(&h.rx_ad_speed, 4)) return LB200_ERR_BAD_ARG;
+  unsigned char flag;
+  if (!c.get(&flag, 1)) return LB200_ERR_BAD_ARG;
+  h.save_init_flag = flag;
+  h.payload_offset = c.at;
+  *out = h;
+  return LB200_OK;
+}
+
+extern "C" size_t lb200_raw_block_bytes(const lb200_raw_header* h, size_t block_bytes)
+{
+  if (!h) return 0;
+  return (h->rx_input_mode & LB200_DWORD_INPUT) ? 18 * block_bytes / 32 : block_bytes;
+}
