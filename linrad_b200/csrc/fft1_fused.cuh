@@ -105,6 +105,26 @@ LB_D void bulk_store(void* gdst, const void* ssrc, uint32_t bytes)
 {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 }
+// TMA bulk load global -> shared, completion counted in bytes on an mbarrier
+LB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+LB_D void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)),
+               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+// the N-frame span starting at ring offset `start` (16-byte aligned) -> dst, split at the ring wrap
+LB_D void bulk_load_span(void* dst, const uint8_t* ring, uint32_t mask, uint32_t start, uint32_t bytes, uint64_t* bar)
+{
+  const uint32_t a = start & mask;
+  const uint32_t size = mask + 1u;
+  const uint32_t n1 = size - a < bytes ? size - a : bytes;
+  mbar_expect_tx(bar, bytes);
+  bulk_load(dst, ring + a, n1, bar);
+  if (n1 < bytes) bulk_load(reinterpret_cast<unsigned char*>(dst) + n1, ring, bytes - n1, bar);
+}
 LB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 LB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 LB_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -164,9 +184,14 @@ fft1_fused_kernel(const Fft1K p)
 
   // pass-1 twiddle table [pair][k] and the window table -> shared memory; last-pass exact powers
   // -> registers
+  // int16 one-channel IQ: a span of N frames is 4N contiguous bytes, exactly the size of the
+  // window table.  Then the table stays in global memory (it lives in L1) and its place takes the
+  // raw frames of the NEXT transform, fetched by the TMA unit while this one is computed.
+  const bool stage = (FMT == FMT_I16_1CH) && p.stage_raw;
   if (P::NPASS == 3)
     for (int i = t; i < P::TAB1; i += T) tab1[i] = p.tab1[i];
-  for (int i = t; i < N; i += T) wsm[i] = p.wtab[i];
+  if (!stage)
+    for (int i = t; i < N; i += T) wsm[i] = p.wtab[i];
   float2 wb[5];
 #pragma unroll
   for (int j = 0; j < 5; j++) wb[j] = p.Wn[t << j];
@@ -174,15 +199,18 @@ fft1_fused_kernel(const Fft1K p)
   // split-phase barriers (arrive when done with a buffer, wait right before it is overwritten):
   // [0] exchange 1 has been read, [1] the last exchange has been read, [2] a staging round has
   // been written (consumer: thread 0), [3] the TMA unit has read the staged round (producer: thread 0)
-  __shared__ uint64_t bars[4];
+  // [4] the staged raw span has landed (TMA, bytes), [5] it has been read by everybody
+  __shared__ uint64_t bars[6];
   if (t == 0) {
     mbar_init(&bars[0], T);
     mbar_init(&bars[1], T);
     mbar_init(&bars[2], T);
     mbar_init(&bars[3], 1);
+    mbar_init(&bars[4], 1);
+    mbar_init(&bars[5], T);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  uint32_t par0 = 0, par1 = 0, par2 = 0, par3 = 0;
+  uint32_t par0 = 0, par1 = 0, par2 = 0, par3 = 0, par4 = 0, par5 = 0;
   bool staged = false;                       // the TMA unit may still be reading the exchange buffer
   bool first_xch = true;
   __syncthreads();
@@ -194,6 +222,11 @@ fft1_fused_kernel(const Fft1K p)
   // work item = (averaging group, channel).  The two channels of a group go to neighbouring CTAs:
   // they read the same timf1 frames at the same time (one DRAM fetch, the second CTA hits L2).
   const int nwork = ngroups * NCH;
+  if (stage && t == 0 && (int)blockIdx.x < nwork) {
+    int fb = ((int)blockIdx.x / NCH) * group_size - c0;
+    if (fb < 0) fb = 0;
+    bulk_load_span(wsm, p.timf1, p.ring_mask, p.ref0 + (uint32_t)fb * p.blockbytes - p.pre_bytes, span, &bars[4]);
+  }
   for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int g = w / NCH;
     const int c = w - g * NCH;
@@ -203,24 +236,46 @@ fft1_fused_kernel(const Fft1K p)
     if (b1 > p.nblocks) b1 = p.nblocks;
     for (int b = b0; b < b1; b++) {
       const uint32_t start = (p.ref0 + (uint32_t)b * p.blockbytes - p.pre_bytes) & p.ring_mask;
-      if (t == 0 && c == 0) {
-        // what this CTA (and its sibling) reads next: the new bytes of b+1, or the whole span of
-        // its next group
-        if (b + 1 < b1) {
-          l2_prefetch_span(p.timf1, p.ring_mask, start + span, p.blockbytes);
-        } else {
-          const int gn = (w + (int)gridDim.x) / NCH;
-          int bn = gn * group_size - c0;
-          if (bn < 0) bn = 0;
-          if (gn < ngroups && bn < p.nblocks)
-            l2_prefetch_span(p.timf1, p.ring_mask, p.ref0 + (uint32_t)bn * p.blockbytes - p.pre_bytes, span);
-        }
+      // the transform this CTA does next: b+1 of the same group, or the first of its next work item
+      uint32_t next_start;
+      bool has_next = true, next_same_group = (b + 1 < b1);
+      if (next_same_group) {
+        next_start = start + p.blockbytes;
+      } else {
+        const int gn = (w + (int)gridDim.x) / NCH;
+        int bn = gn * group_size - c0;
+        if (bn < 0) bn = 0;
+        has_next = (gn < ngroups && bn < p.nblocks);
+        next_start = p.ref0 + (uint32_t)bn * p.blockbytes - p.pre_bytes;
+      }
+      if (t == 0 && c == 0 && has_next && !stage) {
+        // pull it into L2: only the new bytes when the overlap half has just been read
+        if (next_same_group) l2_prefetch_span(p.timf1, p.ring_mask, start + span, p.blockbytes);
+        else l2_prefetch_span(p.timf1, p.ring_mask, next_start, span);
       }
       float* out_block = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
       const bool wraps = (start + span > p.ring_mask + 1u) || (p.skew_i | p.skew_q);
       float2 v[32];
       // ---- load, int -> float, window (sign and, for FC_FOLDED, gain are in the table)
-      if (!wraps) {
+      if (stage) {
+        mbar_wait(&bars[4], par4);               // the TMA unit has delivered this transform's span
+        par4 ^= 1;
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(wsm) + t;
+        const float* wg = p.wtab + t;
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          const uint32_t x = rw[e * T];
+          const float2 s = make_float2((float)(short)(x & 0xffffu), (float)(short)(x >> 16));
+          const float wv = __ldg(wg + e * T);
+          v[e] = p.direction > 0 ? make_float2(s.y * -wv, s.x * wv) : make_float2(s.x * wv, s.y * -wv);
+        }
+        mbar_arrive(&bars[5]);                   // my reads of the span are done
+        if (t == 0 && has_next) {
+          mbar_wait(&bars[5], par5);             // everybody's are: fetch the next span into its place
+          bulk_load_span(wsm, p.timf1, p.ring_mask, next_start, span, &bars[4]);
+        }
+        par5 ^= 1;
+      } else if (!wraps) {
         const uint8_t* src = p.timf1 + start + (uint32_t)t * FRAME + c * CHB;
         if (p.direction > 0) {
 #pragma unroll

@@ -71,6 +71,7 @@ struct Fft1K {
   // ui.sample_shift (one-channel IQ only, fft1.c:770-790): byte offsets of the frame the I word
   // and the frame the Q word of sample n are taken from, relative to frame n (both 0 = off)
   int skew_i, skew_q;
+  int stage_raw;            // fft1_fused_kernel, int16 one-channel IQ: raw spans by TMA bulk load (16-byte aligned spans only)
 };
 
 // I from the frame at off + skew_i, Q from the frame at off + skew_q (one-channel IQ formats)

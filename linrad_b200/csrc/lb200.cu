@@ -453,6 +453,10 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
       const long per_cta = ((long)ngroups * plan->nch * group + grid - 1) / grid;      // transforms per CTA
       if (per_cta >= 8) k.stagger_ns = (uint32_t)env_int("LB200_STAGGER_NS", 0);
     }
+    // int16 one-channel IQ: raw spans by TMA bulk load when every span starts 16-byte aligned
+    k.stage_raw = (plan->fmt == FMT_I16_1CH && !(k.skew_i | k.skew_q) && ((k.ref0 - k.pre_bytes) & 15u) == 0 &&
+                   (k.blockbytes & 15u) == 0 && ((uintptr_t)k.timf1 & 15u) == 0 && k.ring_mask >= 15u)
+                      ? env_int("LB200_STAGE_RAW", 1) : 0;
     LB_CUDA(fn(k, grid, plan->stream));
     plan->launches++;
     if (int r = fold()) return r;
