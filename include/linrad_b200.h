@@ -93,7 +93,9 @@ typedef struct lb200_config {
                                    (fft1.c:4064-4080) */
 } lb200_config;
 
-/* Ring-buffer descriptor: base pointer + power-of-two size (the reference's xxx_mask+1). */
+/* Ring-buffer descriptor: base pointer + power-of-two size (the reference's xxx_mask+1).
+ * Device rings (the *_dev entry points) must be 16-byte aligned (Linrad's own buffers are,
+ * buf.c:2105; the host-ring entry points stage through aligned mirrors). */
 typedef struct lb200_ring {
   void *base;
   size_t size;                  /* bytes for timf1, floats for fft1_float/fft1_sumsq/timf3_float */

@@ -27,6 +27,14 @@ namespace lb {
 #ifndef LB_LARGE_LT
 #define LB_LARGE_LT 3
 #endif
+// points per thread (log2) of the column / row transforms
+#ifndef LB_LARGE_LE
+#define LB_LARGE_LE 4
+#endif
+// resident CTAs per SM asked of the compiler for CTAs of more than 256 threads
+#ifndef LB_LARGE_MINB
+#define LB_LARGE_MINB 1
+#endif
 
 struct Fft1LargeK {
   Fft1K k;               // same parameter block as the single-CTA kernel
@@ -42,7 +50,7 @@ struct Fft1LargeK {
 
 // ------------------------------------------------------------------------------ step A
 template <int LOG2N1, int LOG2N2, int LOG2E, int LOG2TA, int FMT>
-__global__ void __launch_bounds__(1 << (LOG2N1 - LOG2E + LOG2TA), (1 << (LOG2N1 - LOG2E + LOG2TA)) <= 256 ? 3 : 1)
+__global__ void __launch_bounds__(1 << (LOG2N1 - LOG2E + LOG2TA), (1 << (LOG2N1 - LOG2E + LOG2TA)) <= 256 ? 3 : LB_LARGE_MINB)
 fft1_large_cols_kernel(const Fft1LargeK q)
 {
   using P = Plan<LOG2N1, LOG2E>;
@@ -103,7 +111,7 @@ fft1_large_cols_kernel(const Fft1LargeK q)
 
 // ------------------------------------------------------------------------------ step B
 template <int LOG2N1, int LOG2N2, int LOG2E, int LOG2TB, int NCH>
-__global__ void __launch_bounds__(1 << (LOG2N2 - LOG2E + LOG2TB), (1 << (LOG2N2 - LOG2E + LOG2TB)) <= 256 ? 3 : 1)
+__global__ void __launch_bounds__(1 << (LOG2N2 - LOG2E + LOG2TB), (1 << (LOG2N2 - LOG2E + LOG2TB)) <= 256 ? 3 : LB_LARGE_MINB)
 fft1_large_rows_kernel(const Fft1LargeK q)
 {
   using P = Plan<LOG2N2, LOG2E>;

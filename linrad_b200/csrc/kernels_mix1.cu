@@ -3,6 +3,11 @@
 #include "mix1.cuh"
 using namespace lb;
 
+// points per thread (log2) of the back-transform for mix1.size 512 and 1024
+#ifndef LB_MIX1_LE_MID
+#define LB_MIX1_LE_MID 3
+#endif
+
 // transforms side by side in one CTA: fill about 512 threads, at most 8
 template <int LOG2M, int LOG2E, int NCH>
 struct Mix1Par {
@@ -45,8 +50,8 @@ typedef cudaError_t (*mix1_launch_t)(const Mix1K&, int grid, cudaStream_t);
 // memory with the predecessor's tail kept on chip.  (The reference allows up to 32768, buf.c:856.)
 mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem, int* par)
 {
-  LB_MCASE(3, 3) LB_MCASE(4, 3) LB_MCASE(5, 3) LB_MCASE(6, 3) LB_MCASE(7, 3) LB_MCASE(8, 3) LB_MCASE(9, 3)
-  LB_MCASE(10, 3) LB_MCASE(11, 4) LB_MCASE(12, 4)
+  LB_MCASE(3, 3) LB_MCASE(4, 3) LB_MCASE(5, 3) LB_MCASE(6, 3) LB_MCASE(7, 3) LB_MCASE(8, 3) LB_MCASE(9, LB_MIX1_LE_MID)
+  LB_MCASE(10, LB_MIX1_LE_MID) LB_MCASE(11, 4) LB_MCASE(12, 4)
   if (log2m == 13 && nch == 1) LB_MCASE1(13, 4, 1)
   return nullptr;
 }

@@ -291,6 +291,7 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   if ((size_t)plan->fft1_block * a->nblocks > a->fft1_float.size) return LB200_ERR_BAD_ARG;
   if ((size_t)plan->blockbytes * a->nblocks + (size_t)plan->pre_bytes > a->timf1.size) return LB200_ERR_BAD_ARG;
   if (a->fft1_pa % plan->fft1_block) return LB200_ERR_BAD_ARG;
+  if (((uintptr_t)a->fft1_float.base & 15u) || ((uintptr_t)a->timf1.base & 15u)) return LB200_ERR_BAD_ARG;   // 128-bit / TMA accesses
   if (a->apply_filtercorr && plan->fc_mode == 0) return LB200_ERR_BAD_CONFIG;
   cudaSetDevice(plan->device);
   Fft1K k;
