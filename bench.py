@@ -427,31 +427,43 @@ def main():
         st2 = api.new_states([s.selfreq_for_bin(b) for b in selbins])
         os.environ["LB200_NO_HOSTREGISTER"] = "1"      # buffers are already pinned
 
-        def e2e_step():
+        def e2e_step(keep=False):
             plan2.fft1_host(timf1=h_timf1.numpy(), ref=0, nblocks=Be, fft1=h_fft1.numpy(), fft1_pa=0, apply_fc=True,
-                            sumsq=h_sumsq.numpy(), sumsq_pa=0, counter=0)
+                            sumsq=h_sumsq.numpy(), sumsq_pa=0, counter=0, keep_on_device=keep)
             if nsel:
                 plan2.mix1_host(fft1=h_fft1.numpy(), fft1_px=0, nblocks=Be, states=st2, timf3=h_timf3.numpy(),
                                 timf3_floats=t3s, timf3_pa=0)
 
-        for _ in range(3):
-            e2e_step()
-        h0, d0 = plan2.h2d_bytes(), plan2.d2h_bytes()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        nrep = max(3, args.steps // 2)
-        for _ in range(nrep):
-            e2e_step()
-        plan2.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": Be * spt * nrep * world / dt / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": (plan2.h2d_bytes() - h0) // nrep, "d2h_bytes_per_step": (plan2.d2h_bytes() - d0) // nrep,
-               "batch": Be, "api": "lb200_fft1 + lb200_mix1 on pinned host rings"}
+        def e2e_run(keep):
+            for _ in range(3):
+                e2e_step(keep)
+            h0, d0 = plan2.h2d_bytes(), plan2.d2h_bytes()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            nrep = max(3, args.steps // 2)
+            for _ in range(nrep):
+                e2e_step(keep)
+            plan2.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return {"value": Be * spt * nrep * world / dt / 1e6, "unit": "Msamples/s",
+                    "h2d_bytes_per_step": (plan2.h2d_bytes() - h0) // nrep, "d2h_bytes_per_step": (plan2.d2h_bytes() - d0) // nrep,
+                    "batch": Be}
+
+        # the drop-in call: everything the reference's fft1_b / fft1_c / fft1_mix1_fixed leave in host
+        # memory comes back (fft1_float, fft1_sumsq, timf3)
+        e2e = e2e_run(False)
+        e2e["api"] = "lb200_fft1 + lb200_mix1 on pinned host rings"
+        if nsel:
+            # same calls with LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE: for set-ups where mix1 is the only
+            # reader of fft1_float (second FFT / AFC / network output off), informational
+            lazy = e2e_run(True)
+            lazy["api"] = "same, fft1_float kept in the device mirror (LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE); fft1_sumsq and timf3 come back"
+            e2e["spectrum_on_device"] = lazy
         plan2.close()
 
     cpu = None

@@ -116,7 +116,13 @@ typedef struct lb200_fft1_args {
   float *power_rows;            /* optional: nblocks rows of fft1_size floats = per-transform
                                    |z|^2 (lets a host fft1_c keep the reference's own
                                    accumulation order); NULL to skip */
+  int flags;                    /* LB200_FFT1_* (ABI 2) */
 } lb200_fft1_args;
+/* lb200_fft1 (host rings) only: leave fft1_float in the plan's device mirror of the ring and do
+ * not write the host ring.  For set-ups where nothing on the host reads the spectrum (second FFT
+ * and AFC off, no fft1 network output: its only consumer is mix1, and lb200_mix1 finds the
+ * transforms in the mirror).  Saves 8*C*N bytes of device-to-host traffic per transform. */
+#define LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE 1
 
 /* per-selection mix1 state, the reference's per-ss globals (selvar.c:213-220) */
 typedef struct lb200_mix1_state {

@@ -66,8 +66,11 @@ class Fft1Args(C.Structure):
         ("timf1", Ring), ("timf1p_ref", C.c_uint32), ("nblocks", C.c_int),
         ("fft1_float", Ring), ("fft1_pa", C.c_uint32), ("apply_filtercorr", C.c_int),
         ("fft1_sumsq", Ring), ("fft1_sumsq_pa", C.c_uint32), ("fft1_sumsq_counter", C.c_int),
-        ("power_rows", C.c_void_p),
+        ("power_rows", C.c_void_p), ("flags", C.c_int),
     ]
+
+
+FFT1_SPECTRUM_STAYS_ON_DEVICE = 1
 
 
 class Mix1State(C.Structure):
@@ -267,11 +270,12 @@ class Plan:
             raise Lb200Error(rc, "lb200_fft1_dev")
 
     def fft1_host(self, *, timf1, ref, nblocks, fft1, fft1_pa=0, apply_fc=True, sumsq=None, sumsq_pa=0,
-                  counter=0, power=None):
+                  counter=0, power=None, keep_on_device=False):
         """numpy arrays standing in for Linrad's host rings (sizes must be powers of two)."""
         a = self._fft1_args(timf1.ctypes.data, timf1.nbytes, ref, nblocks, fft1.ctypes.data, fft1.size, fft1_pa,
                             apply_fc, _ptr(sumsq), 0 if sumsq is None else sumsq.size, sumsq_pa, counter,
                             _ptr(power))
+        a.flags = FFT1_SPECTRUM_STAYS_ON_DEVICE if keep_on_device else 0
         rc = self.lib.lb200_fft1(self.h, C.byref(a))
         if rc:
             raise Lb200Error(rc, "lb200_fft1")

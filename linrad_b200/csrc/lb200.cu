@@ -628,8 +628,9 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
     LB_CUDA(cudaEventRecord(e_k, plan->stream));
     LB_CUDA(cudaStreamWaitEvent(plan->s_out, e_k, 0));
     // ---- output
-    if ((rc = ring_copy_on(plan, plan->s_out, plan->m_fft1.d, a->fft1_float.base, a->fft1_float.size * 4, (size_t)d.fft1_pa * 4,
-                           (size_t)plan->fft1_block * n * 4, false))) return rc;
+    if (!(a->flags & LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE))
+      if ((rc = ring_copy_on(plan, plan->s_out, plan->m_fft1.d, a->fft1_float.base, a->fft1_float.size * 4, (size_t)d.fft1_pa * 4,
+                             (size_t)plan->fft1_block * n * 4, false))) return rc;
     if (want_power) {
       const size_t bytes = sizeof(float) * (size_t)plan->N * n;
       LB_CUDA(cudaMemcpyAsync(a->power_rows + (size_t)done * plan->N, d.power_rows, bytes, cudaMemcpyDeviceToHost, plan->s_out));

@@ -107,3 +107,42 @@ def test_batch_four_step_200_transforms():
 
 def test_batch_real_input_300_transforms():
     _check("cfg3", 300, [], period=8, nref=10, over=dict(fft1_n=13))
+
+
+def test_spectrum_stays_on_device_flag():
+    """LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE: the host fft1_float ring is not written, lb200_mix1 reads
+    the transforms from the plan's device mirror; fft1_sumsq and timf3 are the same as without it."""
+    kw = dict(CONFIGS["cfg2"])
+    s = sizing.PathSetup(**{a: b for a, b in kw.items() if a != "version"})
+    nblocks, sel = 23, [6000.74]
+    raw = make_timf1(s.input_mode, s.rf_channels, s.fft1_size, nblocks, s.fft1_new_points, seed=3)
+    rawb = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)[: nblocks * s.timf1_blockbytes]
+    hz = s.ad_speed / s.fft1_size
+    res = []
+    for keep in (False, True):
+        timf1, fft1, sumsq, timf3, t3size = _rings(s, nblocks, 1)
+        timf1[: rawb.size] = rawb
+        plan = api.Plan(s)
+        states = api.new_states([sel[0] * hz])
+        try:
+            done, pa, counter, t3pa = 0, 0, 0, 0
+            for nb in (9, 14):
+                plan.fft1_host(timf1=timf1, ref=done * s.timf1_blockbytes, nblocks=nb, fft1=fft1, fft1_pa=done * s.fft1_block,
+                               sumsq=sumsq, sumsq_pa=pa, counter=counter, keep_on_device=keep)
+                tot = counter + nb
+                pa += (tot // s.avg1num) * s.fft1_size
+                counter = tot % s.avg1num
+                plan.mix1_host(fft1=fft1, fft1_px=done * s.fft1_block, nblocks=nb, states=states, timf3=timf3,
+                               timf3_floats=t3size, timf3_pa=t3pa)
+                t3pa += nb * s.timf3_block
+                done += nb
+            plan.synchronize()
+            d2h = plan.d2h_bytes()
+        finally:
+            plan.close()
+        res.append((fft1.copy(), sumsq.copy(), timf3.copy(), d2h))
+    (f0, p0, t0, d0), (f1, p1, t1, d1) = res
+    assert np.abs(f0).max() > 0 and not f1.any()                  # host ring untouched
+    assert np.allclose(p0, p1, rtol=2e-6, atol=0)
+    assert np.array_equal(t0, t1)
+    assert d0 - d1 == nblocks * s.fft1_block * 4                  # exactly the spectrum stayed behind
