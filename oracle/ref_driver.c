@@ -57,6 +57,24 @@ typedef struct {
   double selfreq;
 } sel_state;
 
+/* -DLB200_USE_SHIM: the same harness with the three hot-path calls routed through
+ * linrad_b200/host/lb200_shim.c (i.e. liblinrad_b200.so on the GPU) -- the integration test of
+ * the drop-in boundary: the shim reads the reference's OWN globals and tables. */
+#ifdef LB200_USE_SHIM
+int lb200_shim_open(int no_of_threads);
+void lb200_shim_close(void);
+void lb200_shim_fft1_b(int timf1p_ref, float *out, float *tmp, int gpu_handle_number);
+void lb200_shim_fft1_c(void);
+void lb200_shim_mix1_fixed(void);
+#define HOT_FFT1_B lb200_shim_fft1_b
+#define HOT_FFT1_C lb200_shim_fft1_c
+#define HOT_MIX1_FIXED lb200_shim_mix1_fixed
+#else
+#define HOT_FFT1_B fft1_b
+#define HOT_FFT1_C fft1_c
+#define HOT_MIX1_FIXED fft1_mix1_fixed
+#endif
+
 static ref_cfg C;
 static sel_state SEL[REF_MAX_SEL];
 static float *timf3_all;        /* n_sel regions of 2*timf3_size floats */
@@ -165,6 +183,9 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   int i, j, k, v, mode_row;
   unsigned int ui_, uj, uk;
   float t1;
+#ifdef LB200_USE_SHIM
+  if (inited) lb200_shim_close();
+#endif
   if (inited) free_all();
   C = *cfg;
   ref_last_lirerr = 0;
@@ -372,7 +393,18 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
     SEL[i].selfreq = -1; SEL[i].point = -1;
   }
   inited = 1;
+#ifdef LB200_USE_SHIM
+  if (lb200_shim_open(1) != 0) return ref_last_lirerr ? ref_last_lirerr : -1;
+#endif
   return ref_last_lirerr;
+}
+int ref_uses_shim(void)
+{
+#ifdef LB200_USE_SHIM
+  return 1;
+#else
+  return 0;
+#endif
 }
 
 /* append nblocks*timf1_blockbytes bytes of raw samples to the timf1 ring and
@@ -390,7 +422,7 @@ int ref_process(const void *data, int nblocks, float *fft1_out, float *raw_out, 
     timf1p_pa = (timf1p_pa + timf1_blockbytes) & timf1_bytemask;
     timf1p_pb = timf1p_pa;
     /* wcw.c:1036-1047 */
-    fft1_b(timf1p_px, &fft1_float[fft1_pa], fftw_tmp, 0);
+    HOT_FFT1_B(timf1p_px, &fft1_float[fft1_pa], fftw_tmp, 0);
     timf1p_px = (timf1p_px + timf1_blockbytes) & timf1_bytemask;
     if (raw_out) memcpy(raw_out + (size_t)b * fft1_mulblock, &fft1_float[fft1_pa], sizeof(float) * fft1_mulblock);
     fft1_pa = (fft1_pa + fft1_mulblock) & fft1_mask;
@@ -400,7 +432,7 @@ int ref_process(const void *data, int nblocks, float *fft1_out, float *raw_out, 
     while (fft1_na != fft1_nb) {
       int at = fft1_nb * fft1_block;
       size_t tno = (size_t)b * fft1_muln + sub;      /* running transform number */
-      fft1_c();
+      HOT_FFT1_C();
       fft1_waterfall();
       if (fft1_out) memcpy(fft1_out + tno * fft1_block, &fft1_float[at], sizeof(float) * fft1_block);
       /* wcw.c:1706-1716, one fft1_mix1_fixed per transform; selections looped here (MAX_MIX1==1) */
@@ -413,7 +445,7 @@ int ref_process(const void *data, int nblocks, float *fft1_out, float *raw_out, 
           mix1_phase[0] = SEL[ss].phase; mix1_phase_step[0] = SEL[ss].phase_step;
           mix1_phase_rot[0] = SEL[ss].phase_rot; mix1_old_phase[0] = SEL[ss].old_phase;
           mix1_point[0] = SEL[ss].point; mix1_old_point[0] = SEL[ss].old_point;
-          fft1_mix1_fixed();
+          HOT_MIX1_FIXED();
           SEL[ss].phase = mix1_phase[0]; SEL[ss].phase_step = mix1_phase_step[0];
           SEL[ss].phase_rot = mix1_phase_rot[0]; SEL[ss].old_phase = mix1_old_phase[0];
           SEL[ss].point = mix1_point[0]; SEL[ss].old_point = mix1_old_point[0];

@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libref_oracle.so")
+SHIM_SO = os.path.join(_HERE, "_ref", "libref_shim.so")     # same harness, hot path through lb200_shim.c (GPU)
 
 DWORD_INPUT, TWO_CHANNELS, IQ_DATA = 1, 2, 4
 
@@ -27,14 +28,18 @@ def available():
     return os.path.exists(REF_SO)
 
 
+def shim_available():
+    return os.path.exists(SHIM_SO)
+
+
 class RefOracle:
     """One instance at a time (the reference keeps its state in globals)."""
 
     def __init__(self, *, input_mode, rf_channels, ad_speed, fft1_n, fft1_version, sinpow=2,
                  fft1_gain=2000, mix1_red_n=4, avg1num=5, avg2num=4, waterfall_avgnum=10,
                  direction=1, n_sel=0, first_xpoint=0, xpoints=None, xpoints_per_pixel=1,
-                 pixels_per_xpoint=1, wf_lines=8, sample_shift=0, timf1_bytes=None, max_fft1n=8):
-        self.lib = C.CDLL(REF_SO)
+                 pixels_per_xpoint=1, wf_lines=8, sample_shift=0, timf1_bytes=None, max_fft1n=8, through_shim=False):
+        self.lib = C.CDLL(SHIM_SO if through_shim else REF_SO)
         L = self.lib
         L.ref_init.argtypes = [C.POINTER(RefCfg), C.c_int, C.c_int]
         L.ref_process.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]

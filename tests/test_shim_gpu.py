@@ -1,0 +1,47 @@
+"""The drop-in boundary, exercised the way Linrad would: oracle/_ref/libref_shim.so is the compiled
+reference (its own globals, tables, ring indices, fft1_waterfall, update_fft1_slowsum ...) with the
+three hot-path calls -- fft1_b, fft1_c, fft1_mix1_fixed -- replaced by linrad_b200/host/lb200_shim.c,
+which forwards to liblinrad_b200.so.  Same input through the untouched reference
+(libref_oracle.so): spectra, power sums, baseband and the mixer's state must agree."""
+import numpy as np
+import pytest
+
+from linrad_b200.synth import make_timf1
+from oracle import refwrap
+from tests.helpers import rel_rms, run_reference, IQ_DATA, DWORD_INPUT, TWO_CHANNELS
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (refwrap.available() and refwrap.shim_available()), reason="oracle/_ref not built")]
+
+
+@pytest.mark.parametrize("mode,ch,ver,n,sinpow", [
+    (IQ_DATA, 1, 6, 11, 2),                                   # radix-4 DIT tables (window layout mo=4)
+    (IQ_DATA, 1, 7, 10, 2),                                   # radix-2 DIF tables (interleaved window, mo=1)
+    (IQ_DATA | TWO_CHANNELS | DWORD_INPUT, 2, 7, 10, 2),
+    (IQ_DATA | TWO_CHANNELS, 2, 6, 10, 3),                    # crossover-window mixer
+    (0, 1, 2, 10, 2),                                         # real input, fft1_re.c
+])
+def test_shim_inside_the_reference(mode, ch, ver, n, sinpow):
+    kw = dict(input_mode=mode, rf_channels=ch, ad_speed=96000, fft1_n=n, mix1_red_n=3, version=ver, sinpow=sinpow)
+    N = 1 << n
+    nblocks = 12
+    P = None
+    a = run_reference(kw, np.zeros(16, np.int16), [], 0)      # sizes only
+    P = a["ref"].lib.ref_new_points()
+    raw = make_timf1(mode, ch, N, nblocks, P, seed=7)
+    sel = [N * 0.146 + 0.37]
+    ref = run_reference(kw, raw, sel, nblocks)
+    got = run_reference(kw, raw, sel, nblocks, through_shim=True)
+    assert got["ref"].lib.ref_uses_shim() == 1 and ref["ref"].lib.ref_uses_shim() == 0
+    assert rel_rms(got["fft1"], ref["fft1"]) <= 1e-5
+    rows = nblocks // 5
+    a, b = got["sumsq"][: rows * N].astype(np.float64), ref["sumsq"][: rows * N].astype(np.float64)
+    strong = b > 1e-4 * b.max()
+    assert (np.abs(a - b)[strong] <= 1e-4 * b[strong]).all()
+    assert (got["sumsq_pa"], got["sumsq_counter"]) == (ref["sumsq_pa"], ref["sumsq_counter"])
+    assert got["timf3_pa"] == ref["timf3_pa"]
+    sg, sr = got["states"][0], ref["states"][0]
+    assert sg["point"] == sr["point"] and float(sg["phase"]) == float(sr["phase"])
+    assert rel_rms(got["timf3"][1:, 0], ref["timf3"][1:, 0]) <= 1e-4
+    # the reference's own consumers ran on the shim's output: slowsum / waterfall stay consistent
+    assert np.allclose(got["ref"].slowsum(), ref["ref"].slowsum(), rtol=2e-4, atol=1e-3 * float(np.abs(ref["ref"].slowsum()).max()))
