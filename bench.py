@@ -72,6 +72,16 @@ def cpu_workload(name):
     return kw, version, selbins, note
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def samples_per_transform(s):
     """new input samples per transform (real input: 2P real samples)"""
     return s.fft1_new_points * (1 if s.input_mode & IQ else 2)
@@ -212,6 +222,8 @@ def reference_arm(args, rank, world):
         "config": {"workload": WORKLOAD_TEXT[args.workload], "blocks_per_step_per_core": blocks,
                    "reference_fft1_version": version},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                         "cpu_model": cpu_model(), "nproc": os.cpu_count(),
+                         "algorithmic_GBps": alg_bytes(s, len(selbins))["total"] * value * 1e6 / samples_per_transform(s) / 1e9,
                          "sample": f"{blocks} transforms per core per step, {cores} independent pipelines, "
                                    f"fft1_b(v{version})+fft1_c+fft1_waterfall+fft1_mix1_fixed compiled from the reference C files (-O2 -ffast-math)"
                                    + (f"; {note}" if note else "")},
@@ -241,7 +253,10 @@ def cpu_baseline_quick(workload, seconds=12.0):
             r.process_timed(raw, blocks)
             n += blocks
         dt = time.perf_counter() - t0
-        return {"value": n * samples_per_transform(s) / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "reference",
+        v = n * samples_per_transform(s) / dt / 1e6
+        return {"value": v, "unit": "Msamples/s", "cores": 1, "kind": "reference", "cpu_model": cpu_model(),
+                "nproc": os.cpu_count(),
+                "algorithmic_GBps": alg_bytes(s, len(selbins))["total"] * v * 1e6 / samples_per_transform(s) / 1e9,
                 "sample": f"{n} transforms in {dt:.1f} s, one thread: fft1_b(v{version})+fft1_c+fft1_waterfall+"
                           f"fft1_mix1_fixed from the reference C files (-O2 -ffast-math); nproc={os.cpu_count()}"
                           + (f"; {note}" if note else "")}
@@ -464,6 +479,23 @@ def main():
             lazy = e2e_run(True)
             lazy["api"] = "same, fft1_float kept in the device mirror (LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE); fft1_sumsq and timf3 come back"
             e2e["spectrum_on_device"] = lazy
+        # Linrad-sized calls: one transform per call, as the shim issues them (real-time use)
+        def one_block(i):
+            plan2.fft1_host(timf1=h_timf1.numpy(), ref=(i % Be) * s.timf1_blockbytes, nblocks=1, fft1=h_fft1.numpy(),
+                            fft1_pa=(i % Be) * s.fft1_block, apply_fc=True, sumsq=h_sumsq.numpy(), sumsq_pa=0, counter=0)
+            if nsel:
+                plan2.mix1_host(fft1=h_fft1.numpy(), fft1_px=(i % Be) * s.fft1_block, nblocks=1, states=st2,
+                                timf3=h_timf3.numpy(), timf3_floats=t3s, timf3_pa=0)
+        for i in range(10):
+            one_block(i)
+        plan2.synchronize()
+        t0 = time.perf_counter()
+        for i in range(50):
+            one_block(10 + i)
+        plan2.synchronize()
+        lat = (time.perf_counter() - t0) / 50
+        e2e["single_block_call_us"] = lat * 1e6
+        e2e["single_block_realtime_margin"] = (spt / s.ad_speed) / lat      # sample time of one block / time to process it
         plan2.close()
 
     cpu = None
