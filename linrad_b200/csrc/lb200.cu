@@ -221,11 +221,16 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
     if ((rc = upload(plan, (void**)&plan->d_fqwin, cfg->mix1_fqwin, sizeof(float) * (plan->M / 2 + 1)))) return fail(rc);
     const int Mi = cfg->mix1_interleave_points, Mn = plan->M - Mi;
     if (Mi != 0 && Mi != Mn) {
-      if (!cfg->mix1_window || !cfg->mix1_cos2win || !cfg->mix1_sin2win || cfg->mix1_crossover_points <= 0)
+      // prepare_mixer (buf.c:55-111) can come out with no crossover region at all (tiny mix1.size
+      // with a wide window): then only the inverse window is used
+      const int cross = cfg->mix1_crossover_points;
+      if (!cfg->mix1_window || cross < 0 || (cross > 0 && (!cfg->mix1_cos2win || !cfg->mix1_sin2win)))
         return fail(LB200_ERR_BAD_CONFIG);
       if ((rc = upload(plan, (void**)&plan->d_mixwin, cfg->mix1_window, sizeof(float) * (plan->M / 2 + 1)))) return fail(rc);
-      if ((rc = upload(plan, (void**)&plan->d_cos2win, cfg->mix1_cos2win, sizeof(float) * cfg->mix1_crossover_points))) return fail(rc);
-      if ((rc = upload(plan, (void**)&plan->d_sin2win, cfg->mix1_sin2win, sizeof(float) * cfg->mix1_crossover_points))) return fail(rc);
+      if (cross > 0) {
+        if ((rc = upload(plan, (void**)&plan->d_cos2win, cfg->mix1_cos2win, sizeof(float) * cross))) return fail(rc);
+        if ((rc = upload(plan, (void**)&plan->d_sin2win, cfg->mix1_sin2win, sizeof(float) * cross))) return fail(rc);
+      }
     }
   }
   // the plan keeps its own copies; never dereference the caller's table pointers again
@@ -343,13 +348,17 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   }
   // Calibrated I/Q balance or channel-2 phasing: the transform kernels deliver the plain fft1_b
   // spectrum and fft1_iqpost_kernel does the rest of fft1_b and all of fft1_c (fft1_post.cuh)
-  const bool need_post = plan->d_foldcorr != nullptr || plan->phasing;
+  // fft1_direction < 0: the reference reverses only bins [m, N-m], m = max(1, fft1_first_sym_point)
+  // (fft1.c:3660-3680); the transform kernels reverse everything, so with a display range that
+  // leaves m > 1 the bins outside it are put back by the post kernel
+  const bool partial_flip = k.direction < 0 && plan->first_sym > 1;
+  const bool need_post = plan->d_foldcorr != nullptr || plan->phasing || partial_flip;
   Fft1PostK pk;
   if (need_post) {
     memset(&pk, 0, sizeof(pk));
     pk.k = k;
     pk.foldcorr = plan->d_foldcorr;
-    pk.flip = (plan->d_foldcorr != nullptr && k.direction < 0) ? 1 : 0;
+    pk.flip = (k.direction < 0) ? 1 : 0;
     pk.first_sym = plan->first_sym;
     pk.c1 = plan->cfg.pg_ch2_c1;
     pk.c2 = plan->cfg.pg_ch2_c2;
@@ -358,7 +367,7 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
     k.fc_mode = 0;
     k.sumsq = nullptr;
     k.power_rows = nullptr;
-    if (plan->d_foldcorr) k.direction = 1;    // the reversal is fused with the correction (fft1.c:3628-3655)
+    if (k.direction < 0) k.direction = 1;     // the reversal is done by the post kernel, over the reference's bin range (fft1.c:3628-3680)
   }
   auto post = [&]() -> int {
     if (!need_post) return 0;

@@ -247,7 +247,7 @@ class PathSetup:
         self.mix1_crossover_points = cross
         cos2 = np.zeros(max(cross, 1), f32)
         sin2 = np.zeros(max(cross, 1), f32)
-        t1 = f32(0.25 * PI_L / cross)
+        t1 = f32(0.25 * PI_L / cross) if cross else f32(np.inf)      # C float division, buf.c:97; the loops below are empty then
         j = (M - Mn) // 2
         k = j + cross // 2
         j -= cross // 2

@@ -22,16 +22,20 @@ def power_ok(got, ref, avg):
     strongest signal also carries the single-precision rounding noise of the transform itself
     (the reference's own two C versions, fft_cntrl rows 6 and 7, differ by 3e-4 on such bins of
     the cfg1 signal and by more in spectral nulls), so the allowance per bin is
-        1e-4 * P  +  2 * sqrt(avg * P) * eps_a  +  avg * eps_a^2 ,
-        eps_a = 8 * sqrt(log2 N) * 2^-23 * A_rms
-    where A_rms is the rms bin amplitude of one transform.  eps_a is the amplitude error a
-    4..5-sigma excursion of the difference of two correctly rounded float32 FFTs reaches (their
-    rms error grows like sqrt(log2 N) ulps of the rms spectrum level); for bins within ~40 dB
-    of the rms level the allowance is the plain 1e-4."""
+        1e-4 * P  +  2 * sqrt(avg * P) * eps  +  avg * eps^2 ,
+        eps = max( 8 * sqrt(log2 N) * 2^-23 * A_rms ,  4 * 2^-23 * A_peak )
+    where A_rms is the rms and A_peak the largest bin amplitude of one transform.  The first term
+    is the amplitude error a 4..5-sigma excursion of the difference of two correctly rounded
+    float32 FFTs reaches (their rms error grows like sqrt(log2 N) ulps of the rms spectrum level);
+    the second covers a spectrum dominated by one narrow line (a sin^4 or Gaussian window and a
+    display range holding little else), where the two implementations' different twiddle
+    roundings leave errors of a few ulps of the LINE's amplitude in every bin.  For bins within
+    ~40 dB of the strongest line the allowance is the plain 1e-4."""
     got = got.astype(np.float64)
     ref = ref.astype(np.float64)
     a_rms = np.sqrt(ref.mean() / avg)
-    eps_a = 8 * np.sqrt(np.log2(got.size + 1)) * 2.0 ** -23 * a_rms
+    a_peak = np.sqrt(ref.max() / avg)
+    eps_a = max(8 * np.sqrt(np.log2(got.size + 1)) * 2.0 ** -23 * a_rms, 4 * 2.0 ** -23 * a_peak)
     allow = TOL_POWER * ref + 2 * np.sqrt(avg * ref) * eps_a + avg * eps_a ** 2
     worst = float((np.abs(got - ref) / allow).max())
     return worst <= 1.0, worst
@@ -58,7 +62,7 @@ def _setup(kw, **over):
     return sizing.PathSetup(**k)
 
 
-def _compare(kw, nblocks, selbins, chunk, seed=1, ext=None, **over):
+def _compare(kw, nblocks, selbins, chunk, seed=1, ext=None, power_slack=1.0, **over):
     """ext: the rarely used fft1_b options (foldcorr table, sample_shift, pg_ch2), given to both sides"""
     s = _setup(kw, **over)
     raw = make_timf1(s.input_mode, s.rf_channels, s.fft1_size, nblocks, s.fft1_new_points, seed=seed)
@@ -69,18 +73,27 @@ def _compare(kw, nblocks, selbins, chunk, seed=1, ext=None, **over):
     cs = CudaStream(s, selbins, **ext)
     try:
         got = cs.process(raw, nblocks, chunk=chunk)
-        # fft1_float
-        e = rel_rms(got["fft1"], ref["fft1"])
-        assert e <= TOL_FFT1, f"fft1_float rel rms {e}"
-        # fft1_sumsq: every completed row, per bin; index bookkeeping bit-exact
+        # fft1_float: the bins fft1_c has scaled (first..last) against their own energy; the bins
+        # outside the display range keep the raw fft1_b scale (orders of magnitude larger), so they
+        # are judged against the energy of the raw spectrum
         N, lo, hi = s.fft1_size, s.fft1_first_point, s.fft1_last_point
+        mm = 2 * s.rf_channels
+        g3, r3 = got["fft1"].reshape(nblocks, N, mm), ref["fft1"].reshape(nblocks, N, mm)
+        e = rel_rms(g3[:, lo:hi + 1], r3[:, lo:hi + 1])
+        assert e <= TOL_FFT1, f"fft1_float rel rms {e}"
+        if lo > 0 or hi < N - 1:
+            out_err = ((g3[:, :lo].astype(np.float64) - r3[:, :lo]) ** 2).sum() + ((g3[:, hi + 1:].astype(np.float64) - r3[:, hi + 1:]) ** 2).sum()
+            raw_energy = (ref["raw"].astype(np.float64) ** 2).sum()
+            eo = float(np.sqrt(out_err / max(raw_energy, 1e-300)))
+            assert eo <= TOL_FFT1, f"fft1_float outside the display range: rel rms {eo} of the raw spectrum"
+        # fft1_sumsq: every completed row, per bin; index bookkeeping bit-exact
         rows = (nblocks // s.avg1num)
         assert cs.sumsq_pa == ref["sumsq_pa"] and cs.sumsq_counter == ref["sumsq_counter"]
         for r in range(min(rows, 8)):
             a = cs.sumsq[r * N + lo: r * N + hi + 1]
             b = ref["sumsq"][r * N + lo: r * N + hi + 1]
             ok, worst = power_ok(a, b, s.avg1num)
-            assert ok, f"sumsq row {r}: worst error is {worst:.2f} x the per-bin allowance"
+            assert worst <= power_slack, f"sumsq row {r}: worst error is {worst:.2f} x the per-bin allowance"
         # mix1: bin selection and phase state bit-exact, baseband within tolerance
         for ss in range(len(selbins)):
             st = ref["states"][ss]
