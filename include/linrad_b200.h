@@ -117,6 +117,12 @@ typedef struct lb200_fft1_args {
                                    |z|^2 (lets a host fft1_c keep the reference's own
                                    accumulation order); NULL to skip */
   int flags;                    /* LB200_FFT1_* (ABI 2) */
+  /* fft1_correlation_flag == 1 (two RF channels, fft1.c:4146-4152, 4189-4195): the cross spectrum
+   * 2*z1*conj(z2) of the filter-corrected channels, summed like fft1_sumsq (ABI 2) */
+  lb200_ring fft1_corrsum;      /* fft1_corrsum ring, 2*fft1_sumsq.size floats ([re,im] at 2*(fft1_sumsq
+                                   index)); needs fft1_sumsq; base==NULL to skip */
+  float *corr_rows;             /* with power_rows: nblocks rows of 2*fft1_size floats = per-transform
+                                   cross spectrum; NULL to skip */
 } lb200_fft1_args;
 /* lb200_fft1 (host rings) only: leave fft1_float in the plan's device mirror of the ring and do
  * not write the host ring.  For set-ups where nothing on the host reads the spectrum (second FFT

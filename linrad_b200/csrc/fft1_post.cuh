@@ -27,6 +27,9 @@ struct Fft1PostK {
   float c1, c2;             // pg_ch2_c1 / pg_ch2_c2
   int phasing;              // 0/1
   int N;
+  // fft1_correlation_flag == 1: cross spectrum 2*z1*conj(z2) (fft1.c:4146-4152)
+  float* corrsum;           // ring indexed like fft1_sumsq, two floats per bin; or nullptr
+  float* corr_rows;         // per-transform rows of 2N floats (with power_rows); or nullptr
 };
 
 template <int NCH>
@@ -51,6 +54,7 @@ __global__ void __launch_bounds__(256) fft1_iqpost_kernel(const Fft1PostK q)
     if (b0 < 0) b0 = 0;
     if (b1 > p.nblocks) b1 = p.nblocks;
     float accb = 0.f, accc = 0.f;
+    float2 corb = make_float2(0.f, 0.f), corc = make_float2(0.f, 0.f);
     for (int b = b0; b < b1; b++) {
       float* out = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
       float2 zb[NCH], zc[NCH];
@@ -101,6 +105,7 @@ __global__ void __launch_bounds__(256) fft1_iqpost_kernel(const Fft1PostK q)
       }
       // ---- fft1_c
       float pwb = 0.f, pwc = 0.f;
+      float2 xb = make_float2(0.f, 0.f), xc = make_float2(0.f, 0.f);
       if (p.fc_mode != 0) {
         if (ib >= p.first_point && ib <= p.last_point) {
 #pragma unroll
@@ -110,6 +115,8 @@ __global__ void __launch_bounds__(256) fft1_iqpost_kernel(const Fft1PostK q)
             zb[c] = make_float2(z.x * f.x - z.y * f.y, z.y * f.x + z.x * f.y);
             pwb += zb[c].x * zb[c].x + zb[c].y * zb[c].y;
           }
+          if (NCH == 2) xb = make_float2(2.0f * (zb[0].x * zb[NCH - 1].x + zb[0].y * zb[NCH - 1].y),
+                                         2.0f * (zb[0].y * zb[NCH - 1].x - zb[0].x * zb[NCH - 1].y));
         }
         if (pair && ic >= p.first_point && ic <= p.last_point) {
 #pragma unroll
@@ -119,6 +126,8 @@ __global__ void __launch_bounds__(256) fft1_iqpost_kernel(const Fft1PostK q)
             zc[c] = make_float2(z.x * f.x - z.y * f.y, z.y * f.x + z.x * f.y);
             pwc += zc[c].x * zc[c].x + zc[c].y * zc[c].y;
           }
+          if (NCH == 2) xc = make_float2(2.0f * (zc[0].x * zc[NCH - 1].x + zc[0].y * zc[NCH - 1].y),
+                                         2.0f * (zc[0].y * zc[NCH - 1].x - zc[0].x * zc[NCH - 1].y));
         }
       }
 #pragma unroll
@@ -130,14 +139,31 @@ __global__ void __launch_bounds__(256) fft1_iqpost_kernel(const Fft1PostK q)
         p.power_rows[(size_t)b * N + ib] = pwb;
         if (pair) p.power_rows[(size_t)b * N + ic] = pwc;
       }
+      if (NCH == 2 && q.corr_rows && p.fc_mode != 0) {
+        *reinterpret_cast<float2*>(q.corr_rows + ((size_t)b * N + ib) * 2) = xb;
+        if (pair) *reinterpret_cast<float2*>(q.corr_rows + ((size_t)b * N + ic) * 2) = xc;
+      }
       accb = (b == b0) ? pwb : accb + pwb;
       accc = (b == b0) ? pwc : accc + pwc;
+      corb = (b == b0) ? xb : make_float2(corb.x + xb.x, corb.y + xb.y);
+      corc = (b == b0) ? xc : make_float2(corc.x + xc.x, corc.y + xc.y);
     }
     if (p.sumsq && !p.power_rows && p.fc_mode != 0 && b1 > b0) {
       float* row = p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask);
       const bool continuing = (g == 0 && p.counter0 > 0);
       if (ib >= p.first_point && ib <= p.last_point) row[ib] = continuing ? row[ib] + accb : accb;
       if (pair && ic >= p.first_point && ic <= p.last_point) row[ic] = continuing ? row[ic] + accc : accc;
+      if (NCH == 2 && q.corrsum) {
+        float2* crow = reinterpret_cast<float2*>(q.corrsum) + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask);
+        if (ib >= p.first_point && ib <= p.last_point) {
+          const float2 o = crow[ib];
+          crow[ib] = continuing ? make_float2(o.x + corb.x, o.y + corb.y) : corb;
+        }
+        if (pair && ic >= p.first_point && ic <= p.last_point) {
+          const float2 o = crow[ic];
+          crow[ic] = continuing ? make_float2(o.x + corc.x, o.y + corc.y) : corc;
+        }
+      }
     }
   }
 }

@@ -262,7 +262,7 @@ extern "C" void lb200_destroy(lb200_plan* plan)
     if (plan->mixjobs_done[i]) cudaEventDestroy(plan->mixjobs_done[i]);
   }
   free_mirror(plan->m_timf1); free_mirror(plan->m_fft1); free_mirror(plan->m_sumsq);
-  free_mirror(plan->m_timf3); free_mirror(plan->m_power);
+  free_mirror(plan->m_timf3); free_mirror(plan->m_power); free_mirror(plan->m_corrsum); free_mirror(plan->m_corr);
   free_mirror(plan->m_wg_sumsq); free_mirror(plan->m_wg_slowsum); free_mirror(plan->m_wg_wsum); free_mirror(plan->m_wg_yfac);
   free_mirror(plan->m_wg_waterf); free_mirror(plan->m_codec_in); free_mirror(plan->m_codec_out);
   for (cudaEvent_t e : plan->events) cudaEventDestroy(e);
@@ -342,6 +342,7 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   k.skew_q = plan->shift_q * plan->frame;
 
   if (!plan->iq) {
+    if (a->apply_filtercorr && (a->fft1_corrsum.base || a->corr_rows)) return LB200_ERR_UNSUPPORTED;
     k.Wre = plan->d_Wre;
     LB_CUDA(lb_launch_fft1_real(plan, k));    // counts its own launches
     return LB200_OK;
@@ -352,7 +353,14 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   // (fft1.c:3660-3680); the transform kernels reverse everything, so with a display range that
   // leaves m > 1 the bins outside it are put back by the post kernel
   const bool partial_flip = k.direction < 0 && plan->first_sym > 1;
-  const bool need_post = plan->d_foldcorr != nullptr || plan->phasing || partial_flip;
+  // fft1_correlation_flag == 1 (two RF channels): cross spectrum rows next to the power rows
+  const bool want_corr = a->apply_filtercorr && (a->fft1_corrsum.base || a->corr_rows);
+  if (want_corr) {
+    if (plan->nch != 2) return LB200_ERR_UNSUPPORTED;
+    if (a->corr_rows && !k.power_rows) return LB200_ERR_BAD_ARG;
+    if (a->fft1_corrsum.base && !a->corr_rows && (!k.sumsq || a->fft1_corrsum.size != 2 * a->fft1_sumsq.size)) return LB200_ERR_BAD_ARG;
+  }
+  const bool need_post = plan->d_foldcorr != nullptr || plan->phasing || partial_flip || want_corr;
   Fft1PostK pk;
   if (need_post) {
     memset(&pk, 0, sizeof(pk));
@@ -364,6 +372,8 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
     pk.c2 = plan->cfg.pg_ch2_c2;
     pk.phasing = plan->phasing ? 1 : 0;
     pk.N = plan->N;
+    pk.corr_rows = want_corr ? a->corr_rows : nullptr;
+    pk.corrsum = (want_corr && !a->corr_rows) ? (float*)a->fft1_corrsum.base : nullptr;
     k.fc_mode = 0;
     k.sumsq = nullptr;
     k.power_rows = nullptr;
@@ -579,6 +589,8 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
   if ((rc = ensure_mirror(plan, plan->m_fft1, a->fft1_float.base, a->fft1_float.size * sizeof(float)))) return rc;
   const bool want_power = a->apply_filtercorr && a->power_rows;
   const bool want_sumsq = a->apply_filtercorr && !a->power_rows && a->fft1_sumsq.base;
+  const bool want_corr_rows = want_power && a->corr_rows;
+  const bool want_corrsum = want_sumsq && a->fft1_corrsum.base;
   const int avg = plan->cfg.fft_avg1num;
   if (want_power) {
     const size_t bytes = sizeof(float) * (size_t)plan->N * a->nblocks;
@@ -591,6 +603,19 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
   } else if (want_sumsq) {
     if (!is_pow2(a->fft1_sumsq.size)) return LB200_ERR_BAD_ARG;
     if ((rc = ensure_mirror(plan, plan->m_sumsq, a->fft1_sumsq.base, a->fft1_sumsq.size * sizeof(float)))) return rc;
+    if (want_corrsum) {
+      if (a->fft1_corrsum.size != 2 * a->fft1_sumsq.size) return LB200_ERR_BAD_ARG;
+      if ((rc = ensure_mirror(plan, plan->m_corrsum, a->fft1_corrsum.base, a->fft1_corrsum.size * sizeof(float)))) return rc;
+    }
+  }
+  if (want_corr_rows) {
+    const size_t bytes = sizeof(float) * 2 * (size_t)plan->N * a->nblocks;
+    if (!plan->m_corr.d || plan->m_corr.bytes < bytes) {
+      if (plan->m_corr.d) cudaFree(plan->m_corr.d);
+      plan->m_corr.d = nullptr;
+      LB_CUDA(cudaMalloc(&plan->m_corr.d, bytes));
+      plan->m_corr.bytes = bytes;
+    }
   }
   // sub-batch size: about 16 MB of fft1_float each (a sub-batch costs ~10 driver calls), whole averaging groups once the group that
   // is open on entry has been completed
@@ -616,8 +641,11 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
     const size_t in_off = (size_t)a->timf1p_ref + (size_t)done * plan->blockbytes + a->timf1.size - (done == 0 ? pre : 0);
     const size_t in_len = (size_t)n * plan->blockbytes + (done == 0 ? pre : 0);
     if ((rc = ring_copy_on(plan, plan->s_in, plan->m_timf1.d, a->timf1.base, a->timf1.size, in_off, in_len, true))) return rc;
-    if (want_sumsq && done == 0 && counter > 0)   // a row in progress: bring the host's partial sums over
+    if (want_sumsq && done == 0 && counter > 0) { // a row in progress: bring the host's partial sums over
       if ((rc = ring_copy_on(plan, plan->s_in, plan->m_sumsq.d, a->fft1_sumsq.base, a->fft1_sumsq.size * 4, (size_t)sumsq_pa * 4, (size_t)plan->N * 4, true))) return rc;
+      if (want_corrsum)
+        if ((rc = ring_copy_on(plan, plan->s_in, plan->m_corrsum.d, a->fft1_corrsum.base, a->fft1_corrsum.size * 4, (size_t)sumsq_pa * 8, (size_t)plan->N * 8, true))) return rc;
+    }
     if ((rc = ensure_pipeline(plan, (size_t)ev + 2))) return rc;
     cudaEvent_t e_in = plan->events[ev++], e_k = plan->events[ev++];
     LB_CUDA(cudaEventRecord(e_in, plan->s_in));
@@ -633,6 +661,8 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
     d.fft1_sumsq.base = want_sumsq ? plan->m_sumsq.d : nullptr;
     d.fft1_sumsq_pa = sumsq_pa;
     d.fft1_sumsq_counter = counter;
+    d.corr_rows = want_corr_rows ? (float*)plan->m_corr.d + (size_t)done * 2 * plan->N : nullptr;
+    d.fft1_corrsum.base = want_corrsum ? plan->m_corrsum.d : nullptr;
     if ((rc = lb200_fft1_dev(plan, &d))) return rc;
     LB_CUDA(cudaEventRecord(e_k, plan->stream));
     LB_CUDA(cudaStreamWaitEvent(plan->s_out, e_k, 0));
@@ -644,10 +674,17 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
       const size_t bytes = sizeof(float) * (size_t)plan->N * n;
       LB_CUDA(cudaMemcpyAsync(a->power_rows + (size_t)done * plan->N, d.power_rows, bytes, cudaMemcpyDeviceToHost, plan->s_out));
       plan->d2h += bytes;
+      if (want_corr_rows) {
+        LB_CUDA(cudaMemcpyAsync(a->corr_rows + (size_t)done * 2 * plan->N, d.corr_rows, 2 * bytes, cudaMemcpyDeviceToHost, plan->s_out));
+        plan->d2h += 2 * bytes;
+      }
     } else if (want_sumsq) {
       const size_t rows = ((size_t)counter + n + avg - 1) / avg;           // rows touched, the last may stay open
       if ((rc = ring_copy_on(plan, plan->s_out, plan->m_sumsq.d, a->fft1_sumsq.base, a->fft1_sumsq.size * 4, (size_t)sumsq_pa * 4,
                              rows * plan->N * 4, false))) return rc;
+      if (want_corrsum)
+        if ((rc = ring_copy_on(plan, plan->s_out, plan->m_corrsum.d, a->fft1_corrsum.base, a->fft1_corrsum.size * 4, (size_t)sumsq_pa * 8,
+                               rows * plan->N * 8, false))) return rc;
       const int tot = counter + n;
       sumsq_pa = (uint32_t)((sumsq_pa + (size_t)(tot / avg) * plan->N) & (a->fft1_sumsq.size - 1));
       counter = tot % avg;

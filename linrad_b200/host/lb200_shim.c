@@ -34,6 +34,7 @@
 static lb200_plan *shim_plan[LB200_SHIM_MAX_THREADS];
 static float *shim_power;          /* max_fft1n rows of fft1_size floats, indexed like fft1_float blocks */
 static float *shim_window;         /* natural-order copy of fft1_window */
+static float *shim_corr;           /* fft1_correlation_flag == 1: rows of 2*fft1_size floats, like shim_power */
 
 static void shim_fail(int code)
 {
@@ -87,6 +88,12 @@ c.pg_ch2_c1=pg_ch2_c1;
 c.pg_ch2_c2=pg_ch2_c2;
 shim_power=malloc((size_t)(fft1n_mask+1)*(size_t)fft1_size*sizeof(float));
 if(shim_power == NULL){shim_fail(LB200_ERR_BAD_CONFIG); return -1;}
+shim_corr=NULL;
+if(fft1_correlation_flag == 1)
+  {
+  shim_corr=malloc((size_t)(fft1n_mask+1)*2*(size_t)fft1_size*sizeof(float));
+  if(shim_corr == NULL){shim_fail(LB200_ERR_BAD_CONFIG); return -1;}
+  }
 for(i=0; i<no_of_threads && i<LB200_SHIM_MAX_THREADS; i++)
   {
   k=lb200_create(&c,&shim_plan[i]);
@@ -105,6 +112,7 @@ for(i=0; i<LB200_SHIM_MAX_THREADS; i++)
   }
 free(shim_power); shim_power=NULL;
 free(shim_window); shim_window=NULL;
+free(shim_corr); shim_corr=NULL;
 }
 
 /* Same signature as fft1_b (fft1def.h:363).  `tmp` is not needed.  `out` is &fft1_float[fft1_pa]. */
@@ -123,6 +131,8 @@ a.fft1_float.size=(size_t)fft1_mask+1;
 a.fft1_pa=(uint32_t)(out-fft1_float);
 a.apply_filtercorr=1;
 a.power_rows=&shim_power[(size_t)((out-fft1_float)/fft1_block)*(size_t)fft1_size];
+if(fft1_correlation_flag == 1)
+  a.corr_rows=&shim_corr[(size_t)((out-fft1_float)/fft1_block)*2*(size_t)fft1_size];
 rc=lb200_fft1(shim_plan[gpu_handle_number],&a);
 if(rc != LB200_OK)shim_fail(rc);
 }
@@ -142,6 +152,21 @@ if(fft1_sumsq_counter == 0)
 else
   {
   for(ia=fft1_first_point; ia <= fft1_last_point; ia++)sum[ia]+=pwr[ia];
+  }
+if(fft1_correlation_flag == 1)
+  {
+/* fft1.c:4146-4152 / 4189-4195 */
+  float *cor, *cs;
+  cor=&shim_corr[(size_t)fft1_nb*2*(size_t)fft1_size];
+  cs=&fft1_corrsum[2*fft1_sumsq_pa];
+  if(fft1_sumsq_counter == 0)
+    {
+    for(ia=2*fft1_first_point; ia <= 2*fft1_last_point+1; ia++)cs[ia]=cor[ia];
+    }
+  else
+    {
+    for(ia=2*fft1_first_point; ia <= 2*fft1_last_point+1; ia++)cs[ia]+=cor[ia];
+    }
   }
 fft1_sumsq_counter++;
 if(fft1_sumsq_counter >= wg.fft_avg1num)

@@ -49,6 +49,7 @@ typedef struct {
   int pixels_per_xpoint; /* wg.pixels_per_xpoint */
   int wf_lines;          /* waterfall ring lines */
   int sample_shift;      /* ui.sample_shift */
+  int correlation;       /* genparm[FFT1_CORRELATION_SPECTRUM] -> fft1_correlation_flag (two channels only, buf.c:1223-1224) */
 } ref_cfg;
 
 typedef struct {
@@ -122,6 +123,10 @@ const float *ref_filtercorr(void) { return fft1_filtercorr; }
 const float *ref_desired(void) { return fft1_desired; }
 const float *ref_sumsq(void) { return fft1_sumsq; }
 const float *ref_slowsum(void) { return fft1_slowsum; }
+const float *ref_corrsum(void) { return fft1_corrsum; }
+const float *ref_slowcorr(void) { return fft1_slowcorr; }
+const double *ref_slowcorr_tot(void) { return fft1_slowcorr_tot; }
+int ref_slowcorr_tot_avgnum(void) { return slowcorr_tot_avgnum; }
 const short *ref_waterf(void) { return wg_waterf; }
 const float *ref_waterf_yfac(void) { return wg_waterf_yfac; }
 const float *ref_waterf_sum(void) { return wg_waterf_sum; }
@@ -263,7 +268,8 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   fft1_calibrate_flag = 0;
   fft1_direction = C.direction;
   pg_ch2_c1 = 1; pg_ch2_c2 = 0;
-  fft1afc_flag = 0; fft1_correlation_flag = 0; no_of_spurs = 0;
+  fft1afc_flag = 0; no_of_spurs = 0;
+  fft1_correlation_flag = (C.correlation == 1 && ui.rx_rf_channels == 2) ? 1 : 0;   /* buf.c:1223-1224 */
 
   /* ---- rings ---- */
   timf1_bytes = timf1_bytes_req;
@@ -289,6 +295,13 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   fft1_sumsq_mask = fft1_sumsq_bufsize - 1;
   fft1_sumsq = zalloc(sizeof(float) * fft1_sumsq_bufsize);
   fft1_slowsum = zalloc(sizeof(float) * fft1_size);
+  if (fft1_correlation_flag == 1) {                       /* buf.c:1229-1232, clear_fft1_correlation fft1.c:5386 */
+    fft1_corrsum = zalloc(sizeof(float) * 2 * fft1_sumsq_bufsize);
+    fft1_slowcorr = zalloc(sizeof(double) * 2 * fft1_size);
+    fft1_slowcorr_tot = zalloc(sizeof(double) * 2 * fft1_size);
+    slowcorr_tot_avgnum = 0;
+    correlation_reset_flag = fft1corr_reset_flag;
+  }
   fft1_sumsq_pa = 0; fft1_sumsq_counter = 0; fft1_sumsq_pwg = 0;
   ag_pa = 0; ag_mask = 255;
 

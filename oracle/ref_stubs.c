@@ -61,4 +61,18 @@ void new_fft1_averages(int ptr, int ia, int ib)
       if (fft1_slowsum[bin] < FFT1_SMALL) fft1_slowsum[bin] = FFT1_SMALL;
     }
   }
+  if (fft1_correlation_flag == 1) {                       /* wide_graph.c:1031-1050 */
+    src = (ptr - (wg_fft_avg2num - 1) * fft1_size + fft1_sumsq_bufsize) & fft1_sumsq_mask;
+    for (bin = ia; bin <= ib; bin++) {
+      fft1_slowcorr[2 * bin] = fft1_corrsum[2 * (src + bin)];
+      fft1_slowcorr[2 * bin + 1] = fft1_corrsum[2 * (src + bin) + 1];
+    }
+    for (row = 1; row < wg_fft_avg2num; row++) {
+      src = (src + fft1_size) & fft1_sumsq_mask;
+      for (bin = ia; bin <= ib; bin++) {
+        fft1_slowcorr[2 * bin] += fft1_corrsum[2 * (src + bin)];
+        fft1_slowcorr[2 * bin + 1] += fft1_corrsum[2 * (src + bin) + 1];
+      }
+    }
+  }
 }

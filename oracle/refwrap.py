@@ -21,7 +21,7 @@ class RefCfg(C.Structure):
         "input_mode", "rf_channels", "ad_speed", "fft1_n", "fft1_version", "sinpow",
         "fft1_gain", "mix1_red_n", "avg1num", "avg2num", "waterfall_avgnum", "direction",
         "n_sel", "first_xpoint", "xpoints", "xpoints_per_pixel", "pixels_per_xpoint",
-        "wf_lines", "sample_shift")]
+        "wf_lines", "sample_shift", "correlation")]
 
 
 def available():
@@ -38,7 +38,8 @@ class RefOracle:
     def __init__(self, *, input_mode, rf_channels, ad_speed, fft1_n, fft1_version, sinpow=2,
                  fft1_gain=2000, mix1_red_n=4, avg1num=5, avg2num=4, waterfall_avgnum=10,
                  direction=1, n_sel=0, first_xpoint=0, xpoints=None, xpoints_per_pixel=1,
-                 pixels_per_xpoint=1, wf_lines=8, sample_shift=0, timf1_bytes=None, max_fft1n=8, through_shim=False):
+                 pixels_per_xpoint=1, wf_lines=8, sample_shift=0, timf1_bytes=None, max_fft1n=8, through_shim=False,
+                 correlation=0):
         self.lib = C.CDLL(SHIM_SO if through_shim else REF_SO)
         L = self.lib
         L.ref_init.argtypes = [C.POINTER(RefCfg), C.c_int, C.c_int]
@@ -53,7 +54,8 @@ class RefOracle:
             getattr(L, f).restype = C.c_float
         for f in ("ref_window", "ref_filtercorr", "ref_desired", "ref_sumsq", "ref_slowsum",
                   "ref_waterf", "ref_waterf_yfac", "ref_waterf_sum", "ref_mix1_fqwin",
-                  "ref_mix1_window", "ref_mix1_cos2win", "ref_mix1_sin2win"):
+                  "ref_mix1_window", "ref_mix1_cos2win", "ref_mix1_sin2win", "ref_corrsum", "ref_slowcorr",
+                  "ref_slowcorr_tot"):
             getattr(L, f).restype = C.c_void_p
         L.ref_timf3.restype = C.c_void_p
         L.ref_timf3.argtypes = [C.c_int]
@@ -63,7 +65,7 @@ class RefOracle:
         self.cfg = RefCfg(input_mode, rf_channels, ad_speed, fft1_n, fft1_version, sinpow,
                           fft1_gain, mix1_red_n, avg1num, avg2num, waterfall_avgnum, direction,
                           n_sel, first_xpoint, xpoints, xpoints_per_pixel, pixels_per_xpoint,
-                          wf_lines, sample_shift)
+                          wf_lines, sample_shift, correlation)
         frame = (4 if input_mode & IQ_DATA else 2) * rf_channels
         if input_mode & DWORD_INPUT:
             frame *= 2
@@ -156,6 +158,16 @@ class RefOracle:
 
     def sumsq_counter(self):
         return self.lib.ref_sumsq_counter()
+
+    def corrsum(self):
+        """fft1_corrsum ring (fft1_correlation_flag == 1): 2*fft1_sumsq_bufsize floats"""
+        return self._arr("ref_corrsum", 2 * self.lib.ref_sumsq_bufsize())
+
+    def slowcorr(self):
+        return self._arr("ref_slowcorr", 2 * self.lib.ref_fft1_size())
+
+    def slowcorr_tot(self):
+        return self._arr("ref_slowcorr_tot", 2 * self.lib.ref_fft1_size(), np.float64)
 
     def slowsum(self):
         return self._arr("ref_slowsum", self.fft1_size)

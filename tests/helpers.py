@@ -63,7 +63,7 @@ class CudaStream:
     fft1_mix1_fixed."""
 
     def __init__(self, setup, selbins, window=None, filtercorr=None, max_fft1n=8, sumsq_rows=16,
-                 timf3_size=None, timf1_bytes=None, foldcorr=None, sample_shift=0, pg_ch2=(1.0, 0.0)):
+                 timf3_size=None, timf1_bytes=None, foldcorr=None, sample_shift=0, pg_ch2=(1.0, 0.0), correlation=0):
         self.s = setup
         self.plan = api.Plan(setup, window=window, filtercorr=filtercorr, foldcorr=foldcorr, sample_shift=sample_shift,
                              pg_ch2=pg_ch2)
@@ -73,6 +73,7 @@ class CudaStream:
         self.timf1 = np.zeros(self.timf1_bytes, np.uint8)
         self.fft1 = np.zeros(max_fft1n * setup.fft1_block, np.float32)
         self.sumsq = np.zeros(sumsq_rows * N, np.float32)
+        self.corrsum = np.zeros(2 * sumsq_rows * N, np.float32) if correlation == 1 else None
         self.timf3_size = timf3_size or 16 * setup.mix1_size * 2 * setup.rf_channels
         self.nsel = len(selbins)
         self.timf3 = np.zeros(max(self.nsel, 1) * 2 * self.timf3_size, np.float32)
@@ -100,7 +101,8 @@ class CudaStream:
             self.pa = (self.pa + nbytes) & (self.timf1_bytes - 1)
             self.plan.fft1_host(timf1=self.timf1, ref=self.px, nblocks=nb, fft1=self.fft1, fft1_pa=self.fft1_pa,
                                 apply_fc=apply_fc, sumsq=self.sumsq if apply_fc else None,
-                                sumsq_pa=self.sumsq_pa, counter=self.sumsq_counter)
+                                sumsq_pa=self.sumsq_pa, counter=self.sumsq_counter,
+                                corrsum=self.corrsum if apply_fc else None)
             for b in range(nb):
                 at = (self.fft1_pa + b * s.fft1_block) & (self.fft1.size - 1)
                 fft1_out[done + b] = self.fft1[at: at + s.fft1_block]

@@ -94,6 +94,19 @@ def _compare(kw, nblocks, selbins, chunk, seed=1, ext=None, power_slack=1.0, **o
             b = ref["sumsq"][r * N + lo: r * N + hi + 1]
             ok, worst = power_ok(a, b, s.avg1num)
             assert worst <= power_slack, f"sumsq row {r}: worst error is {worst:.2f} x the per-bin allowance"
+        # fft1_corrsum (fft1_correlation_flag == 1): |2 z1 conj(z2)| <= the bin's summed power, so the
+        # power row's allowance bounds its error too
+        if ext.get("correlation") == 1:
+            gc = cs.corrsum.reshape(-1, 2)
+            rc = ref["ref"].corrsum().reshape(-1, 2)
+            for r in range(min(rows, 8)):
+                b = ref["sumsq"][r * N + lo: r * N + hi + 1].astype(np.float64)
+                a_rms, a_peak = np.sqrt(b.mean() / s.avg1num), np.sqrt(b.max() / s.avg1num)
+                eps = max(8 * np.sqrt(np.log2(b.size + 1)) * 2.0 ** -23 * a_rms, 4 * 2.0 ** -23 * a_peak)
+                allow = TOL_POWER * b + 2 * np.sqrt(s.avg1num * b) * eps + s.avg1num * eps ** 2
+                d = np.abs(gc[r * N + lo: r * N + hi + 1].astype(np.float64) - rc[r * N + lo: r * N + hi + 1]).max(axis=1)
+                assert (d <= 2 * power_slack * allow).all(), f"corrsum row {r}: {float((d / allow).max()):.2f} x the allowance"
+            assert np.abs(rc[: rows * N]).max() > 0
         # mix1: bin selection and phase state bit-exact, baseband within tolerance
         for ss in range(len(selbins)):
             st = ref["states"][ss]
@@ -147,6 +160,19 @@ def test_channel2_phasing(direction):
     _compare(kw, 7, [300.37], chunk=4, direction=direction, ext=dict(pg_ch2=(c1, c2)))
     _compare(kw, 7, [300.37], chunk=4, direction=direction,
              ext=dict(pg_ch2=(c1, c2), foldcorr=_foldcorr_table(11, 2, seed=9)))
+
+
+@pytest.mark.parametrize("n,mode,direction,chunk", [(11, IQ_DATA | TWO_CHANNELS, 1, 4), (10, IQ_DATA | TWO_CHANNELS | DWORD_INPUT, -1, 3),
+                                                    (14, IQ_DATA | TWO_CHANNELS, 1, 7), (15, IQ_DATA | TWO_CHANNELS, 1, 8)])
+def test_correlation_spectrum(n, mode, direction, chunk):
+    """fft1_correlation_flag == 1: fft1_corrsum next to fft1_sumsq (fft1.c:4146-4152, 4189-4195)"""
+    kw = dict(input_mode=mode, rf_channels=2, ad_speed=96000, fft1_n=n, mix1_red_n=n - 8, version=7)
+    _compare(kw, 13, [0.146 * (1 << n) + 0.37], chunk=chunk, direction=direction, ext=dict(correlation=1))
+
+
+def test_correlation_spectrum_limited_range():
+    kw = dict(input_mode=IQ_DATA | TWO_CHANNELS, rf_channels=2, ad_speed=96000, fft1_n=11, mix1_red_n=3, version=7)
+    _compare(kw, 12, [], chunk=5, first_xpoint=200, xpoints=1500, ext=dict(correlation=1, pg_ch2=(0.9, 0.3)))
 
 
 @pytest.mark.parametrize("shift", [-3, -1, 2])

@@ -45,3 +45,26 @@ def test_shim_inside_the_reference(mode, ch, ver, n, sinpow):
     assert rel_rms(got["timf3"][1:, 0], ref["timf3"][1:, 0]) <= 1e-4
     # the reference's own consumers ran on the shim's output: slowsum / waterfall stay consistent
     assert np.allclose(got["ref"].slowsum(), ref["ref"].slowsum(), rtol=2e-4, atol=1e-3 * float(np.abs(ref["ref"].slowsum()).max()))
+
+
+def test_shim_correlation_spectrum():
+    """fft1_correlation_flag == 1 inside the reference: the shim's fft1_c fills fft1_corrsum from the
+    library's per-transform cross-spectrum rows, the reference's own update_fft1_slowsum turns it
+    into fft1_slowcorr / fft1_slowcorr_tot"""
+    mode, n = IQ_DATA | TWO_CHANNELS, 10
+    kw = dict(input_mode=mode, rf_channels=2, ad_speed=96000, fft1_n=n, mix1_red_n=3, version=7)
+    N = 1 << n
+    nblocks = 27
+    P = run_reference(kw, np.zeros(16, np.int16), [], 0)["ref"].lib.ref_new_points()
+    raw = make_timf1(mode, 2, N, nblocks, P, seed=8)
+    ref = run_reference(kw, raw, [], nblocks, correlation=1)
+    got = run_reference(kw, raw, [], nblocks, through_shim=True, correlation=1)
+    rows = nblocks // 5
+    a, b = got["ref"].corrsum()[: 2 * rows * N], ref["ref"].corrsum()[: 2 * rows * N]
+    scale = float(np.abs(b).max())
+    assert scale > 0 and np.abs(a - b).max() <= 2e-5 * scale
+    sa, sb = got["ref"].slowcorr(), ref["ref"].slowcorr()
+    assert np.abs(sa - sb).max() <= 2e-5 * float(np.abs(sb).max())
+    ta, tb = got["ref"].slowcorr_tot(), ref["ref"].slowcorr_tot()
+    assert np.abs(ta - tb).max() <= 2e-5 * float(np.abs(tb).max())
+    assert got["ref"].lib.ref_slowcorr_tot_avgnum() == ref["ref"].lib.ref_slowcorr_tot_avgnum() > 0
