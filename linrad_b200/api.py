@@ -372,3 +372,21 @@ def new_states(selfreqs):
         arr[i].mix1_selfreq = f
         arr[i].mix1_point = -1
     return arr
+
+
+def advance_mix1_states(plan, states, ntransforms):
+    """Step the per-selection mixer state over `ntransforms` transforms without computing them
+    (set_mix1_phases mix1.c:781-861 + the running phase sum of do_mix1): what a rank that starts in
+    the middle of a stream does to arrive at the sequential run's state (shard.block_ranges)."""
+    s = plan.setup
+    count = s.mix1_new_points if s.mix1_interleave_points else s.mix1_size
+    for st in states:
+        if st.mix1_selfreq < 0:
+            continue
+        one = (Mix1State * 1).from_address(C.addressof(st))
+        for _ in range(ntransforms):
+            rc = plan.lib.lb200_set_mix1_phases(C.byref(plan.cfg), one, C.c_float(st.mix1_selfreq))
+            if rc:
+                raise Lb200Error(rc, "lb200_set_mix1_phases")
+            st.mix1_phase = plan.lib.lb200_phase_advance(st.mix1_phase, st.mix1_phase_rot, count)
+    return states

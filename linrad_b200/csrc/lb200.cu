@@ -601,7 +601,8 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
       plan->m_power.bytes = bytes;
     }
   } else if (want_sumsq) {
-    if (!is_pow2(a->fft1_sumsq.size)) return LB200_ERR_BAD_ARG;
+    if (!is_pow2(a->fft1_sumsq.size) || a->fft1_sumsq_pa % plan->N) return LB200_ERR_BAD_ARG;
+    if (a->fft1_sumsq_counter < 0 || a->fft1_sumsq_counter >= avg) return LB200_ERR_BAD_ARG;
     if ((rc = ensure_mirror(plan, plan->m_sumsq, a->fft1_sumsq.base, a->fft1_sumsq.size * sizeof(float)))) return rc;
     if (want_corrsum) {
       if (a->fft1_corrsum.size != 2 * a->fft1_sumsq.size) return LB200_ERR_BAD_ARG;

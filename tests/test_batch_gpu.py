@@ -146,3 +146,54 @@ def test_spectrum_stays_on_device_flag():
     assert np.allclose(p0, p1, rtol=2e-6, atol=0)
     assert np.array_equal(t0, t1)
     assert d0 - d1 == nblocks * s.fft1_block * 4                  # exactly the spectrum stayed behind
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_time_block_sharding_equals_one_pass(world):
+    """SURVEY.md 8(e), secondary partitioning: one stream cut into per-rank time-block ranges on
+    averaging-group borders (shard.block_ranges), each rank re-reading the overlap halo, stepping
+    the mixer state to its start and running one warm-up transform for the mix1 seam.  Ranks are
+    run one after the other on this GPU; together they must reproduce the one-pass result."""
+    from linrad_b200 import shard
+    kw = dict(CONFIGS["cfg1"], fft1_n=11, mix1_red_n=3)
+    s = sizing.PathSetup(**{a: b for a, b in kw.items() if a != "version"})
+    nblocks, sel = 38, [300.37, 1234.0]
+    raw = make_timf1(s.input_mode, s.rf_channels, s.fft1_size, nblocks, s.fft1_new_points, seed=5)
+    rawb = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)[: nblocks * s.timf1_blockbytes]
+    f_one, p_one, t_one = _run(s, rawb, nblocks, sel, chunk=nblocks)
+    hz = s.ad_speed / s.fft1_size
+    f_all = np.zeros_like(f_one)
+    p_all = np.zeros_like(p_one)
+    t_all = [np.zeros_like(t) for t in t_one]
+    for br in shard.block_ranges(nblocks, world, avg1num=s.avg1num):
+        if br.count == 0:
+            continue
+        timf1, fft1, sumsq, timf3, t3size = _rings(s, nblocks, len(sel))
+        timf1[: rawb.size] = rawb                       # a rank reads only [first - warmup - halo, first + count)
+        plan = api.Plan(s)
+        try:
+            states = api.new_states([b * hz for b in sel])
+            start = br.first - br.warmup
+            api.advance_mix1_states(plan, states, start)
+            if br.warmup:                               # warm-up transform: spectrum only, its power belongs to the previous rank's row
+                plan.fft1_host(timf1=timf1, ref=start * s.timf1_blockbytes, nblocks=br.warmup, fft1=fft1,
+                               fft1_pa=start * s.fft1_block, apply_fc=True, sumsq=None)
+            plan.fft1_host(timf1=timf1, ref=br.first * s.timf1_blockbytes, nblocks=br.count, fft1=fft1,
+                           fft1_pa=br.first * s.fft1_block, apply_fc=True, sumsq=sumsq,
+                           sumsq_pa=(br.first // s.avg1num) * s.fft1_size, counter=0)
+            plan.mix1_host(fft1=fft1, fft1_px=start * s.fft1_block, nblocks=br.warmup + br.count, states=states,
+                           timf3=timf3, timf3_floats=t3size, timf3_pa=start * s.timf3_block)
+            plan.synchronize()
+        finally:
+            plan.close()
+        sl = slice(br.first, br.first + br.count)
+        f_all[sl] = fft1[: nblocks * s.fft1_block].reshape(nblocks, -1)[sl]
+        r0, r1 = br.first // s.avg1num, min((br.first + br.count) // s.avg1num, p_one.shape[0])
+        p_all[r0:r1] = sumsq[: p_one.size].reshape(p_one.shape)[r0:r1]
+        for i in range(len(sel)):
+            ring = timf3[i * 2 * t3size: i * 2 * t3size + nblocks * s.timf3_block].reshape(nblocks, -1)
+            t_all[i].reshape(nblocks, -1)[sl] = ring[sl]
+    assert np.array_equal(f_all, f_one)
+    assert np.array_equal(p_all, p_one)
+    for a, b in zip(t_all, t_one):
+        assert rel_rms(a, b) <= 1e-6
