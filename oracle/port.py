@@ -100,12 +100,19 @@ def timf1_span(ring, mask_bytes, ref, setup):
     return raw.view(dt).reshape(nfr, -1).astype(np.float64)
 
 
-def fft1_b(ring, mask_bytes, ref, setup, window=None):
+def fft1_b(ring, mask_bytes, ref, setup, window=None, sample_shift=0, foldcorr=None, pg_ch2=None):
     """One call of fft1_b (fft1.c:3302): returns fft1_block floats in fft1_float layout
     (mm floats per bin: re1,im1[,re2,im2]), BEFORE fft1_c.
       complex input (versions 6/7, fft1.c:3495-3506,3788-3796; cores fft0.c:1590,161):
           out[k] = conj( sum_n w[n] x[n] exp(-2 pi i n ((k+N/2) mod N)/N) )     (probed)
-          fft1_direction<0: spectrum reversed and re/im swapped (fft1.c:3660-3680)
+          ui.sample_shift (one channel only, fft1.c:770-790): < 0 takes Q from |shift| frames
+              earlier, > 0 takes I from shift frames earlier
+          CALIQ (fft1.c:3607-3657, 3941-4026), per channel, ib = m..N/2-1, ic = N-ib,
+              m = max(1, fft1_first_sym_point): z'[ib] = z[ib] - conj(z[ic]) f[ic],
+              z'[ic] = z[ic] - conj(z[ib] f[ib])
+          fft1_direction<0 (fft1.c:3628-3680): bins ib in [m, N/2) and their mirrors are exchanged
+              with re/im swapped, bins 0 and N/2 swap re/im, bins outside [m, N-m] stay
+          channel 2 phasing (fft1.c:4064-4080): ch2 *= (c1 - i c2) on [first_sym, N - first_sym)
       real input (version 2, fft1_re.c:32-131): 2N reals, X_k = sum x[n] w[n] exp(-2 pi i n k/2N),
           out[2k]=Im X_k, out[2k+1]=Re X_k for k=1..N-1, bin 0 = (X_N, X_0) (fft1_re.c:100-114)."""
     s = setup
@@ -113,17 +120,42 @@ def fft1_b(ring, mask_bytes, ref, setup, window=None):
     x = timf1_span(ring, mask_bytes, ref, s)
     w = window if window is not None else s.window
     out = np.zeros((N, 2 * C_), np.float64)
+    first_sym = min(N - 1 - s.fft1_last_point, s.fft1_first_point)      # fft1.c:4647-4649
     if s.input_mode & 4:
+        if sample_shift and C_ == 1:
+            # gather I and Q from different frames of the ring
+            dt = np.int32 if (s.input_mode & 1) else np.int16
+            words = ring.view(dt)
+            wmask = (mask_bytes + 1) // words.itemsize - 1
+            p0 = (ref - s.fft1_interleave_points * s.frame_bytes) // words.itemsize
+            n = np.arange(N)
+            di = -sample_shift if sample_shift > 0 else 0
+            dq = sample_shift if sample_shift < 0 else 0
+            x = np.stack([words[(p0 + 2 * (n + di)) & wmask], words[((p0 + 2 * (n + dq)) & wmask) + 1]], axis=1).astype(np.float64)
         for c in range(C_):
             z = x[:, 2 * c] + 1j * x[:, 2 * c + 1]
             if w is not None:
                 z = z * w.astype(np.float64)
             X = np.fft.fft(z)
             y = np.conj(np.roll(X, -N // 2))
+            m = max(1, first_sym)
+            ib = np.arange(m, N // 2)
+            ic = N - ib
+            if foldcorr is not None:
+                f = np.asarray(foldcorr, np.float64).reshape(N, 2 * C_)
+                f = f[:, 2 * c] + 1j * f[:, 2 * c + 1]
+                yb, yc = y[ib].copy(), y[ic].copy()
+                y[ib] = yb - np.conj(yc) * f[ic]
+                y[ic] = yc - np.conj(yb * f[ib])
             if s.direction < 0:
-                # fft1.c:3660-3680 (full symmetric range): out'[b] = (im, re) of out[(N-b) mod N]
-                y = y[(-np.arange(N)) % N]
-                y = y.imag + 1j * y.real
+                yb, yc = y[ib].copy(), y[ic].copy()
+                y[ib] = yc.imag + 1j * yc.real
+                y[ic] = yb.imag + 1j * yb.real
+                for k in (0, N // 2):
+                    y[k] = y[k].imag + 1j * y[k].real
+            if pg_ch2 is not None and c == 1:
+                k = np.arange(first_sym, N - first_sym)
+                y[k] = y[k] * (pg_ch2[0] - 1j * pg_ch2[1])
             out[:, 2 * c] = y.real
             out[:, 2 * c + 1] = y.imag
     else:
@@ -152,6 +184,20 @@ def fft1_b(ring, mask_bytes, ref, setup, window=None):
 
 
 # ------------------------------------------------------------------------------------------
+def fft1_corr(block, setup):
+    """fft1_correlation_flag == 1 (fft1.c:4146-4152): 2 z1 conj(z2) of a filter-corrected
+    two-channel block on [first_point,last_point], as [N,2] floats (zero outside)."""
+    s = setup
+    N = s.fft1_size
+    z = np.asarray(block, np.float64).reshape(N, 4)
+    lo, hi = s.fft1_first_point, s.fft1_last_point
+    c = np.zeros((N, 2))
+    x = 2 * (z[lo:hi + 1, 0] + 1j * z[lo:hi + 1, 1]) * np.conj(z[lo:hi + 1, 2] + 1j * z[lo:hi + 1, 3])
+    c[lo:hi + 1, 0] = x.real
+    c[lo:hi + 1, 1] = x.imag
+    return c
+
+
 def fft1_c(block, filtercorr, setup):
     """fft1.c:4115-4200: z *= filtercorr on [first_point,last_point]; returns (block', power)
     with power[k] = sum over channels |z|^2 (zero outside the range)."""
@@ -354,7 +400,8 @@ class Mix1Port:
 
 
 # ------------------------------------------------------------------------------------------
-def run_path(setup, raw, selbins, nblocks, timf1_bytes=None, timf3_size=None, filtercorr=None, window=None):
+def run_path(setup, raw, selbins, nblocks, timf1_bytes=None, timf3_size=None, filtercorr=None, window=None,
+             sample_shift=0, foldcorr=None, pg_ch2=None, correlation=0):
     """Drive the whole path the way wideband_dsp/narrowband_dsp do (wcw.c:1036-1085,1706-1716)
     over `nblocks` blocks of raw timf1 data; mirrors oracle/refwrap.RefOracle.process."""
     s = setup
@@ -368,6 +415,7 @@ def run_path(setup, raw, selbins, nblocks, timf1_bytes=None, timf3_size=None, fi
     mixers = [Mix1Port(s, t3size) for _ in selbins]
     hz = s.ad_speed / N / (1 if s.input_mode & 4 else 2)
     sq = SumsqState(s)
+    corr_ring = np.zeros(2 * sq.ring.size)
     fft1_out = np.zeros((nblocks, s.fft1_block))
     raw_out = np.zeros((nblocks, s.fft1_block))
     t3_out = np.zeros((nblocks, max(len(selbins), 1), s.timf3_block))
@@ -375,15 +423,22 @@ def run_path(setup, raw, selbins, nblocks, timf1_bytes=None, timf3_size=None, fi
         src = rawb[b * s.timf1_blockbytes:(b + 1) * s.timf1_blockbytes]
         ring[(pa + np.arange(src.size)) & (tb - 1)] = src
         pa = (pa + src.size) & (tb - 1)
-        blk = fft1_b(ring, tb - 1, px, s, window=window)
+        blk = fft1_b(ring, tb - 1, px, s, window=window, sample_shift=sample_shift, foldcorr=foldcorr, pg_ch2=pg_ch2)
         px = (px + s.timf1_blockbytes) & (tb - 1)
         raw_out[b] = blk
         blk, pw = fft1_c(blk, fc, s)
+        if correlation == 1 and s.rf_channels == 2:
+            cr = fft1_corr(blk, s)
+            row = corr_ring[2 * sq.pa: 2 * (sq.pa + N)].reshape(N, 2)
+            if sq.counter == 0:
+                row[s.fft1_first_point:s.fft1_last_point + 1] = cr[s.fft1_first_point:s.fft1_last_point + 1]
+            else:
+                row[s.fft1_first_point:s.fft1_last_point + 1] += cr[s.fft1_first_point:s.fft1_last_point + 1]
         sq.add(pw, s.fft1_first_point, s.fft1_last_point)
         fft1_out[b] = blk
         for i, fb in enumerate(selbins):
             t3_out[b, i] = mixers[i].step(blk, fb * hz if fb >= 0 else -1.0)
-    return dict(fft1=fft1_out, raw=raw_out, timf3=t3_out, sumsq=sq.ring, sumsq_pa=sq.pa, sumsq_counter=sq.counter,
+    return dict(fft1=fft1_out, raw=raw_out, timf3=t3_out, sumsq=sq.ring, corrsum=corr_ring, sumsq_pa=sq.pa, sumsq_counter=sq.counter,
                 states=[m.st for m in mixers], timf3_ring=[m.ring for m in mixers])
 
 

@@ -268,6 +268,40 @@ def test_port_matches_compiled_reference_other_windows():
         assert got["states"][0]["point"] == ref["states"][0]["point"]
 
 
+@pytest.mark.skipif(not refwrap.available(), reason="oracle/_ref not built")
+def test_port_fft1_b_options_match_compiled_reference():
+    """the rarely used fft1_b / fft1_c options in the restatement: ui.sample_shift, CALIQ foldcorr
+    with both directions and a display range that leaves fft1_first_sym_point > 1, channel-2
+    phasing, the cross spectrum of fft1_correlation_flag == 1"""
+    from linrad_b200.synth import make_timf1
+    from tests.helpers import run_reference
+    rng = np.random.default_rng(12)
+    cases = [
+        (dict(input_mode=sizing.IQ_DATA, rf_channels=1, fft1_n=8, version=6), dict(sample_shift=-3), {}),
+        (dict(input_mode=sizing.IQ_DATA | sizing.DWORD_INPUT, rf_channels=1, fft1_n=8, version=7), dict(sample_shift=2), dict(direction=-1)),
+        (dict(input_mode=sizing.IQ_DATA, rf_channels=1, fft1_n=9, version=6), dict(foldcorr=True), dict(direction=-1, first_xpoint=60, xpoints=300)),
+        (dict(input_mode=sizing.IQ_DATA, rf_channels=1, fft1_n=8, version=7), {}, dict(direction=-1, first_xpoint=90, xpoints=120)),
+        (dict(input_mode=sizing.IQ_DATA | sizing.TWO_CHANNELS, rf_channels=2, fft1_n=8, version=7), dict(foldcorr=True, pg_ch2=(0.8, -0.5), correlation=1), {}),
+        (dict(input_mode=sizing.IQ_DATA | sizing.TWO_CHANNELS, rf_channels=2, fft1_n=8, version=7), dict(pg_ch2=(1.02, 0.2), correlation=1), dict(direction=-1, first_xpoint=20, xpoints=200)),
+    ]
+    for kw, ext, over in cases:
+        kw = dict(kw, ad_speed=96000, mix1_red_n=2)
+        N, ch = 1 << kw["fft1_n"], kw["rf_channels"]
+        ext = dict(ext)
+        if ext.get("foldcorr"):
+            ext["foldcorr"] = (0.03 * rng.standard_normal(2 * ch * N)).astype(np.float32)
+        s = sizing.PathSetup(**{k: v for k, v in kw.items() if k != "version"}, **over)
+        raw = make_timf1(s.input_mode, ch, N, 7, s.fft1_new_points, seed=3)
+        ref = run_reference(dict(kw, **over), raw, [], 7, want_raw=True, **ext)
+        got = port.run_path(s, raw, [], 7, **ext)
+        scale = float(np.sqrt((ref["raw"].astype(np.float64) ** 2).mean()))
+        assert np.abs(got["raw"] - ref["raw"]).max() <= 2e-5 * scale * np.sqrt(N), (kw, ext.keys(), over)
+        rows = 7 // s.avg1num
+        assert rel_rms(got["sumsq"][: rows * N], ref["sumsq"][: rows * N]) <= 1e-5
+        if ext.get("correlation") == 1:
+            assert rel_rms(got["corrsum"][: 2 * rows * N], ref["ref"].corrsum()[: 2 * rows * N]) <= 1e-5
+
+
 # ------------------------------------------------------------------------------------------
 def test_stream_and_block_sharding():
     a = shard.stream_assignment(64, 8)
