@@ -123,6 +123,11 @@ typedef struct lb200_fft1_args {
                                    index)); needs fft1_sumsq; base==NULL to skip */
   float *corr_rows;             /* with power_rows: nblocks rows of 2*fft1_size floats = per-transform
                                    cross spectrum; NULL to skip */
+  float *xypower_rows;          /* with power_rows, two RF channels: nblocks rows of fft1_size
+                                   TWOCHAN_POWER {x2, y2, im_xy, re_xy} (globdef.h:1371-1376) = what
+                                   fft1_c stores in fft1_xypower when fft1afc_flag > 0
+                                   (fft1.c:4349-4368); NULL to skip.  One channel: fft1_power is
+                                   power_rows itself. */
 } lb200_fft1_args;
 /* lb200_fft1 (host rings) only: leave fft1_float in the plan's device mirror of the ring and do
  * not write the host ring.  For set-ups where nothing on the host reads the spectrum (second FFT

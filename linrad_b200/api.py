@@ -67,7 +67,7 @@ class Fft1Args(C.Structure):
         ("fft1_float", Ring), ("fft1_pa", C.c_uint32), ("apply_filtercorr", C.c_int),
         ("fft1_sumsq", Ring), ("fft1_sumsq_pa", C.c_uint32), ("fft1_sumsq_counter", C.c_int),
         ("power_rows", C.c_void_p), ("flags", C.c_int),
-        ("fft1_corrsum", Ring), ("corr_rows", C.c_void_p),
+        ("fft1_corrsum", Ring), ("corr_rows", C.c_void_p), ("xypower_rows", C.c_void_p),
     ]
 
 
@@ -271,7 +271,7 @@ class Plan:
             raise Lb200Error(rc, "lb200_fft1_dev")
 
     def fft1_host(self, *, timf1, ref, nblocks, fft1, fft1_pa=0, apply_fc=True, sumsq=None, sumsq_pa=0,
-                  counter=0, power=None, keep_on_device=False, corrsum=None, corr_rows=None):
+                  counter=0, power=None, keep_on_device=False, corrsum=None, corr_rows=None, xypower_rows=None):
         """numpy arrays standing in for Linrad's host rings (sizes must be powers of two)."""
         a = self._fft1_args(timf1.ctypes.data, timf1.nbytes, ref, nblocks, fft1.ctypes.data, fft1.size, fft1_pa,
                             apply_fc, _ptr(sumsq), 0 if sumsq is None else sumsq.size, sumsq_pa, counter,
@@ -280,6 +280,7 @@ class Plan:
         if corrsum is not None:
             a.fft1_corrsum = Ring(corrsum.ctypes.data, corrsum.size)
         a.corr_rows = _ptr(corr_rows)
+        a.xypower_rows = _ptr(xypower_rows)
         rc = self.lib.lb200_fft1(self.h, C.byref(a))
         if rc:
             raise Lb200Error(rc, "lb200_fft1")

@@ -30,6 +30,7 @@ struct Fft1PostK {
   // fft1_correlation_flag == 1: cross spectrum 2*z1*conj(z2) (fft1.c:4146-4152)
   float* corrsum;           // ring indexed like fft1_sumsq, two floats per bin; or nullptr
   float* corr_rows;         // per-transform rows of 2N floats (with power_rows); or nullptr
+  float* xypower_rows;      // per-transform rows of N TWOCHAN_POWER {x2, y2, im_xy, re_xy} (fft1.c:4361-4364); or nullptr
 };
 
 template <int NCH>
@@ -138,6 +139,18 @@ __global__ void __launch_bounds__(256) fft1_iqpost_kernel(const Fft1PostK q)
       if (p.power_rows && p.fc_mode != 0) {
         p.power_rows[(size_t)b * N + ib] = pwb;
         if (pair) p.power_rows[(size_t)b * N + ic] = pwc;
+      }
+      if (NCH == 2 && q.xypower_rows && p.fc_mode != 0) {
+        // xb = 2 (re_xy, im_xy); bins outside [first_point, last_point] give zeros
+        const bool inb = ib >= p.first_point && ib <= p.last_point, inc = ic >= p.first_point && ic <= p.last_point;
+        const float4 vb = inb ? make_float4(zb[0].x * zb[0].x + zb[0].y * zb[0].y, zb[1].x * zb[1].x + zb[1].y * zb[1].y, 0.5f * xb.y, 0.5f * xb.x)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(q.xypower_rows + ((size_t)b * N + ib) * 4) = vb;
+        if (pair) {
+          const float4 vc = inc ? make_float4(zc[0].x * zc[0].x + zc[0].y * zc[0].y, zc[1].x * zc[1].x + zc[1].y * zc[1].y, 0.5f * xc.y, 0.5f * xc.x)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(q.xypower_rows + ((size_t)b * N + ic) * 4) = vc;
+        }
       }
       if (NCH == 2 && q.corr_rows && p.fc_mode != 0) {
         *reinterpret_cast<float2*>(q.corr_rows + ((size_t)b * N + ib) * 2) = xb;

@@ -262,7 +262,7 @@ extern "C" void lb200_destroy(lb200_plan* plan)
     if (plan->mixjobs_done[i]) cudaEventDestroy(plan->mixjobs_done[i]);
   }
   free_mirror(plan->m_timf1); free_mirror(plan->m_fft1); free_mirror(plan->m_sumsq);
-  free_mirror(plan->m_timf3); free_mirror(plan->m_power); free_mirror(plan->m_corrsum); free_mirror(plan->m_corr);
+  free_mirror(plan->m_timf3); free_mirror(plan->m_power); free_mirror(plan->m_corrsum); free_mirror(plan->m_corr); free_mirror(plan->m_xy);
   free_mirror(plan->m_wg_sumsq); free_mirror(plan->m_wg_slowsum); free_mirror(plan->m_wg_wsum); free_mirror(plan->m_wg_yfac);
   free_mirror(plan->m_wg_waterf); free_mirror(plan->m_codec_in); free_mirror(plan->m_codec_out);
   for (cudaEvent_t e : plan->events) cudaEventDestroy(e);
@@ -342,7 +342,7 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   k.skew_q = plan->shift_q * plan->frame;
 
   if (!plan->iq) {
-    if (a->apply_filtercorr && (a->fft1_corrsum.base || a->corr_rows)) return LB200_ERR_UNSUPPORTED;
+    if (a->apply_filtercorr && (a->fft1_corrsum.base || a->corr_rows || a->xypower_rows)) return LB200_ERR_UNSUPPORTED;
     k.Wre = plan->d_Wre;
     LB_CUDA(lb_launch_fft1_real(plan, k));    // counts its own launches
     return LB200_OK;
@@ -354,11 +354,11 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   // leaves m > 1 the bins outside it are put back by the post kernel
   const bool partial_flip = k.direction < 0 && plan->first_sym > 1;
   // fft1_correlation_flag == 1 (two RF channels): cross spectrum rows next to the power rows
-  const bool want_corr = a->apply_filtercorr && (a->fft1_corrsum.base || a->corr_rows);
+  const bool want_corr = a->apply_filtercorr && (a->fft1_corrsum.base || a->corr_rows || a->xypower_rows);
   if (want_corr) {
     if (plan->nch != 2) return LB200_ERR_UNSUPPORTED;
-    if (a->corr_rows && !k.power_rows) return LB200_ERR_BAD_ARG;
-    if (a->fft1_corrsum.base && !a->corr_rows && (!k.sumsq || a->fft1_corrsum.size != 2 * a->fft1_sumsq.size)) return LB200_ERR_BAD_ARG;
+    if ((a->corr_rows || a->xypower_rows) && !k.power_rows) return LB200_ERR_BAD_ARG;
+    if (a->fft1_corrsum.base && !k.power_rows && (!k.sumsq || a->fft1_corrsum.size != 2 * a->fft1_sumsq.size)) return LB200_ERR_BAD_ARG;
   }
   const bool need_post = plan->d_foldcorr != nullptr || plan->phasing || partial_flip || want_corr;
   Fft1PostK pk;
@@ -373,7 +373,8 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
     pk.phasing = plan->phasing ? 1 : 0;
     pk.N = plan->N;
     pk.corr_rows = want_corr ? a->corr_rows : nullptr;
-    pk.corrsum = (want_corr && !a->corr_rows) ? (float*)a->fft1_corrsum.base : nullptr;
+    pk.corrsum = (want_corr && !k.power_rows) ? (float*)a->fft1_corrsum.base : nullptr;
+    pk.xypower_rows = want_corr ? a->xypower_rows : nullptr;
     k.fc_mode = 0;
     k.sumsq = nullptr;
     k.power_rows = nullptr;
@@ -590,6 +591,7 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
   const bool want_power = a->apply_filtercorr && a->power_rows;
   const bool want_sumsq = a->apply_filtercorr && !a->power_rows && a->fft1_sumsq.base;
   const bool want_corr_rows = want_power && a->corr_rows;
+  const bool want_xy_rows = want_power && a->xypower_rows;
   const bool want_corrsum = want_sumsq && a->fft1_corrsum.base;
   const int avg = plan->cfg.fft_avg1num;
   if (want_power) {
@@ -616,6 +618,15 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
       plan->m_corr.d = nullptr;
       LB_CUDA(cudaMalloc(&plan->m_corr.d, bytes));
       plan->m_corr.bytes = bytes;
+    }
+  }
+  if (want_xy_rows) {
+    const size_t bytes = sizeof(float) * 4 * (size_t)plan->N * a->nblocks;
+    if (!plan->m_xy.d || plan->m_xy.bytes < bytes) {
+      if (plan->m_xy.d) cudaFree(plan->m_xy.d);
+      plan->m_xy.d = nullptr;
+      LB_CUDA(cudaMalloc(&plan->m_xy.d, bytes));
+      plan->m_xy.bytes = bytes;
     }
   }
   // sub-batch size: about 16 MB of fft1_float each (a sub-batch costs ~10 driver calls), whole averaging groups once the group that
@@ -664,6 +675,7 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
     d.fft1_sumsq_counter = counter;
     d.corr_rows = want_corr_rows ? (float*)plan->m_corr.d + (size_t)done * 2 * plan->N : nullptr;
     d.fft1_corrsum.base = want_corrsum ? plan->m_corrsum.d : nullptr;
+    d.xypower_rows = want_xy_rows ? (float*)plan->m_xy.d + (size_t)done * 4 * plan->N : nullptr;
     if ((rc = lb200_fft1_dev(plan, &d))) return rc;
     LB_CUDA(cudaEventRecord(e_k, plan->stream));
     LB_CUDA(cudaStreamWaitEvent(plan->s_out, e_k, 0));
@@ -678,6 +690,10 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
       if (want_corr_rows) {
         LB_CUDA(cudaMemcpyAsync(a->corr_rows + (size_t)done * 2 * plan->N, d.corr_rows, 2 * bytes, cudaMemcpyDeviceToHost, plan->s_out));
         plan->d2h += 2 * bytes;
+      }
+      if (want_xy_rows) {
+        LB_CUDA(cudaMemcpyAsync(a->xypower_rows + (size_t)done * 4 * plan->N, d.xypower_rows, 4 * bytes, cudaMemcpyDeviceToHost, plan->s_out));
+        plan->d2h += 4 * bytes;
       }
     } else if (want_sumsq) {
       const size_t rows = ((size_t)counter + n + avg - 1) / avg;           // rows touched, the last may stay open

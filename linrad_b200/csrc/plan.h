@@ -73,7 +73,7 @@ struct lb200_plan {
   cudaEvent_t mixjobs_done[kJobSlots] = {nullptr, nullptr, nullptr, nullptr};
   int mixjobs_next = 0;
   // host-pointer API mirrors
-  HostMirror m_timf1, m_fft1, m_sumsq, m_timf3, m_power, m_corrsum, m_corr;
+  HostMirror m_timf1, m_fft1, m_sumsq, m_timf3, m_power, m_corrsum, m_corr, m_xy;
   HostMirror m_wg_sumsq, m_wg_slowsum, m_wg_wsum, m_wg_yfac, m_wg_waterf, m_codec_in, m_codec_out;
   std::map<const void*, size_t> registered;
   // pipelined host path: copy streams, event pool, validity of the fft1_float mirror per block

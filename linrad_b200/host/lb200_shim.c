@@ -35,6 +35,7 @@ static lb200_plan *shim_plan[LB200_SHIM_MAX_THREADS];
 static float *shim_power;          /* max_fft1n rows of fft1_size floats, indexed like fft1_float blocks */
 static float *shim_window;         /* natural-order copy of fft1_window */
 static float *shim_corr;           /* fft1_correlation_flag == 1: rows of 2*fft1_size floats, like shim_power */
+static float *shim_xy;             /* fft1afc_flag > 0, two channels: rows of fft1_size TWOCHAN_POWER */
 
 static void shim_fail(int code)
 {
@@ -88,6 +89,12 @@ c.pg_ch2_c1=pg_ch2_c1;
 c.pg_ch2_c2=pg_ch2_c2;
 shim_power=malloc((size_t)(fft1n_mask+1)*(size_t)fft1_size*sizeof(float));
 if(shim_power == NULL){shim_fail(LB200_ERR_BAD_CONFIG); return -1;}
+shim_xy=NULL;
+if(fft1afc_flag > 0 && ui.rx_rf_channels == 2)
+  {
+  shim_xy=malloc((size_t)(fft1n_mask+1)*4*(size_t)fft1_size*sizeof(float));
+  if(shim_xy == NULL){shim_fail(LB200_ERR_BAD_CONFIG); return -1;}
+  }
 shim_corr=NULL;
 if(fft1_correlation_flag == 1)
   {
@@ -113,6 +120,7 @@ for(i=0; i<LB200_SHIM_MAX_THREADS; i++)
 free(shim_power); shim_power=NULL;
 free(shim_window); shim_window=NULL;
 free(shim_corr); shim_corr=NULL;
+free(shim_xy); shim_xy=NULL;
 }
 
 /* Same signature as fft1_b (fft1def.h:363).  `tmp` is not needed.  `out` is &fft1_float[fft1_pa]. */
@@ -133,6 +141,8 @@ a.apply_filtercorr=1;
 a.power_rows=&shim_power[(size_t)((out-fft1_float)/fft1_block)*(size_t)fft1_size];
 if(fft1_correlation_flag == 1)
   a.corr_rows=&shim_corr[(size_t)((out-fft1_float)/fft1_block)*2*(size_t)fft1_size];
+if(shim_xy != NULL)
+  a.xypower_rows=&shim_xy[(size_t)((out-fft1_float)/fft1_block)*4*(size_t)fft1_size];
 rc=lb200_fft1(shim_plan[gpu_handle_number],&a);
 if(rc != LB200_OK)shim_fail(rc);
 }
@@ -145,6 +155,32 @@ int ia;
 float *sum, *pwr;
 sum=&fft1_sumsq[fft1_sumsq_pa];
 pwr=&shim_power[(size_t)fft1_nb*(size_t)fft1_size];
+if(fft1afc_flag > 0)
+  {
+/* fft1.c:4203-4426: AFC runs from fft1, so fft1_c also leaves the per-transform powers behind */
+/* (fft1_power, or fft1_xypower for two channels).  Spur elimination works on fft1_float on */
+/* the host between the filter and the power step and is not part of the library. */
+  if(no_of_spurs > 0){shim_fail(LB200_ERR_UNSUPPORTED); return;}
+  ffts_na=fft1_nb;
+  ffts_nm=fft1_nm;
+  if(ui.rx_rf_channels == 1)
+    {
+    float *fp;
+    fp=&fft1_power[(size_t)fft1_nb*(size_t)fft1_size];
+    for(ia=fft1_first_point; ia <= fft1_last_point; ia++)fp[ia]=pwr[ia];
+    }
+  else
+    {
+    TWOCHAN_POWER *pxy, *src;
+    pxy=&fft1_xypower[(size_t)fft1_nb*(size_t)fft1_size];
+    src=(TWOCHAN_POWER*)&shim_xy[(size_t)fft1_nb*4*(size_t)fft1_size];
+    for(ia=fft1_first_point; ia <= fft1_last_point; ia++)
+      {
+      pxy[ia]=src[ia];
+      pwr[ia]=pxy[ia].x2+pxy[ia].y2;         /* fft1.c:4365 */
+      }
+    }
+  }
 if(fft1_sumsq_counter == 0)
   {
   for(ia=fft1_first_point; ia <= fft1_last_point; ia++)sum[ia]=pwr[ia];

@@ -50,6 +50,7 @@ typedef struct {
   int wf_lines;          /* waterfall ring lines */
   int sample_shift;      /* ui.sample_shift */
   int correlation;       /* genparm[FFT1_CORRELATION_SPECTRUM] -> fft1_correlation_flag (two channels only, buf.c:1223-1224) */
+  int afc;               /* fft1afc_flag: AFC from fft1 (second FFT off), fft1_c keeps fft1_power / fft1_xypower */
 } ref_cfg;
 
 typedef struct {
@@ -124,6 +125,9 @@ const float *ref_desired(void) { return fft1_desired; }
 const float *ref_sumsq(void) { return fft1_sumsq; }
 const float *ref_slowsum(void) { return fft1_slowsum; }
 const float *ref_corrsum(void) { return fft1_corrsum; }
+const float *ref_fft1_power(void) { return fft1_power; }
+const float *ref_fft1_xypower(void) { return (const float *)fft1_xypower; }
+int ref_max_fft1n(void) { return max_fft1n; }
 const float *ref_slowcorr(void) { return fft1_slowcorr; }
 const double *ref_slowcorr_tot(void) { return fft1_slowcorr_tot; }
 int ref_slowcorr_tot_avgnum(void) { return slowcorr_tot_avgnum; }
@@ -268,7 +272,7 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   fft1_calibrate_flag = 0;
   fft1_direction = C.direction;
   pg_ch2_c1 = 1; pg_ch2_c2 = 0;
-  fft1afc_flag = 0; no_of_spurs = 0;
+  fft1afc_flag = C.afc ? 1 : 0; no_of_spurs = 0;
   fft1_correlation_flag = (C.correlation == 1 && ui.rx_rf_channels == 2) ? 1 : 0;   /* buf.c:1223-1224 */
 
   /* ---- rings ---- */
@@ -295,6 +299,10 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   fft1_sumsq_mask = fft1_sumsq_bufsize - 1;
   fft1_sumsq = zalloc(sizeof(float) * fft1_sumsq_bufsize);
   fft1_slowsum = zalloc(sizeof(float) * fft1_size);
+  if (fft1afc_flag > 0) {                                 /* buf.c:935-940 */
+    fft1_power = zalloc(sizeof(float) * fft1_size * max_fft1n);
+    fft1_xypower = zalloc(sizeof(TWOCHAN_POWER) * fft1_size * max_fft1n);
+  }
   if (fft1_correlation_flag == 1) {                       /* buf.c:1229-1232, clear_fft1_correlation fft1.c:5386 */
     fft1_corrsum = zalloc(sizeof(float) * 2 * fft1_sumsq_bufsize);
     fft1_slowcorr = zalloc(sizeof(double) * 2 * fft1_size);

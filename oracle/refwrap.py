@@ -21,7 +21,7 @@ class RefCfg(C.Structure):
         "input_mode", "rf_channels", "ad_speed", "fft1_n", "fft1_version", "sinpow",
         "fft1_gain", "mix1_red_n", "avg1num", "avg2num", "waterfall_avgnum", "direction",
         "n_sel", "first_xpoint", "xpoints", "xpoints_per_pixel", "pixels_per_xpoint",
-        "wf_lines", "sample_shift", "correlation")]
+        "wf_lines", "sample_shift", "correlation", "afc")]
 
 
 def available():
@@ -39,7 +39,7 @@ class RefOracle:
                  fft1_gain=2000, mix1_red_n=4, avg1num=5, avg2num=4, waterfall_avgnum=10,
                  direction=1, n_sel=0, first_xpoint=0, xpoints=None, xpoints_per_pixel=1,
                  pixels_per_xpoint=1, wf_lines=8, sample_shift=0, timf1_bytes=None, max_fft1n=8, through_shim=False,
-                 correlation=0):
+                 correlation=0, afc=0):
         self.lib = C.CDLL(SHIM_SO if through_shim else REF_SO)
         L = self.lib
         L.ref_init.argtypes = [C.POINTER(RefCfg), C.c_int, C.c_int]
@@ -55,7 +55,7 @@ class RefOracle:
         for f in ("ref_window", "ref_filtercorr", "ref_desired", "ref_sumsq", "ref_slowsum",
                   "ref_waterf", "ref_waterf_yfac", "ref_waterf_sum", "ref_mix1_fqwin",
                   "ref_mix1_window", "ref_mix1_cos2win", "ref_mix1_sin2win", "ref_corrsum", "ref_slowcorr",
-                  "ref_slowcorr_tot"):
+                  "ref_slowcorr_tot", "ref_fft1_power", "ref_fft1_xypower"):
             getattr(L, f).restype = C.c_void_p
         L.ref_timf3.restype = C.c_void_p
         L.ref_timf3.argtypes = [C.c_int]
@@ -65,7 +65,7 @@ class RefOracle:
         self.cfg = RefCfg(input_mode, rf_channels, ad_speed, fft1_n, fft1_version, sinpow,
                           fft1_gain, mix1_red_n, avg1num, avg2num, waterfall_avgnum, direction,
                           n_sel, first_xpoint, xpoints, xpoints_per_pixel, pixels_per_xpoint,
-                          wf_lines, sample_shift, correlation)
+                          wf_lines, sample_shift, correlation, afc)
         frame = (4 if input_mode & IQ_DATA else 2) * rf_channels
         if input_mode & DWORD_INPUT:
             frame *= 2
@@ -158,6 +158,14 @@ class RefOracle:
 
     def sumsq_counter(self):
         return self.lib.ref_sumsq_counter()
+
+    def fft1_power(self):
+        """fft1_power (fft1afc_flag > 0, one channel): max_fft1n rows of fft1_size floats"""
+        return self._arr("ref_fft1_power", self.lib.ref_max_fft1n() * self.lib.ref_fft1_size())
+
+    def fft1_xypower(self):
+        """fft1_xypower (two channels): max_fft1n rows of fft1_size TWOCHAN_POWER {x2, y2, im_xy, re_xy}"""
+        return self._arr("ref_fft1_xypower", 4 * self.lib.ref_max_fft1n() * self.lib.ref_fft1_size())
 
     def corrsum(self):
         """fft1_corrsum ring (fft1_correlation_flag == 1): 2*fft1_sumsq_bufsize floats"""

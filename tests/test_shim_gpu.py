@@ -68,3 +68,32 @@ def test_shim_correlation_spectrum():
     ta, tb = got["ref"].slowcorr_tot(), ref["ref"].slowcorr_tot()
     assert np.abs(ta - tb).max() <= 2e-5 * float(np.abs(tb).max())
     assert got["ref"].lib.ref_slowcorr_tot_avgnum() == ref["ref"].lib.ref_slowcorr_tot_avgnum() > 0
+
+
+@pytest.mark.parametrize("mode,ch,ver", [(IQ_DATA, 1, 6), (IQ_DATA | TWO_CHANNELS, 2, 7)])
+def test_shim_afc_mode_fft1_c(mode, ch, ver):
+    """fft1afc_flag > 0 (AFC run from fft1, no spur elimination): fft1_c also keeps the per-transform
+    powers -- fft1_power for one channel, fft1_xypower {x2, y2, im_xy, re_xy} for two
+    (fft1.c:4203-4426).  The shim fills them from the library's power / xypower rows."""
+    n = 10
+    kw = dict(input_mode=mode, rf_channels=ch, ad_speed=96000, fft1_n=n, mix1_red_n=3, version=ver)
+    N = 1 << n
+    nblocks = 11
+    P = run_reference(kw, np.zeros(16, np.int16), [], 0)["ref"].lib.ref_new_points()
+    raw = make_timf1(mode, ch, N, nblocks, P, seed=9)
+    ext = dict(afc=1, correlation=1 if ch == 2 else 0)
+    ref = run_reference(kw, raw, [], nblocks, **ext)
+    got = run_reference(kw, raw, [], nblocks, through_shim=True, **ext)
+    assert rel_rms(got["fft1"], ref["fft1"]) <= 1e-5
+    rows = nblocks // 5
+    a, b = got["sumsq"][: rows * N].astype(np.float64), ref["sumsq"][: rows * N].astype(np.float64)
+    strong = b > 1e-4 * b.max()
+    assert (np.abs(a - b)[strong] <= 1e-4 * b[strong]).all()
+    if ch == 1:
+        pa, pb = got["ref"].fft1_power(), ref["ref"].fft1_power()
+    else:
+        pa, pb = got["ref"].fft1_xypower(), ref["ref"].fft1_xypower()
+        ca, cb = got["ref"].corrsum()[: 2 * rows * N], ref["ref"].corrsum()[: 2 * rows * N]
+        assert np.abs(ca - cb).max() <= 2e-5 * float(np.abs(cb).max())
+    assert float(np.abs(pb).max()) > 0
+    assert np.abs(pa - pb).max() <= 2e-5 * float(np.abs(pb).max())
