@@ -8,11 +8,13 @@ using namespace lb;
 #define LB_MIX1_LE_MID 3
 #endif
 
-// transforms side by side in one CTA: fill about 512 threads, at most 8
+// transforms side by side in one CTA, at most 8: about 512 threads for small mix1.size, 256 from
+// 1024 points up (measured: two half-size CTAs per SM overlap each other's barrier phases better
+// than one -- cfg4 mix1 75 -> 60 us, cfg2 84 -> 76 us -- while mix1.size 512 loses with 256)
 template <int LOG2M, int LOG2E, int NCH>
 struct Mix1Par {
   static constexpr int LANE = NCH << (LOG2M - LOG2E);
-  static constexpr int RAW = 512 / LANE;
+  static constexpr int RAW = (LOG2M >= 10 ? 256 : 512) / LANE;
   static constexpr int value = RAW < 1 ? 1 : (RAW > 8 ? 8 : RAW);
 };
 
