@@ -27,6 +27,13 @@ namespace lb {
 #ifndef LB_LARGE_LT
 #define LB_LARGE_LT 3
 #endif
+// separate widths for the two steps (default: both LB_LARGE_LT)
+#ifndef LB_LARGE_LTA
+#define LB_LARGE_LTA LB_LARGE_LT
+#endif
+#ifndef LB_LARGE_LTB
+#define LB_LARGE_LTB LB_LARGE_LT
+#endif
 // points per thread (log2) of the column / row transforms
 #ifndef LB_LARGE_LE
 #define LB_LARGE_LE 4

@@ -125,7 +125,7 @@ cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k)
   q.Wn2 = plan->d_Wn2;
   q.Wbig = plan->d_Wn;
   large_fn_t fn = large_fn(plan->fmt);
-  const int tilesA = (1 << ln2) >> LB_LARGE_LT, tilesB = (1 << ln1) >> LB_LARGE_LT;
+  const int tilesA = (1 << ln2) >> LB_LARGE_LTA, tilesB = (1 << ln1) >> LB_LARGE_LTB;
   if (k.sumsq && !k.power_rows && k.fc_mode != 0) {
     cudaError_t e = lb_zero_sumsq_rows(plan, k, ngroups);    // step B adds |z|^2 into the rows
     if (e != cudaSuccess) return e;
@@ -237,7 +237,7 @@ cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k)
       q.b_count = b_count;
       q.g_first = b_first;          // groups of one transform (avg1num = 1, counter0 = 0)
       q.g_count = b_count;
-      const int tilesA = (1 << ln2) >> LB_LARGE_LT, tilesB = (1 << ln1) >> LB_LARGE_LT;
+      const int tilesA = (1 << ln2) >> LB_LARGE_LTA, tilesB = (1 << ln1) >> LB_LARGE_LTB;
       int gridA = b_count * nch * tilesA, gridB = b_count * tilesB;
       const int cap = plan->sm_count * 8;
       if (gridA > cap) gridA = cap;
