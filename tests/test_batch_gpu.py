@@ -197,3 +197,49 @@ def test_time_block_sharding_equals_one_pass(world):
     assert np.array_equal(p_all, p_one)
     for a, b in zip(t_all, t_one):
         assert rel_rms(a, b) <= 1e-6
+
+
+def test_concurrent_fft1b_workers():
+    """Linrad farms fft1_b out to up to six worker threads, each with its own handle, on distinct
+    time blocks of the SAME timf1 / fft1_float rings (wcw.c:476-513, 974-1033): the entry point must
+    be re-entrant across plans.  Three threads, one plan each, one transform per call, against one
+    plan doing the same blocks in order."""
+    import threading
+    kw = dict(CONFIGS["cfg1"], fft1_n=12, mix1_red_n=4)
+    s = sizing.PathSetup(**{a: b for a, b in kw.items() if a != "version"})
+    nblocks, workers = 30, 3
+    raw = make_timf1(s.input_mode, s.rf_channels, s.fft1_size, nblocks, s.fft1_new_points, seed=6)
+    rawb = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)[: nblocks * s.timf1_blockbytes]
+
+    def run(nthreads):
+        timf1, fft1, _, _, _ = _rings(s, nblocks, 0)
+        timf1[: rawb.size] = rawb
+        power = np.zeros((nblocks, s.fft1_size), np.float32)
+        plans = [api.Plan(s) for _ in range(nthreads)]
+        errors = []
+
+        def work(k):
+            try:
+                for b in range(k, nblocks, nthreads):
+                    plans[k].fft1_host(timf1=timf1, ref=b * s.timf1_blockbytes, nblocks=1, fft1=fft1,
+                                       fft1_pa=b * s.fft1_block, apply_fc=True, power=power[b])
+            except Exception as e:              # surfaced below: a worker must not die silently
+                errors.append(e)
+        try:
+            th = [threading.Thread(target=work, args=(k,)) for k in range(nthreads)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            for p in plans:
+                p.synchronize()
+        finally:
+            for p in plans:
+                p.close()
+        assert not errors, errors
+        return fft1[: nblocks * s.fft1_block].copy(), power
+
+    f1, p1 = run(1)
+    f3, p3 = run(workers)
+    assert np.array_equal(f1, f3) and np.array_equal(p1, p3)
+    assert np.abs(f1).max() > 0 and p1.min() >= 0
