@@ -259,3 +259,57 @@ timf3_pa=(timf3_pa+timf3_block)&timf3_mask;         /* mix1.c:1038-1040 */
 fft1_nx=(fft1_nx+1)&fft1n_mask;
 fft1_px=(fft1_px+fft1_block)&fft1_mask;
 }
+
+/* fft1_mix1_afc (mix1.c:1044-1096): the mixer frequency of every transform comes from the AFC
+ * track mix1_fq_mid[] instead of mix1_selfreq[]; the arithmetic is fft1_mix1_fixed's.  What
+ * do_mix1_afc (mix1.c:648-768) does besides calling do_mix1 -- stepping mix1_fq_slope / _curv /
+ * _start and bending future mix1_fq_mid entries -- is host logic on Linrad's AFC tables.  It must
+ * be reachable without the CPU mixer: split do_mix1_afc in mix1.c at its last line into
+ *     void mix1_afc_tables(int ss)   (everything up to, not including, do_mix1(ss,t2-t1))
+ * and point lb200_shim_afc_tables at it. */
+void (*lb200_shim_afc_tables)(int ss);
+
+void lb200_shim_mix1_afc(void)
+{
+lb200_mix1_args a;
+lb200_mix1_state st[MAX_MIX1];
+int ss, rc, k;
+if(lb200_shim_afc_tables == NULL){shim_fail(LB200_ERR_UNSUPPORTED); return;}
+k=genparm[MIX1_NO_OF_CHANNELS];
+for(ss=0; ss<k; ss++)
+  {
+  st[ss].mix1_selfreq=-1;
+  if(mix1_selfreq[ss] >= 0)st[ss].mix1_selfreq=mix1_fq_mid[ss*max_fft1n+fft1_nx];     /* mix1.c:1059 */
+  st[ss].mix1_phase=mix1_phase[ss];
+  st[ss].mix1_phase_step=mix1_phase_step[ss];
+  st[ss].mix1_phase_rot=mix1_phase_rot[ss];
+  st[ss].mix1_old_phase=mix1_old_phase[ss];
+  st[ss].mix1_point=mix1_point[ss];
+  st[ss].mix1_old_point=mix1_old_point[ss];
+  }
+memset(&a,0,sizeof(a));
+a.fft1_float.base=fft1_float;
+a.fft1_float.size=(size_t)fft1_mask+1;
+a.fft1_px=(uint32_t)fft1_px;
+a.nblocks=1;
+a.no_of_channels=k;
+a.state=st;
+a.timf3_float.base=timf3_float;
+a.timf3_float.size=(size_t)timf3_size;
+a.timf3_pa=(uint32_t)timf3_pa;
+rc=lb200_mix1(shim_plan[0],&a);
+if(rc != LB200_OK){shim_fail(rc); return;}
+for(ss=0; ss<k; ss++)
+  {
+  mix1_phase[ss]=st[ss].mix1_phase;
+  mix1_phase_step[ss]=st[ss].mix1_phase_step;
+  mix1_phase_rot[ss]=st[ss].mix1_phase_rot;
+  mix1_old_phase[ss]=st[ss].mix1_old_phase;
+  mix1_point[ss]=st[ss].mix1_point;
+  mix1_old_point[ss]=st[ss].mix1_old_point;
+  if(mix1_selfreq[ss] >= 0)lb200_shim_afc_tables(ss);
+  }
+timf3_pa=(timf3_pa+timf3_block)&timf3_mask;         /* mix1.c:1093-1095 */
+fft1_nx=(fft1_nx+1)&fft1n_mask;
+fft1_px=(fft1_px+fft1_block)&fft1_mask;
+}

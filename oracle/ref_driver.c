@@ -51,6 +51,7 @@ typedef struct {
   int sample_shift;      /* ui.sample_shift */
   int correlation;       /* genparm[FFT1_CORRELATION_SPECTRUM] -> fft1_correlation_flag (two channels only, buf.c:1223-1224) */
   int afc;               /* fft1afc_flag: AFC from fft1 (second FFT off), fft1_c keeps fft1_power / fft1_xypower */
+  int afc_mix;           /* drive fft1_mix1_afc with a synthetic AFC track instead of fft1_mix1_fixed (one selection) */
 } ref_cfg;
 
 typedef struct {
@@ -68,6 +69,9 @@ void lb200_shim_close(void);
 void lb200_shim_fft1_b(int timf1p_ref, float *out, float *tmp, int gpu_handle_number);
 void lb200_shim_fft1_c(void);
 void lb200_shim_mix1_fixed(void);
+void lb200_shim_mix1_afc(void);
+extern void (*lb200_shim_afc_tables)(int ss);
+#define HOT_MIX1_AFC lb200_shim_mix1_afc
 #define HOT_FFT1_B lb200_shim_fft1_b
 #define HOT_FFT1_C lb200_shim_fft1_c
 #define HOT_MIX1_FIXED lb200_shim_mix1_fixed
@@ -75,6 +79,29 @@ void lb200_shim_mix1_fixed(void);
 #define HOT_FFT1_B fft1_b
 #define HOT_FFT1_C fft1_c
 #define HOT_MIX1_FIXED fft1_mix1_fixed
+#define HOT_MIX1_AFC fft1_mix1_afc
+#endif
+void fft1_mix1_afc(void);
+void do_mix1_afc(int ss);        /* mix1.c:648, external linkage but no prototype in the headers */
+
+/* the synthetic AFC track of the afc_mix harness: the selected frequency wobbling slowly */
+static double afc_track(int ss, long tno);
+#ifdef LB200_USE_SHIM
+/* Stand-in for the split mix1.c a Linrad maintainer would make (see lb200_shim.c): run the
+ * reference's own do_mix1_afc for its table maintenance with the mixer's output and phase state
+ * held away, so that nothing of its CPU do_mix1 reaches the results. */
+static float *afc_dummy_timf3;
+static void afc_tables_via_reference(int ss)
+{
+  float *keep = timf3_float;
+  float ph = mix1_phase[ss], oph = mix1_old_phase[ss];
+  if (!afc_dummy_timf3) afc_dummy_timf3 = calloc((size_t)2 * timf3_size + 64, sizeof(float));
+  timf3_float = afc_dummy_timf3;
+  do_mix1_afc(ss);
+  timf3_float = keep;
+  mix1_phase[ss] = ph;
+  mix1_old_phase[ss] = oph;
+}
 #endif
 
 static ref_cfg C;
@@ -299,6 +326,19 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   fft1_sumsq_mask = fft1_sumsq_bufsize - 1;
   fft1_sumsq = zalloc(sizeof(float) * fft1_sumsq_bufsize);
   fft1_slowsum = zalloc(sizeof(float) * fft1_size);
+  if (C.afc_mix) {                                        /* buf.c:1089-1092, 1255-1258, 1598 */
+    int nafc = REF_MAX_SEL * max_fft1n;
+    mix1_fq_mid = zalloc(sizeof(float) * nafc);
+    mix1_fq_start = zalloc(sizeof(float) * nafc);
+    mix1_fq_curv = zalloc(sizeof(float) * nafc);
+    mix1_fq_slope = zalloc(sizeof(float) * nafc);
+    for (i = 0; i < nafc; i++) { mix1_fq_mid[i] = -1; mix1_fq_start[i] = -1; }
+    fftxn_mask = fft1n_mask;
+    baseband_bw_hz = 0.05f * fft1_hz_per_point * (float)mix1.size;
+#ifdef LB200_USE_SHIM
+    lb200_shim_afc_tables = afc_tables_via_reference;
+#endif
+  }
   if (fft1afc_flag > 0) {                                 /* buf.c:935-940 */
     fft1_power = zalloc(sizeof(float) * fft1_size * max_fft1n);
     fft1_xypower = zalloc(sizeof(TWOCHAN_POWER) * fft1_size * max_fft1n);
@@ -466,7 +506,15 @@ int ref_process(const void *data, int nblocks, float *fft1_out, float *raw_out, 
           mix1_phase[0] = SEL[ss].phase; mix1_phase_step[0] = SEL[ss].phase_step;
           mix1_phase_rot[0] = SEL[ss].phase_rot; mix1_old_phase[0] = SEL[ss].old_phase;
           mix1_point[0] = SEL[ss].point; mix1_old_point[0] = SEL[ss].old_point;
-          HOT_MIX1_FIXED();
+          if (C.afc_mix) {
+            /* what the AFC would have put there: this transform's and the next one's frequency */
+            if (mix1_fq_mid[fft1_nx] < 0) mix1_fq_mid[fft1_nx] = (float)afc_track(ss, (long)tno);
+            if (mix1_fq_start[fft1_nx] < 0) mix1_fq_start[fft1_nx] = mix1_fq_mid[fft1_nx];
+            mix1_fq_mid[(fft1_nx + 1) & fft1n_mask] = (float)afc_track(ss, (long)tno + 1);
+            HOT_MIX1_AFC();
+          } else {
+            HOT_MIX1_FIXED();
+          }
           SEL[ss].phase = mix1_phase[0]; SEL[ss].phase_step = mix1_phase_step[0];
           SEL[ss].phase_rot = mix1_phase_rot[0]; SEL[ss].old_phase = mix1_old_phase[0];
           SEL[ss].point = mix1_point[0]; SEL[ss].old_point = mix1_old_point[0];
@@ -484,6 +532,11 @@ int ref_process(const void *data, int nblocks, float *fft1_out, float *raw_out, 
     if (ref_last_lirerr) return ref_last_lirerr;
   }
   return 0;
+}
+
+static double afc_track(int ss, long tno)
+{
+  return SEL[ss].selfreq + 0.4 * fft1_hz_per_point * sin(0.35 * (double)tno);
 }
 
 /* timing leg for bench.py --impl reference / cpu_baseline: same loop, no copies */

@@ -21,7 +21,7 @@ class RefCfg(C.Structure):
         "input_mode", "rf_channels", "ad_speed", "fft1_n", "fft1_version", "sinpow",
         "fft1_gain", "mix1_red_n", "avg1num", "avg2num", "waterfall_avgnum", "direction",
         "n_sel", "first_xpoint", "xpoints", "xpoints_per_pixel", "pixels_per_xpoint",
-        "wf_lines", "sample_shift", "correlation", "afc")]
+        "wf_lines", "sample_shift", "correlation", "afc", "afc_mix")]
 
 
 def available():
@@ -39,7 +39,7 @@ class RefOracle:
                  fft1_gain=2000, mix1_red_n=4, avg1num=5, avg2num=4, waterfall_avgnum=10,
                  direction=1, n_sel=0, first_xpoint=0, xpoints=None, xpoints_per_pixel=1,
                  pixels_per_xpoint=1, wf_lines=8, sample_shift=0, timf1_bytes=None, max_fft1n=8, through_shim=False,
-                 correlation=0, afc=0):
+                 correlation=0, afc=0, afc_mix=0):
         self.lib = C.CDLL(SHIM_SO if through_shim else REF_SO)
         L = self.lib
         L.ref_init.argtypes = [C.POINTER(RefCfg), C.c_int, C.c_int]
@@ -65,7 +65,7 @@ class RefOracle:
         self.cfg = RefCfg(input_mode, rf_channels, ad_speed, fft1_n, fft1_version, sinpow,
                           fft1_gain, mix1_red_n, avg1num, avg2num, waterfall_avgnum, direction,
                           n_sel, first_xpoint, xpoints, xpoints_per_pixel, pixels_per_xpoint,
-                          wf_lines, sample_shift, correlation, afc)
+                          wf_lines, sample_shift, correlation, afc, afc_mix)
         frame = (4 if input_mode & IQ_DATA else 2) * rf_channels
         if input_mode & DWORD_INPUT:
             frame *= 2

@@ -97,3 +97,28 @@ def test_shim_afc_mode_fft1_c(mode, ch, ver):
         assert np.abs(ca - cb).max() <= 2e-5 * float(np.abs(cb).max())
     assert float(np.abs(pb).max()) > 0
     assert np.abs(pa - pb).max() <= 2e-5 * float(np.abs(pb).max())
+
+
+@pytest.mark.parametrize("mode,ch,ver,sinpow", [(IQ_DATA, 1, 6, 2), (IQ_DATA | TWO_CHANNELS, 2, 7, 2), (IQ_DATA, 1, 7, 3)])
+def test_shim_mix1_afc(mode, ch, ver, sinpow):
+    """fft1_mix1_afc (mix1.c:1044-1096): the mixer frequency of every transform comes from the AFC
+    track mix1_fq_mid[], which do_mix1_afc keeps bending (mix1.c:648-768).  The harness feeds both
+    sides the same synthetic track; the shim mixes on the GPU and leaves the table maintenance to
+    the reference's own code (here through a stand-in for the split of do_mix1_afc that
+    lb200_shim.c asks of mix1.c)."""
+    n = 10
+    kw = dict(input_mode=mode, rf_channels=ch, ad_speed=96000, fft1_n=n, mix1_red_n=3, version=ver, sinpow=sinpow)
+    N = 1 << n
+    nblocks = 17
+    P = run_reference(kw, np.zeros(16, np.int16), [], 0)["ref"].lib.ref_new_points()
+    raw = make_timf1(mode, ch, N, nblocks, P, seed=10)
+    sel = [N * 0.146 + 0.37]
+    ref = run_reference(kw, raw, sel, nblocks, afc_mix=1)
+    got = run_reference(kw, raw, sel, nblocks, through_shim=True, afc_mix=1)
+    fixed = run_reference(kw, raw, sel, nblocks)
+    assert np.abs(ref["timf3"] - fixed["timf3"]).max() > 1e-3 * np.abs(fixed["timf3"]).max()     # the track really moves the mixer
+    sg, sr = got["states"][0], ref["states"][0]
+    assert sg["point"] == sr["point"] and float(sg["phase"]) == float(sr["phase"])
+    assert float(sg["phase_rot"]) == float(sr["phase_rot"]) and float(sg["phase_step"]) == float(sr["phase_step"])
+    assert rel_rms(got["timf3"][1:, 0], ref["timf3"][1:, 0]) <= 1e-4
+    assert got["timf3_pa"] == ref["timf3_pa"]
