@@ -50,6 +50,8 @@ fft1_small_launch_t lb_get_fft1_fused(int log2n, int fmt, int fc, int* threads, 
 // in L2 between step A and step B
 #include "fft1_large.cuh"
 #include <cstdlib>
+cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k);
+bool lb_fft1_pipe_supported(const lb200_plan* plan, const Fft1K& k);
 cudaError_t lb_large_launch_fmt0(int, int, const Fft1LargeK&, int, cudaStream_t);
 cudaError_t lb_large_launch_fmt1(int, int, const Fft1LargeK&, int, cudaStream_t);
 cudaError_t lb_large_launch_fmt2(int, int, const Fft1LargeK&, int, cudaStream_t);
@@ -181,13 +183,13 @@ cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k)
   const int ngroups = (c0 + k.nblocks + group - 1) / group;
   const char* env = getenv("LB200_SCRATCH_MB");
   const size_t budget = (size_t)(env ? atoi(env) : 48) << 20;
-  const size_t per_group = (size_t)group * nch * N * sizeof(float2) * (large ? 2 : 1);
+  const size_t per_group = (size_t)group * nch * N * sizeof(float2) * ((large && !lb_fft1_pipe_supported(plan, k)) ? 2 : 1);
   int gps = (int)(budget / per_group);
   if (gps < 1) gps = 1;
   const size_t need = (size_t)gps * group * nch * N;
   cudaError_t e = ensure_buf(&plan->d_zbuf, &plan->zbuf_elems, need);
   if (e != cudaSuccess) return e;
-  if (large) {
+  if (large && !lb_fft1_pipe_supported(plan, k)) {
     e = ensure_buf(&plan->d_scratch, &plan->scratch_elems, need);
     if (e != cudaSuccess) return e;
   }
@@ -225,6 +227,12 @@ cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k)
       e = fn(k1, grid, plan->stream);
       if (e != cudaSuccess) return e;
       plan->launches += 1;
+    } else if (lb_fft1_pipe_supported(plan, k)) {
+      k1.ref0 = k.ref0 + (uint32_t)b_first * k.blockbytes;
+      k1.nblocks = b_count;
+      k1.zb_first = 0;
+      e = lb_launch_fft1_pipe(plan, k1);    // counts its own launch
+      if (e != cudaSuccess) return e;
     } else {
       Fft1LargeK q;
       k1.zb_first = b_first;

@@ -28,6 +28,9 @@ mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem, int* p
 fft1_small_launch_t lb_get_fft1_fused(int log2n, int fmt, int fc, int* threads, size_t* smem);
 cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k);
 cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k);
+cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k);
+bool lb_fft1_pipe_supported(const lb200_plan* plan, const Fft1K& k);
+int lb_fft1_pipe_status(lb200_plan* plan);
 bool lb_fft1_large_supported(int log2n);
 
 // fft1_sumsq rows from per-transform power rows (small-batch path of lb200_fft1_dev): one thread
@@ -141,6 +144,30 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
     if ((rc = upload(plan, (void**)&plan->d_Wn1, w.data(), sizeof(float2) * w.size()))) return fail(rc);
     make_twiddles(w, 1 << ln2);
     if ((rc = upload(plan, (void**)&plan->d_Wn2, w.data(), sizeof(float2) * w.size()))) return fail(rc);
+    // persistent four-step kernel: the window transposed to [n2][n1] so that the lanes of a column
+    // transform (along n1) read it as contiguous runs (fft1_pipe.cuh); IQ input gets (-1)^n folded in
+    // (n = n1*N2 + n2 has the parity of n2), real input keeps its (w[2n], w[2n+1]) pairs
+    {
+      const size_t n1 = (size_t)1 << ln1, n2 = (size_t)1 << ln2;
+      const float* win = cfg->fft1_window;
+      if (plan->iq) {
+        std::vector<float> wt(n1 * n2);
+        for (size_t a = 0; a < n2; a++)
+          for (size_t b = 0; b < n1; b++) {
+            const float wv = win ? win[b * n2 + a] : 1.0f;
+            wt[a * n1 + b] = (a & 1) ? -wv : wv;
+          }
+        if ((rc = upload(plan, &plan->d_wT, wt.data(), sizeof(float) * wt.size()))) return fail(rc);
+      } else {
+        std::vector<float2> wt(n1 * n2);
+        for (size_t a = 0; a < n2; a++)
+          for (size_t b = 0; b < n1; b++) {
+            const size_t n = b * n2 + a;
+            wt[a * n1 + b] = win ? make_float2(win[2 * n], win[2 * n + 1]) : make_float2(1.0f, 1.0f);
+          }
+        if ((rc = upload(plan, &plan->d_wT, wt.data(), sizeof(float2) * wt.size()))) return fail(rc);
+      }
+    }
   }
   if (cfg->fft1_window)   // real input: 2N real samples per transform (fft1_re.c:44-57)
     if ((rc = upload(plan, (void**)&plan->d_window, cfg->fft1_window, sizeof(float) * plan->N * (plan->iq ? 1 : 2)))) return fail(rc);
@@ -254,7 +281,8 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   for (auto& kv : plan->registered) cudaHostUnregister(const_cast<void*>(kv.first));
   void* ptrs[] = {plan->d_foldcorr, plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
                   plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wn1, plan->d_Wn2,
-                  plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2, plan->d_zbuf, plan->d_Wre, plan->d_powtmp};
+                  plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2, plan->d_zbuf, plan->d_Wre, plan->d_powtmp,
+                  plan->d_wT, plan->d_pipe_y, plan->d_pipe_sync};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < lb200_plan::kJobSlots; i++) {
     if (plan->d_mixjobs[i]) cudaFree(plan->d_mixjobs[i]);
@@ -277,6 +305,10 @@ extern "C" int lb200_synchronize(lb200_plan* plan)
 {
   if (!plan) return LB200_ERR_BAD_ARG;
   LB_CUDA(cudaStreamSynchronize(plan->stream));
+  if (lb_fft1_pipe_status(plan)) {
+    fprintf(stderr, "[lb200] four-step pipeline: a dependency wait timed out\n");
+    return LB200_ERR_CUDA;
+  }
   return LB200_OK;
 }
 extern "C" uint64_t lb200_launch_count(const lb200_plan* plan) { return plan ? plan->launches : 0; }
@@ -395,7 +427,8 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
     return 0;
   };
   if (plan->cfg.fft1_n > 14) {
-    LB_CUDA(lb_launch_fft1_large(plan, k));   // counts its own launches
+    if (lb_fft1_pipe_supported(plan, k)) LB_CUDA(lb_launch_fft1_pipe(plan, k));
+    else LB_CUDA(lb_launch_fft1_large(plan, k));   // both count their own launches
     return post();
   }
   int threads = 0;

@@ -64,6 +64,17 @@ struct lb200_plan {
   float2* d_Wre = nullptr;     // real input: exp(-i pi k / N), k = 0..N
   float2* d_Wn1 = nullptr;     // four-step: exp(-2 pi i m / N1)
   float2* d_Wn2 = nullptr;     // four-step: exp(-2 pi i m / N2)
+  // persistent four-step kernel (fft1_pipe.cuh)
+  void* d_wT = nullptr;        // window transposed to [n2][n1] (IQ: float with (-1)^n folded in; real input: float2)
+  int* d_pipe_sync = nullptr;  // queue head, error flag, per-transform completion counters
+  size_t pipe_sync_ints = 0;
+  float2* d_pipe_y = nullptr;  // the Y ring: [pipe_slots * nch][N2][N1]
+  int pipe_slots = 0;          // transforms the Y ring holds
+  alignas(64) unsigned char map_y[128];      // CUtensorMap of the Y ring
+  alignas(64) unsigned char map_out[128];    // CUtensorMap of the output ring / zbuf of the last call
+  const void* map_out_base = nullptr;
+  size_t map_out_planes = 0;
+  bool pipe_checked = false;   // the error flag of the last launch has been read back
   // mix1 per-call staging: a small ring of pinned/device job tables so that consecutive
   // calls never wait for each other on the host
   static constexpr int kJobSlots = 4;

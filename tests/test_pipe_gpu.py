@@ -1,0 +1,200 @@
+"""The persistent four-step kernel (fft1_large_pipe_kernel, N = 2^15 .. 2^20) against the two-kernel
+four-step path it replaces and against itself under every data-movement variant.
+
+  * every size and input format the pipeline takes == the legacy cols/rows kernels (which the
+    parity tests pin on the compiled reference) to float32 rounding: both are correctly rounded
+    float32 FFTs of different structure, so fft1_float agrees to ~3e-7 relative rms;
+  * the same batch with the Y tile fetched by TMA tensor load or by cp.async, the output written
+    by TMA tensor store or by streaming stores, and any queue lag / ring depth, gives bit-identical
+    fft1_float (same arithmetic, different plumbing) and fft1_sumsq equal to summation order;
+  * one call of B transforms == calls of 7; the dependency waits never time out.
+Reference parity itself: tests/test_parity_gpu.py (test_large_*, test_cfg4_*, test_cfg3_*,
+test_real_large_*) and tests/test_batch_gpu.py run through this kernel as well."""
+import os
+
+import numpy as np
+import pytest
+
+from linrad_b200 import api, sizing
+from linrad_b200.synth import make_timf1
+from tests.helpers import rel_rms, pow2_at_least, IQ_DATA, DWORD_INPUT, TWO_CHANNELS
+
+pytestmark = [pytest.mark.gpu]
+
+ENV_KEYS = ("LB200_LARGE_LEGACY", "LB200_PIPE_TMA_IN", "LB200_PIPE_TMA_OUT", "LB200_PIPE_LAG", "LB200_PIPE_SLOTS",
+            "LB200_PIPE_PREFETCH")
+
+
+class _Env:
+    def __init__(self, **kw):
+        self.kw = {k: str(v) for k, v in kw.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in ENV_KEYS}
+        for k in ENV_KEYS:
+            os.environ.pop(k, None)
+        os.environ.update(self.kw)
+
+    def __exit__(self, *a):
+        for k in ENV_KEYS:
+            os.environ.pop(k, None)
+            if self.old[k] is not None:
+                os.environ[k] = self.old[k]
+
+
+def _run(s, rawb, nblocks, chunk, first=0, **plan_kw):
+    """fft1 + fft1_c over host rings in calls of `chunk`; returns (fft1_float, fft1_sumsq rows)"""
+    timf1 = np.zeros(pow2_at_least((nblocks + 2) * s.timf1_blockbytes), np.uint8)
+    # start somewhere inside the ring so that spans wrap
+    idx = (first + np.arange(rawb.size)) & (timf1.size - 1)
+    timf1[idx] = rawb
+    fft1 = np.zeros(pow2_at_least(nblocks * s.fft1_block), np.float32)
+    sumsq = np.zeros(pow2_at_least((nblocks // s.avg1num + 2) * s.fft1_size), np.float32)
+    plan = api.Plan(s, **plan_kw)
+    try:
+        done, pa, counter = 0, 0, 0
+        while done < nblocks:
+            nb = min(chunk, nblocks - done)
+            plan.fft1_host(timf1=timf1, ref=(first + done * s.timf1_blockbytes) & (timf1.size - 1), nblocks=nb, fft1=fft1,
+                           fft1_pa=done * s.fft1_block, apply_fc=True, sumsq=sumsq, sumsq_pa=pa, counter=counter)
+            tot = counter + nb
+            pa += (tot // s.avg1num) * s.fft1_size
+            counter = tot % s.avg1num
+            done += nb
+        plan.synchronize()          # raises if a dependency wait of the pipeline timed out
+    finally:
+        plan.close()
+    rows = nblocks // s.avg1num
+    return fft1[: nblocks * s.fft1_block].reshape(nblocks, -1).copy(), sumsq[: rows * s.fft1_size].reshape(rows, -1).copy()
+
+
+def _input(s, nblocks, seed):
+    raw = make_timf1(s.input_mode, s.rf_channels, s.fft1_size, nblocks, s.fft1_new_points, seed=seed)
+    return np.ascontiguousarray(raw).view(np.uint8).reshape(-1)[: nblocks * s.timf1_blockbytes]
+
+
+FORMATS = [
+    (IQ_DATA, 1), (IQ_DATA | TWO_CHANNELS, 2), (IQ_DATA | DWORD_INPUT, 1),
+    (0, 1), (TWO_CHANNELS, 2), (DWORD_INPUT, 1),
+]
+
+
+@pytest.mark.parametrize("n", [15, 16, 17, 18, 19, 20])
+def test_pipe_equals_legacy_all_sizes(n):
+    s = sizing.PathSetup(input_mode=IQ_DATA, rf_channels=1, ad_speed=20000000, fft1_n=n, mix1_red_n=6)
+    nblocks = 7 if n <= 18 else 4
+    rawb = _input(s, nblocks, seed=n)
+    with _Env(LB200_LARGE_LEGACY=1):
+        f0, p0 = _run(s, rawb, nblocks, chunk=nblocks)
+    with _Env():
+        f1, p1 = _run(s, rawb, nblocks, chunk=nblocks, first=3 * s.timf1_blockbytes + 4096)
+    e = rel_rms(f1, f0)
+    assert e <= 6e-7, f"fft1_float pipe vs legacy: rel rms {e}"
+    assert np.isfinite(f1).all()
+    strong = p0 > 1e-4 * p0.max()
+    assert (np.abs(p1 - p0)[strong] <= 2e-5 * p0[strong]).all(), "fft1_sumsq pipe vs legacy"
+
+
+@pytest.mark.parametrize("mode,ch", FORMATS)
+@pytest.mark.parametrize("n", [15, 17])
+def test_pipe_equals_legacy_formats(mode, ch, n):
+    s = sizing.PathSetup(input_mode=mode, rf_channels=ch, ad_speed=2400000, fft1_n=n, mix1_red_n=5)
+    nblocks = 6
+    rawb = _input(s, nblocks, seed=3 * n + ch)
+    with _Env(LB200_LARGE_LEGACY=1):
+        f0, p0 = _run(s, rawb, nblocks, chunk=4)
+    with _Env():
+        f1, p1 = _run(s, rawb, nblocks, chunk=4)
+    e = rel_rms(f1, f0)
+    assert e <= 6e-7, f"fft1_float pipe vs legacy: rel rms {e}"
+    strong = p0 > 1e-4 * p0.max()
+    assert (np.abs(p1 - p0)[strong] <= 2e-5 * p0[strong]).all()
+
+
+@pytest.mark.parametrize("direction,first_x,xpoints", [(-1, 0, 0), (1, 3000, 20000), (-1, 700, 9000)])
+def test_pipe_equals_legacy_direction_and_range(direction, first_x, xpoints):
+    kw = dict(input_mode=IQ_DATA, rf_channels=1, ad_speed=2400000, fft1_n=16, mix1_red_n=5, direction=direction)
+    if xpoints:
+        kw.update(first_xpoint=first_x, xpoints=xpoints)
+    s = sizing.PathSetup(**kw)
+    nblocks = 6
+    rawb = _input(s, nblocks, seed=8)
+    with _Env(LB200_LARGE_LEGACY=1):
+        f0, p0 = _run(s, rawb, nblocks, chunk=5)
+    with _Env():
+        f1, p1 = _run(s, rawb, nblocks, chunk=5)
+    # bins outside the display range keep the raw fft1_b scale: compare on the common energy
+    assert rel_rms(f1, f0) <= 6e-7
+    strong = p0 > 1e-4 * p0.max()
+    assert (np.abs(p1 - p0)[strong] <= 2e-5 * p0[strong]).all()
+    assert np.array_equal(p1 == 0, p0 == 0), "bins outside the range must stay untouched in both"
+
+
+VARIANTS = [
+    dict(LB200_PIPE_TMA_IN=0, LB200_PIPE_TMA_OUT=0),
+    dict(LB200_PIPE_TMA_IN=1, LB200_PIPE_TMA_OUT=0),
+    dict(LB200_PIPE_TMA_IN=0, LB200_PIPE_TMA_OUT=1),
+    dict(LB200_PIPE_LAG=1, LB200_PIPE_SLOTS=2),
+    dict(LB200_PIPE_LAG=2, LB200_PIPE_SLOTS=3, LB200_PIPE_PREFETCH=0),
+    dict(LB200_PIPE_LAG=40, LB200_PIPE_SLOTS=64),
+]
+
+
+@pytest.mark.parametrize("mode,ch,n", [(IQ_DATA, 1, 18), (IQ_DATA, 1, 15), (0, 1, 15), (IQ_DATA | TWO_CHANNELS, 2, 16)])
+def test_pipe_variants_bit_identical(mode, ch, n):
+    """TMA or cp.async in, TMA or plain stores out, any queue lag and ring depth: same bits"""
+    s = sizing.PathSetup(input_mode=mode, rf_channels=ch, ad_speed=20000000, fft1_n=n, mix1_red_n=6)
+    nblocks = 23 if n <= 16 else 11
+    rawb = _input(s, nblocks, seed=21)
+    with _Env():
+        f0, p0 = _run(s, rawb, nblocks, chunk=nblocks)
+    assert np.isfinite(f0).all() and np.abs(f0).max() > 0
+    for v in VARIANTS:
+        with _Env(**v):
+            f1, p1 = _run(s, rawb, nblocks, chunk=nblocks)
+        assert np.array_equal(f1, f0), f"fft1_float differs under {v}"
+        assert np.allclose(p1, p0, rtol=3e-6, atol=0), f"fft1_sumsq differs under {v}"
+
+
+def test_pipe_batch_cfg4_one_call_equals_calls_of_seven():
+    """bench-shaped batch at configs[3]: 60 transforms of 2^18 points through the device-ring API
+    (one launch, the Y ring wraps several times) == the same input in calls of 7"""
+    import torch
+    s = sizing.PathSetup(input_mode=IQ_DATA, rf_channels=1, ad_speed=20000000, fft1_n=18, mix1_red_n=6)
+    nblocks, period = 60, 6
+    one = _input(s, period, seed=5)
+    rawb = np.tile(one, nblocks // period)
+    dev = torch.device("cuda", 0)
+    N = s.fft1_size
+    timf1_bytes = pow2_at_least((nblocks + 2) * s.timf1_blockbytes)
+    fft1_floats = pow2_at_least(nblocks * s.fft1_block)
+    rows = nblocks // s.avg1num
+    sumsq_floats = pow2_at_least((rows + 1) * N)
+    res = []
+    for chunk in (nblocks, 7):
+        t1 = torch.zeros(timf1_bytes, dtype=torch.uint8, device=dev)
+        t1[: rawb.size].copy_(torch.from_numpy(rawb))
+        f = torch.zeros(fft1_floats, dtype=torch.float32, device=dev)
+        sq = torch.zeros(sumsq_floats, dtype=torch.float32, device=dev)
+        plan = api.Plan(s)
+        try:
+            done, pa, counter = 0, 0, 0
+            while done < nblocks:
+                nb = min(chunk, nblocks - done)
+                plan.fft1_dev(timf1=t1.data_ptr(), timf1_bytes=timf1_bytes, ref=done * s.timf1_blockbytes, nblocks=nb,
+                              fft1=f.data_ptr(), fft1_floats=fft1_floats, fft1_pa=done * s.fft1_block, apply_fc=True,
+                              sumsq=sq.data_ptr(), sumsq_floats=sumsq_floats, sumsq_pa=pa, counter=counter)
+                tot = counter + nb
+                pa += (tot // s.avg1num) * N
+                counter = tot % s.avg1num
+                done += nb
+            plan.synchronize()
+        finally:
+            plan.close()
+        res.append((f[: nblocks * s.fft1_block].cpu().numpy().reshape(nblocks, -1), sq[: rows * N].cpu().numpy().reshape(rows, -1)))
+    (f_big, p_big), (f_small, p_small) = res
+    assert np.array_equal(f_big, f_small), "fft1_float differs between one call and calls of 7"
+    assert np.allclose(p_big, p_small, rtol=3e-6, atol=0)
+    # periodic input -> periodic spectra (transform 0 sees the empty ring in its overlap half)
+    assert np.array_equal(f_big[1: nblocks - period], f_big[1 + period:])
+    assert np.isfinite(f_big).all() and np.abs(f_big).max() > 0
