@@ -21,9 +21,14 @@
 //     k1).  The window table is stored transposed (wT[n2][n1]) so that it is read the same way.
 //   * role B: 256/T2 adjacent rows (k1) side by side with the row index fastest across lanes; the
 //     Y tile [N2][TB] arrives by ONE TMA tensor load (cp.async.bulk.tensor.3d, mbarrier
-//     complete_tx) issued while the previous item is computed; bins k1..k1+TB-1 of one k2 leave
-//     as one 128-byte run, either as streaming stores or (one channel) staged and written by TMA
-//     tensor stores (cp.async.bulk.tensor.3d shared -> global).
+//     complete_tx) issued while the previous item is computed; the exchange between the two passes
+//     goes through the input buffer once it has been read (one barrier pair per item); bins
+//     k1..k1+TB-1 of one k2 leave as one 128-byte run, as streaming stores or (optionally, one
+//     channel) staged and written by TMA tensor stores (cp.async.bulk.tensor.3d shared -> global).
+//   * the queue position of the item after next is claimed two items ahead and readiness flags
+//     are read with relaxed loads that stay in flight under the conversion, so the atomic / L2
+//     round trips of the scheduling never sit on a warp's critical path; a column item's completion
+//     is published once per CTA behind the next CTA barrier.
 //   * the new timf1 bytes of a later transform are pulled into L2 by cp.async.bulk.prefetch.L2.
 #pragma once
 #include <cuda.h>
@@ -76,6 +81,16 @@ LB_D void red_add(float* p, float v)
 {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+LB_D void st_global(float2* p, float2 v)
+{
+  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+LB_D int ld_relaxed(const int* p)
+{
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 LB_D int ld_acquire(const int* p)
 {
   int v;
@@ -86,16 +101,18 @@ LB_D int ld_acquire(const int* p)
 // up) the error flag is set and the wait returns; the host reports LB200_ERR_CUDA for the call.
 LB_D void pipe_wait(const int* ctr, int target, int* err)
 {
-  if (ld_acquire(ctr) >= target) return;
-  const long long t0 = clock64();
-  while (ld_acquire(ctr) < target) {
-    __nanosleep(100);
-    if (*reinterpret_cast<volatile int*>(err)) return;
-    if (clock64() - t0 > (1ll << 31)) {
-      atomicExch(err, 1);
-      return;
+  if (ld_relaxed(ctr) < target) {
+    const long long t0 = clock64();
+    while (ld_relaxed(ctr) < target) {
+      __nanosleep(64);
+      if (*reinterpret_cast<volatile int*>(err)) return;
+      if (clock64() - t0 > (1ll << 31)) {
+        atomicExch(err, 1);
+        return;
+      }
     }
   }
+  (void)ld_acquire(ctr);
 }
 
 // mbarrier wait that cannot hang either (a tensor map the TMA unit rejects would never complete_tx)
@@ -136,14 +153,14 @@ struct PipeCfg {
   // role B: T2 threads per row, TB rows per item
   static constexpr int T2 = N2 / 32, LT2 = LN2 - 5, TB = NTHREADS / T2, TILES_B = N1 / TB;
   static constexpr int Q2 = 32 / T2;
-  static constexpr int ROUND_B = 8192 * 8 / Q2;            // one exchange round, all rows
+  static constexpr int ROUND_B = 8192 * 8 / Q2;            // one exchange round, all rows (the rounds lie side by side in the input buffer)
   static constexpr int STAGE_B = 32768;                    // half an output tile (TMA store rounds)
   static constexpr int BOX_IN = N2 < 256 ? N2 : 256;       // rows per input box
   static constexpr int BOX_OUT = N2 / 2 < 256 ? N2 / 2 : 256;
   static constexpr int IA = TILES_A * NCH, IB = TILES_B * NCH;   // items per transform
   static constexpr int cmax(int a, int b) { return a > b ? a : b; }
   static constexpr int IN_BYTES = (cmax(N1 * PITCH_A, 65536) + 127) & ~127;
-  static constexpr int WORK_BYTES = (cmax(cmax(NWARPS * AREA_A, ROUND_B), STAGE_B) + 127) & ~127;
+  static constexpr int WORK_BYTES = (cmax(NWARPS * AREA_A, STAGE_B) + 127) & ~127;
   static constexpr int TAB_BYTES = (T1 + T2) * 5 * 8;
   static constexpr int SMEM = IN_BYTES + WORK_BYTES + TAB_BYTES;
   static constexpr int MINB = SMEM + 1024 <= 113 * 1024 ? 2 : 1;
@@ -223,6 +240,48 @@ LB_HD void rowx_load(float2 (&u)[32], const float2* buf, int t, int r, int q)
 }
 
 #ifdef __CUDACC__
+// The general form of the rows epilogue (limited bin range, calibrated filtercorr table, tapered
+// edge bins, per-transform power rows): fft1_b's direction flip and fft1_c (fft1.c:3660-3680,
+// 4115-4200) for the 32 bins k0 + e*kstep a thread holds.  Kept out of line: only the outermost
+// tiles of an uncalibrated full-range set-up come here, and the common path keeps its registers.
+template <int NCH>
+__device__ __noinline__ void pipe_epilogue_general(float2 (&v)[32], const Fft1K& p, float* rowp, float* outb, int b, int c, int k0, int kstep, int N,
+                                                   bool keep)
+{
+  constexpr int MM = 2 * NCH;
+  float* prow = p.power_rows ? p.power_rows + (size_t)b * N : nullptr;
+#pragma unroll 4
+  for (int e = 0; e < 32; e++) {
+    const int k = k0 + kstep * e;
+    const float2 z = v[e];
+    float2 ov = p.direction < 0 ? make_float2(z.y, z.x) : make_float2(z.x, -z.y);
+    if (p.fc_mode != 0) {
+      const bool inr = (k >= p.first_point) && (k <= p.last_point);
+      if (inr) {
+        float2 f;
+        if (p.fc_mode == 2 || k < p.fc_edge || k >= N - p.fc_edge)
+          f = *reinterpret_cast<const float2*>(p.filtercorr + (size_t)k * MM + 2 * c);
+        else
+          f = make_float2(p.fc_gain, 0.0f);
+        const float re = ov.x * f.x - ov.y * f.y;      // fft1.c:4121-4125
+        const float im = ov.y * f.x + ov.x * f.y;
+        ov = make_float2(re, im);
+        const float pw = fmaf(re, re, im * im);
+        if (prow) {
+          if (NCH == 1) prow[k] = pw;
+          else red_add(prow + k, pw);                  // two channel items add into the host-zeroed row
+        } else if (rowp) {
+          red_add(rowp + k, pw);
+        }
+      } else if (prow && NCH == 1) {
+        prow[k] = 0.0f;
+      }
+    }
+    v[e] = ov;
+    if (!keep) __stcs(reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c), ov);
+  }
+}
+
 // raw frame at a shared-memory address -> the complex point of channel c (same conversions as load_iq)
 template <int FMT>
 LB_D float2 cvt_raw(const unsigned char* p, int c)
@@ -237,13 +296,15 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   using C = PipeCfg<LN1, LN2, FMT>;
   constexpr int N1 = C::N1, N2 = C::N2, N = C::N, NCH = C::NCH, MM = 2 * NCH, FRAME = C::FRAME;
   constexpr int T1 = C::T1, CW = C::CW, TA = C::TA, Q1 = C::Q1;
-  constexpr int T2 = C::T2, TB = C::TB, Q2 = C::Q2;
+  constexpr int T2 = C::T2, TB = C::TB;
+  constexpr int DONE_A = C::IA * C::NWARPS;      // doneA[b] when all columns of transform b are in Y
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* const in = smem_raw;
   unsigned char* const work = smem_raw + C::IN_BYTES;
   float2* const wbt = reinterpret_cast<float2*>(smem_raw + C::IN_BYTES + C::WORK_BYTES);
   __shared__ uint64_t bar_in;
   __shared__ PipeItem items[2];
+  __shared__ int slot_ok[2];
   const Fft1K& p = q.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int* const head = q.sync;
@@ -262,13 +323,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   }
 
   // ---- helpers ---------------------------------------------------------------------------------
-  auto claim = [&](PipeItem& dst) {               // thread 0 only
-    const int i = atomicAdd(head, 1);
-    PipeItem it = i < total ? pipe_decode(i, nb, q.lag, C::IA, C::IB) : pipe_decode(total, nb, q.lag, C::IA, C::IB);
-    if (it.role == 0) it.ready = 1;
-    else if (it.role == 1) it.ready = ld_acquire(doneA + it.b) >= C::IA * C::NWARPS ? 1 : 0;
-    dst = it;
-  };
+  auto decode = [&](int i) { return pipe_decode(i < total ? i : total, nb, q.lag, C::IA, C::IB); };
   auto slot_of = [&](int b) { return b % q.nslots; };
   // fetch the input of an item into `in`; called by all threads, the item's dependency is satisfied
   auto issue_load = [&](const PipeItem& it) {
@@ -296,8 +351,8 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       const int plane = slot_of(it.b) * NCH + c;
       if (q.tma_in) {
         if (tid == 0) {
-          // Y was written through the generic proxy (other SMs, observed by an acquire): order it
-          // before the TMA unit's reads
+          // Y was written through the generic proxy (other SMs, seen complete through doneA): order
+          // it before the TMA unit's reads
           asm volatile("fence.proxy.async;" ::: "memory");
           mbar_expect_tx(&bar_in, 65536u);
 #pragma unroll
@@ -318,24 +373,50 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
     }
   };
+  // thread 0: completion of a column item is published once per CTA, after a CTA barrier that all
+  // warps reach behind their Y stores (one fence per item instead of one per warp)
+  int pend_sig = -1;
+  auto flush_signal = [&]() {
+    if (pend_sig >= 0) {
+      __threadfence();
+      atomicAdd(doneA + pend_sig, C::NWARPS);
+      pend_sig = -1;
+    }
+  };
+  // an item whose input could not be prefetched: publish, wait for its producer, fetch
+  auto fetch_now = [&](const PipeItem& it) {
+    __syncthreads();                             // every warp is behind its stores of the item before
+    if (tid == 0) {
+      flush_signal();                            // ... which the awaited producer count may include
+      if (it.role == 1) pipe_wait(doneA + it.b, DONE_A, err);
+    }
+    __syncthreads();
+    issue_load(it);
+  };
 
+  // thread 0 keeps one queue position in flight: the atomic's latency is never waited for
+  int pend_idx = 0;
   if (tid == 0) {
-    claim(items[0]);
-    items[0].ready = 0;                          // the first item goes through the deferred path below
+    items[0] = decode(atomicAdd(head, 1));       // ready = 0: fetched through fetch_now
+    pend_idx = atomicAdd(head, 1);
   }
   __syncthreads();
   PipeItem cur = items[0];
-  if (cur.role >= 0) {
-    if (cur.role == 1 && tid == 0) pipe_wait(doneA + cur.b, C::IA * C::NWARPS, err);
-    __syncthreads();
-    issue_load(cur);
-  }
+  if (cur.role >= 0) fetch_now(cur);
   uint32_t par = 0;
   int s = 0;
   bool stores_pending = false;                   // thread 0: TMA stores may still be reading `work`
 
   while (cur.role >= 0) {
-    if (tid == 0) claim(items[s ^ 1]);
+    // ---- thread 0: next item, its readiness and this item's slot; loads in flight until barrier 1
+    PipeItem nx;
+    int rd = 0, sl = 0;
+    if (tid == 0) {
+      nx = decode(pend_idx);
+      pend_idx = atomicAdd(head, 1);
+      if (nx.role == 1) rd = ld_relaxed(doneA + nx.b);
+      if (cur.role == 0 && cur.b >= q.nslots) sl = ld_relaxed(doneB + (cur.b - q.nslots));
+    }
     const int tile = cur.j / NCH;
     const int c = cur.j - tile * NCH;
     float2 v[32];
@@ -371,12 +452,19 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           else v[e] = make_float2(sm.x * wv[e], sm.y * (wv[e] * dq));
         }
       }
-      if (tid == 0 && stores_pending) {          // role B's TMA stores read `work`: done before anybody rewrites it
-        bulk_wait_read();
-        stores_pending = false;
+      if (tid == 0) {
+        if (stores_pending) {                     // role B's TMA stores read `work`: done before anybody rewrites it
+          bulk_wait_read();
+          stores_pending = false;
+        }
+        nx.ready = nx.role == 0 ? 1 : (nx.role == 1 && rd >= DONE_A ? 1 : 0);
+        items[s ^ 1] = nx;
+        slot_ok[s] = (cur.b < q.nslots || sl >= C::IB) ? 1 : 0;
       }
-      __syncthreads();                            // the raw tile is consumed; items[s^1] is visible
+      __syncthreads();                            // barrier 1: the raw tile is consumed; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
+      const int my_slot_ok = slot_ok[s];
+      if (tid == 0) flush_signal();               // the item before this one is in Y
       if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
       // inter-step twiddle W_N^(n2*(t+T1*e)) = base * step^e, step given by exact binary powers
       const float2 tw_base = __ldg(q.Wbig + n2 * t);
@@ -406,25 +494,17 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
       apply_power_twiddles<32>(v, tw_base, tw_sb);
       // ---- the slot must have been read by the rows of transform b - nslots
-      if (cur.b >= q.nslots) {
+      if (!my_slot_ok) {
         if (lane == 0) pipe_wait(doneB + (cur.b - q.nslots), C::IB, err);
         __syncwarp();
       }
       {
         float2* Yp = q.Y + (size_t)(slot_of(cur.b) * NCH + c) * N + (size_t)n2 * N1 + t;
 #pragma unroll
-        for (int e = 0; e < 32; e++) Yp[e * T1] = v[e];
+        for (int e = 0; e < 32; e++) st_global(Yp + e * T1, v[e]);
       }
-      __syncwarp();
-      if (lane == 0) {
-        __threadfence();
-        atomicAdd(doneA + cur.b, 1);
-      }
-      if (nxt.role >= 0 && !nxt.ready) {
-        if (nxt.role == 1 && tid == 0) pipe_wait(doneA + nxt.b, C::IA * C::NWARPS, err);
-        __syncthreads();
-        issue_load(nxt);
-      }
+      if (tid == 0) pend_sig = cur.b;             // published behind the next CTA barrier
+      if (nxt.role >= 0 && !nxt.ready) fetch_now(nxt);
       cur = nxt;
     } else {
       // =============================== role B: TB rows of transform cur.b ======================
@@ -436,32 +516,36 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
 #pragma unroll
         for (int e = 0; e < 32; e++) v[e] = ip[e * (T2 * TB)];
       }
-      if (tid == 0 && stores_pending) {
-        bulk_wait_read();
-        stores_pending = false;
+      if (tid == 0) {
+        if (stores_pending) {
+          bulk_wait_read();
+          stores_pending = false;
+        }
+        nx.ready = nx.role == 0 ? 1 : (nx.role == 1 && rd >= DONE_A ? 1 : 0);
+        items[s ^ 1] = nx;
       }
-      __syncthreads();                            // the Y tile is in registers; items[s^1] is visible
+      __syncthreads();                            // barrier 1: the Y tile is in registers; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
-      if (tid == 0) {                             // this tile's share of the slot may be overwritten
-        __threadfence();
+      if (tid == 0) {
+        flush_signal();
+        __threadfence();                          // this tile's share of the slot may be overwritten
         atomicAdd(doneB + cur.b, 1);
       }
-      if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
-      // ---- row transforms
+      // ---- row transforms: one exchange through the (now free) input buffer, all rows at once
       pass0<T2>(v);
       {
-        float2* buf = reinterpret_cast<float2*>(work);
+        float2* buf = reinterpret_cast<float2*>(in);
         float2 u[32];
 #pragma unroll
-        for (int qq = 0; qq < Q2; qq++) {
-          if (qq > 0) __syncthreads();            // the previous round has been read
-          rowx_store<T2, TB>(v, buf, t, r, qq);
-          __syncthreads();
-          rowx_load<T2, TB>(u, buf, t, r, qq);
-        }
+        for (int qq = 0; qq < C::Q2; qq++) rowx_store<T2, TB>(v, buf + qq * (T2 * T2 * TB), t, r, qq);
+        __syncthreads();
+#pragma unroll
+        for (int qq = 0; qq < C::Q2; qq++) rowx_load<T2, TB>(u, buf + qq * (T2 * T2 * TB), t, r, qq);
 #pragma unroll
         for (int e = 0; e < 32; e++) v[e] = u[e];
       }
+      __syncthreads();                            // the input buffer is free again
+      if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
       {
         float2 wb[5];
 #pragma unroll
@@ -477,7 +561,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         if (!use_tma_out) {
           float2* zp = p.zbuf + ((size_t)(b - p.zb_first) * NCH + c) * N + k1 + (size_t)t * N1;
 #pragma unroll
-          for (int e = 0; e < 32; e++) zp[(size_t)e * (T2 * N1)] = v[e];
+          for (int e = 0; e < 32; e++) st_global(zp + (size_t)e * (T2 * N1), v[e]);
         }
       } else {
         const int group_size = p.power_rows ? 1 : p.avg1num;
@@ -492,51 +576,32 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         const bool fast = p.fc_mode == 1 && !p.power_rows && klo >= p.first_point && khi + N1 * (N2 - 1) <= p.last_point &&
                           p.fc_edge <= N1 && klo >= p.fc_edge && khi < N1 - p.fc_edge;
         if (fast) {
-          const float gain = p.fc_gain;
-          const bool rev = p.direction < 0;
-          float* rp = rowp ? rowp + k1 + N1 * t : nullptr;
-          float2* op = reinterpret_cast<float2*>(outb + (size_t)(k1 + N1 * t) * MM + 2 * c);
+          const float gain = p.fc_gain;           // fft1.c:4121-4125 with filtercorr = (gain, 0)
+          if (p.direction < 0) {
 #pragma unroll
-          for (int e = 0; e < 32; e++) {
-            const float2 z = v[e];
-            const float re = (rev ? z.y : z.x) * gain;           // fft1.c:4121-4125 with filtercorr = (gain, 0)
-            const float im = (rev ? z.x : -z.y) * gain;
-            if (rp) red_add(rp + e * (N1 * T2), fmaf(re, re, im * im));
-            v[e] = make_float2(re, im);
-            if (!use_tma_out) __stcs(op + (size_t)e * (N1 * T2 * NCH), v[e]);
+            for (int e = 0; e < 32; e++) v[e] = make_float2(v[e].y * gain, v[e].x * gain);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e++) v[e] = make_float2(v[e].x * gain, -v[e].y * gain);
+          }
+          if (rowp) {
+            float* rp = rowp + k1 + N1 * t;
+#pragma unroll
+            for (int e = 0; e < 32; e++) red_add(rp + e * (N1 * T2), fmaf(v[e].x, v[e].x, v[e].y * v[e].y));
+          }
+          if (!use_tma_out) {
+            float2* op = reinterpret_cast<float2*>(outb + (size_t)(k1 + N1 * t) * MM + 2 * c);
+#pragma unroll
+            for (int e = 0; e < 32; e++) __stcs(op + (size_t)e * (N1 * T2 * NCH), v[e]);
           }
         } else {
-          float* prow = p.power_rows ? p.power_rows + (size_t)b * N : nullptr;
+          // through a copy: only the copy's address is taken, v itself stays in registers
+          float2 tmp[32];
 #pragma unroll
-          for (int e = 0; e < 32; e++) {
-            const int k = k1 + N1 * (t + T2 * e);
-            const float2 z = v[e];
-            float2 ov = p.direction < 0 ? make_float2(z.y, z.x) : make_float2(z.x, -z.y);
-            if (p.fc_mode != 0) {
-              const bool inr = (k >= p.first_point) && (k <= p.last_point);
-              if (inr) {
-                float2 f;
-                if (p.fc_mode == 2 || k < p.fc_edge || k >= N - p.fc_edge)
-                  f = *reinterpret_cast<const float2*>(p.filtercorr + (size_t)k * MM + 2 * c);
-                else
-                  f = make_float2(p.fc_gain, 0.0f);
-                const float re = ov.x * f.x - ov.y * f.y;      // fft1.c:4121-4125
-                const float im = ov.y * f.x + ov.x * f.y;
-                ov = make_float2(re, im);
-                const float pw = fmaf(re, re, im * im);
-                if (prow) {
-                  if (NCH == 1) prow[k] = pw;
-                  else red_add(prow + k, pw);                  // two channel items add into the host-zeroed row
-                } else if (rowp) {
-                  red_add(rowp + k, pw);
-                }
-              } else if (prow && NCH == 1) {
-                prow[k] = 0.0f;
-              }
-            }
-            v[e] = ov;
-            if (!use_tma_out) __stcs(reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c), ov);
-          }
+          for (int e = 0; e < 32; e++) tmp[e] = v[e];
+          pipe_epilogue_general<NCH>(tmp, p, rowp, outb, b, c, k1 + N1 * t, N1 * T2, N, use_tma_out);
+#pragma unroll
+          for (int e = 0; e < 32; e++) v[e] = tmp[e];
         }
       }
       if (use_tma_out) {
@@ -546,8 +611,10 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         float2* st = reinterpret_cast<float2*>(work) + t * TB + r;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          if (h > 0 && tid == 0) bulk_wait_read();           // round 0 has left `work`
-          __syncthreads();                                   // exchange reads / round 0 are over
+          if (h > 0) {
+            if (tid == 0) bulk_wait_read();                    // round 0 has left `work`
+            __syncthreads();
+          }
 #pragma unroll
           for (int e = 0; e < 16; e++) st[e * (T2 * TB)] = v[16 * h + e];
           fence_async_smem();
@@ -561,16 +628,16 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           }
         }
       }
-      if (nxt.role >= 0 && !nxt.ready) {
-        if (nxt.role == 1 && tid == 0) pipe_wait(doneA + nxt.b, C::IA * C::NWARPS, err);
-        __syncthreads();
-        issue_load(nxt);
-      }
+      if (nxt.role >= 0 && !nxt.ready) fetch_now(nxt);
       cur = nxt;
     }
     s ^= 1;
   }
-  if (tid == 0) bulk_wait_all();                  // shared memory must outlive the last TMA store
+  __syncthreads();
+  if (tid == 0) {
+    flush_signal();
+    bulk_wait_all();                              // shared memory must outlive the last TMA store
+  }
 }
 #endif  // __CUDACC__
 

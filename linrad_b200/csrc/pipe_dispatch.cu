@@ -165,7 +165,7 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   q.tma_in = (have_map_y && env_i("LB200_PIPE_TMA_IN", 1)) ? 1 : 0;
   // ---- output by TMA tensor stores: planar targets only (one channel, or the packed spectrum of real input)
   q.tma_out = 0;
-  if (env_i("LB200_PIPE_TMA_OUT", 1) && (k.zbuf || nch == 1)) {
+  if (env_i("LB200_PIPE_TMA_OUT", 0) && (k.zbuf || nch == 1)) {   // measured: streaming stores are a little faster (profiles/r2_notes.txt)
     void* base = k.zbuf ? (void*)k.zbuf : (void*)k.out;
     const size_t planes = k.zbuf ? plan->zbuf_elems / N : ((size_t)k.out_mask + 1) / (2 * N);
     if (planes >= 1 && (k.zbuf || (k.out_pa % (2 * N)) == 0)) {

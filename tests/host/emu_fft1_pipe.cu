@@ -103,11 +103,14 @@ static int run_case()
       for (int e = 0; e < 32; e++) V(tid)[e] = in[(size_t)(t + T2 * e) * TB + r];
       pass0<T2>(V(tid));
     }
-    for (int qq = 0; qq < C::Q2; qq++) {
-      for (auto& f : work) f = make_float2(NAN, NAN);
-      if ((size_t)C::ROUND_B > work.size() * 8) { printf("round buffer too small\n"); return 1; }
-      for (int tid = 0; tid < 256; tid++) rowx_store<T2, TB>(V(tid), work.data(), tid / TB, tid & (TB - 1), qq);
-      for (int tid = 0; tid < 256; tid++) rowx_load<T2, TB>(U(tid), work.data(), tid / TB, tid & (TB - 1), qq);
+    {
+      // all rounds side by side in the (consumed) input buffer, one barrier between stores and loads
+      std::vector<float2> buf(C::IN_BYTES / 8, make_float2(NAN, NAN));
+      if ((size_t)C::Q2 * C::ROUND_B > buf.size() * 8) { printf("input buffer too small for the exchange\n"); return 1; }
+      for (int tid = 0; tid < 256; tid++)
+        for (int qq = 0; qq < C::Q2; qq++) rowx_store<T2, TB>(V(tid), buf.data() + qq * (T2 * T2 * TB), tid / TB, tid & (TB - 1), qq);
+      for (int tid = 0; tid < 256; tid++)
+        for (int qq = 0; qq < C::Q2; qq++) rowx_load<T2, TB>(U(tid), buf.data() + qq * (T2 * T2 * TB), tid / TB, tid & (TB - 1), qq);
     }
     for (int tid = 0; tid < 256; tid++) {
       const int r = tid & (TB - 1), t = tid / TB;

@@ -65,7 +65,7 @@ def _run(s, rawb, nblocks, chunk, first=0, **plan_kw):
     finally:
         plan.close()
     rows = nblocks // s.avg1num
-    return fft1[: nblocks * s.fft1_block].reshape(nblocks, -1).copy(), sumsq[: rows * s.fft1_size].reshape(rows, -1).copy()
+    return fft1[: nblocks * s.fft1_block].reshape(nblocks, s.fft1_block).copy(), sumsq[: rows * s.fft1_size].reshape(rows, s.fft1_size).copy()
 
 
 def _input(s, nblocks, seed):
@@ -82,7 +82,7 @@ FORMATS = [
 @pytest.mark.parametrize("n", [15, 16, 17, 18, 19, 20])
 def test_pipe_equals_legacy_all_sizes(n):
     s = sizing.PathSetup(input_mode=IQ_DATA, rf_channels=1, ad_speed=20000000, fft1_n=n, mix1_red_n=6)
-    nblocks = 7 if n <= 18 else 4
+    nblocks = 7 if n <= 18 else 5
     rawb = _input(s, nblocks, seed=n)
     with _Env(LB200_LARGE_LEGACY=1):
         f0, p0 = _run(s, rawb, nblocks, chunk=nblocks)
@@ -91,8 +91,9 @@ def test_pipe_equals_legacy_all_sizes(n):
     e = rel_rms(f1, f0)
     assert e <= 6e-7, f"fft1_float pipe vs legacy: rel rms {e}"
     assert np.isfinite(f1).all()
-    strong = p0 > 1e-4 * p0.max()
-    assert (np.abs(p1 - p0)[strong] <= 2e-5 * p0[strong]).all(), "fft1_sumsq pipe vs legacy"
+    if p0.size:
+        strong = p0 > 1e-4 * p0.max()
+        assert (np.abs(p1 - p0)[strong] <= 2e-5 * p0[strong]).all(), "fft1_sumsq pipe vs legacy"
 
 
 @pytest.mark.parametrize("mode,ch", FORMATS)
