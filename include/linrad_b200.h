@@ -274,6 +274,33 @@ int lb200_raw_header_parse(const void *bytes, size_t nbytes, lb200_raw_header *o
 /* bytes one block of `block_bytes` timf1 bytes occupies in the file (save_rw_bytes, buf.c:599) */
 size_t lb200_raw_block_bytes(const lb200_raw_header *h, size_t block_bytes);
 
+/* ---- multi-GPU: sum of the averaged power spectra ------------------------
+ * The hot path shards over independent receiver streams / time-block ranges, one process per
+ * GPU, with no data-path collective; what one Linrad instance's wide graph needs from all of
+ * them is the SUM of their fft1_sumsq rows (the reference sums rows of one stream in fft1_c,
+ * fft1.c:4507-4520; it has no multi-device path).  Every rank deposits its rows in the root's
+ * mailbox with the copy engine over NVLink (IPC-mapped peer memory), the root adds them with
+ * one small kernel: no collective shares the SMs with the persistent fft1 kernels.
+ *   create -> export (64-byte cudaIpcMemHandle_t) -> caller all-gathers the handles ->
+ *   connect -> per round: push on every rank, sum on the root.
+ * push/sum are queued on a side stream owned by the reducer and ordered against the plan's
+ * stream by events; nothing here synchronises with the host. */
+typedef struct lb200_reduce lb200_reduce; /* opaque */
+#define LB200_IPC_HANDLE_BYTES 64
+int lb200_reduce_create(lb200_plan *plan, int rank, int world, size_t floats, int depth, lb200_reduce **out);
+int lb200_reduce_export(lb200_reduce *r, void *handle64);
+int lb200_reduce_connect(lb200_reduce *r, const void *handles /* world x 64 bytes, by rank */, int root);
+/* every rank: its rows (device pointer, `floats` of create) for the next round */
+int lb200_reduce_push(lb200_reduce *r, const float *rows);
+/* plan's stream waits until the last pushed rows have been copied out (call before rewriting them) */
+int lb200_reduce_rows_released(lb200_reduce *r);
+/* root: out[i] = sum over ranks (in rank order) of the next round's rows */
+int lb200_reduce_sum(lb200_reduce *r, float *out);
+/* plan's stream waits for the last sum */
+int lb200_reduce_result_ready(lb200_reduce *r);
+int lb200_reduce_synchronize(lb200_reduce *r);
+void lb200_reduce_destroy(lb200_reduce *r);
+
 /* Host helpers shared by the shim and the tests (pure integer / scalar logic) */
 /* set_mix1_phases (mix1.c:781-861) for one selection and one transform; returns 0 or 1211/1212 */
 int lb200_set_mix1_phases(const lb200_config *cfg, lb200_mix1_state *s, float fq);

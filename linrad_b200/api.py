@@ -22,7 +22,10 @@ EXPORTS = ["lb200_create", "lb200_destroy", "lb200_strerror", "lb200_abi_version
            "lb200_phase_advance", "lb200_window_to_natural",
            "lb200_update_fft1_slowsum_dev", "lb200_update_fft1_slowsum", "lb200_fft1_waterfall_dev",
            "lb200_fft1_waterfall", "lb200_expand_rawdat_dev", "lb200_expand_rawdat", "lb200_widen_24bit_dev",
-           "lb200_widen_24bit", "lb200_raw_header_parse", "lb200_raw_block_bytes"]
+           "lb200_widen_24bit", "lb200_raw_header_parse", "lb200_raw_block_bytes",
+           "lb200_reduce_create", "lb200_reduce_export", "lb200_reduce_connect", "lb200_reduce_push",
+           "lb200_reduce_rows_released", "lb200_reduce_sum", "lb200_reduce_result_ready", "lb200_reduce_synchronize",
+           "lb200_reduce_destroy"]
 
 
 class Lb200Error(RuntimeError):
@@ -364,6 +367,56 @@ def widen_24bit_host(plan, pcm):
     if rc:
         raise Lb200Error(rc, "lb200_widen_24bit")
     return out
+
+
+class Reducer:
+    """lb200_reduce_*: sum of the ranks' averaged power spectra on the root (copy-engine push over
+    NVLink + one add kernel).  `exchange` is a callable that all-gathers one 64-byte handle per rank
+    (e.g. torch.distributed.all_gather_object) and returns the list ordered by rank."""
+
+    def __init__(self, plan, rank, world, floats, exchange=None, root=0, depth=2):
+        self.plan, self.rank, self.world, self.root = plan, rank, world, root
+        lib = plan.lib
+        lib.lb200_reduce_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+        for name in ("lb200_reduce_export", "lb200_reduce_push", "lb200_reduce_sum"):
+            getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p]
+        lib.lb200_reduce_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        for name in ("lb200_reduce_rows_released", "lb200_reduce_result_ready", "lb200_reduce_synchronize", "lb200_reduce_destroy"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+        lib.lb200_reduce_destroy.restype = None
+        h = C.c_void_p()
+        self._check(lib.lb200_reduce_create(plan.h, rank, world, floats, depth, C.byref(h)), "lb200_reduce_create")
+        self.h = h
+        if world > 1:
+            mine = C.create_string_buffer(64)
+            self._check(lib.lb200_reduce_export(self.h, mine), "lb200_reduce_export")
+            handles = exchange(bytes(mine.raw))
+            assert len(handles) == world and all(len(x) == 64 for x in handles)
+            self._check(lib.lb200_reduce_connect(self.h, b"".join(handles), root), "lb200_reduce_connect")
+
+    def _check(self, rc, what):
+        if rc:
+            raise Lb200Error(rc, what)
+
+    def push(self, rows_ptr):
+        self._check(self.plan.lib.lb200_reduce_push(self.h, C.c_void_p(rows_ptr)), "lb200_reduce_push")
+
+    def rows_released(self):
+        self._check(self.plan.lib.lb200_reduce_rows_released(self.h), "lb200_reduce_rows_released")
+
+    def sum(self, out_ptr):
+        self._check(self.plan.lib.lb200_reduce_sum(self.h, C.c_void_p(out_ptr)), "lb200_reduce_sum")
+
+    def result_ready(self):
+        self._check(self.plan.lib.lb200_reduce_result_ready(self.h), "lb200_reduce_result_ready")
+
+    def synchronize(self):
+        self._check(self.plan.lib.lb200_reduce_synchronize(self.h), "lb200_reduce_synchronize")
+
+    def close(self):
+        if self.h:
+            self.plan.lib.lb200_reduce_destroy(self.h)
+            self.h = None
 
 
 def new_states(selfreqs):

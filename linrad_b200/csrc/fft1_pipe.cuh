@@ -394,12 +394,13 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     issue_load(it);
   };
 
-  // thread 0 keeps one queue position in flight: the atomic's latency is never waited for
-  int pend_idx = 0;
-  if (tid == 0) {
-    items[0] = decode(atomicAdd(head, 1));       // ready = 0: fetched through fetch_now
-    pend_idx = atomicAdd(head, 1);
-  }
+  // thread 0: the queue position of the NEXT item is claimed at the top of an item and its result
+  // is only read right before the item's first CTA barrier, under the input wait and conversion.
+  // Readiness is kept as two watermarks (all transforms below a_upto have their columns in Y, all
+  // below b_upto have been read by their rows), advanced by relaxed loads that are in flight
+  // during the same time: no atomic or L2 round trip is waited for where a warp would be held up.
+  int a_upto = 0, b_upto = 0;
+  if (tid == 0) items[0] = decode(atomicAdd(head, 1));       // ready = 0: fetched through fetch_now
   __syncthreads();
   PipeItem cur = items[0];
   if (cur.role >= 0) fetch_now(cur);
@@ -408,15 +409,24 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   bool stores_pending = false;                   // thread 0: TMA stores may still be reading `work`
 
   while (cur.role >= 0) {
-    // ---- thread 0: next item, its readiness and this item's slot; loads in flight until barrier 1
-    PipeItem nx;
-    int rd = 0, sl = 0;
+    // ---- thread 0: claim and watermark loads, in flight until barrier 1
+    int nidx = 0, wa0 = 0, wa1 = 0, wb0 = 0, wb1 = 0;
     if (tid == 0) {
-      nx = decode(pend_idx);
-      pend_idx = atomicAdd(head, 1);
-      if (nx.role == 1) rd = ld_relaxed(doneA + nx.b);
-      if (cur.role == 0 && cur.b >= q.nslots) sl = ld_relaxed(doneB + (cur.b - q.nslots));
+      nidx = atomicAdd(head, 1);
+      wa0 = a_upto < nb ? ld_relaxed(doneA + a_upto) : 0;
+      wa1 = a_upto + 1 < nb ? ld_relaxed(doneA + a_upto + 1) : 0;
+      wb0 = b_upto < nb ? ld_relaxed(doneB + b_upto) : 0;
+      wb1 = b_upto + 1 < nb ? ld_relaxed(doneB + b_upto + 1) : 0;
     }
+    // thread 0, right before barrier 1: publish the next item and this item's slot state
+    auto publish = [&]() {
+      if (wa0 >= DONE_A) { a_upto++; if (wa1 >= DONE_A) a_upto++; }
+      if (wb0 >= C::IB) { b_upto++; if (wb1 >= C::IB) b_upto++; }
+      PipeItem nx = decode(nidx);
+      nx.ready = nx.role == 0 ? 1 : (nx.role == 1 && nx.b < a_upto ? 1 : 0);
+      items[s ^ 1] = nx;
+      slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || cur.b - q.nslots < b_upto) ? 1 : 0;
+    };
     const int tile = cur.j / NCH;
     const int c = cur.j - tile * NCH;
     float2 v[32];
@@ -457,9 +467,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           bulk_wait_read();
           stores_pending = false;
         }
-        nx.ready = nx.role == 0 ? 1 : (nx.role == 1 && rd >= DONE_A ? 1 : 0);
-        items[s ^ 1] = nx;
-        slot_ok[s] = (cur.b < q.nslots || sl >= C::IB) ? 1 : 0;
+        publish();
       }
       __syncthreads();                            // barrier 1: the raw tile is consumed; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
@@ -521,16 +529,11 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           bulk_wait_read();
           stores_pending = false;
         }
-        nx.ready = nx.role == 0 ? 1 : (nx.role == 1 && rd >= DONE_A ? 1 : 0);
-        items[s ^ 1] = nx;
+        publish();
       }
       __syncthreads();                            // barrier 1: the Y tile is in registers; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
-      if (tid == 0) {
-        flush_signal();
-        __threadfence();                          // this tile's share of the slot may be overwritten
-        atomicAdd(doneB + cur.b, 1);
-      }
+      if (tid == 0) atomicAdd(doneB + cur.b, 1);  // the tile is in registers: its share of the slot may be overwritten
       // ---- row transforms: one exchange through the (now free) input buffer, all rows at once
       pass0<T2>(v);
       {
@@ -545,6 +548,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         for (int e = 0; e < 32; e++) v[e] = u[e];
       }
       __syncthreads();                            // the input buffer is free again
+      if (tid == 0) flush_signal();               // (its fence sits behind the item's last barrier)
       if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
       {
         float2 wb[5];

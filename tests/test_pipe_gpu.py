@@ -81,7 +81,7 @@ FORMATS = [
 
 @pytest.mark.parametrize("n", [15, 16, 17, 18, 19, 20])
 def test_pipe_equals_legacy_all_sizes(n):
-    s = sizing.PathSetup(input_mode=IQ_DATA, rf_channels=1, ad_speed=20000000, fft1_n=n, mix1_red_n=6)
+    s = sizing.PathSetup(input_mode=IQ_DATA, rf_channels=1, ad_speed=20000000, fft1_n=n, mix1_red_n=max(6, n - 12))
     nblocks = 7 if n <= 18 else 5
     rawb = _input(s, nblocks, seed=n)
     with _Env(LB200_LARGE_LEGACY=1):
