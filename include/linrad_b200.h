@@ -236,6 +236,13 @@ int lb200_expand_rawdat(lb200_plan *plan, const void *packed, void *out, size_t 
 /* 24-bit PCM -> left-justified int32 (rxin.c:1603-1614); nsamples multiple of 4 */
 int lb200_widen_24bit_dev(lb200_plan *plan, const void *pcm24, void *out, size_t nsamples);
 int lb200_widen_24bit(lb200_plan *plan, const void *pcm24, void *out, size_t nsamples);
+/* 8-bit unsigned PCM -> int16: (byte << 8) - 32640 (rxin.c:1573-1583); nsamples multiple of 4 */
+int lb200_widen_8bit_dev(lb200_plan *plan, const void *pcm8, void *out, size_t nsamples);
+int lb200_widen_8bit(lb200_plan *plan, const void *pcm8, void *out, size_t nsamples);
+/* 32-bit float wav samples -> int32: 0x7fffffff * z truncated, out of range / NaN -> 0x80000000 like
+ * the reference's x86 conversion (rxin.c:1624-1634); nsamples multiple of 4 */
+int lb200_float_to_int32_dev(lb200_plan *plan, const void *f32, void *out, size_t nsamples);
+int lb200_float_to_int32(lb200_plan *plan, const void *f32, void *out, size_t nsamples);
 
 /* ---- Linrad .raw recordings (modesub.c:656-733 reader, 1519-1640 writer) -------------------
  * Little-endian, no padding:

@@ -23,6 +23,7 @@ EXPORTS = ["lb200_create", "lb200_destroy", "lb200_strerror", "lb200_abi_version
            "lb200_update_fft1_slowsum_dev", "lb200_update_fft1_slowsum", "lb200_fft1_waterfall_dev",
            "lb200_fft1_waterfall", "lb200_expand_rawdat_dev", "lb200_expand_rawdat", "lb200_widen_24bit_dev",
            "lb200_widen_24bit", "lb200_raw_header_parse", "lb200_raw_block_bytes",
+           "lb200_widen_8bit_dev", "lb200_widen_8bit", "lb200_float_to_int32_dev", "lb200_float_to_int32",
            "lb200_reduce_create", "lb200_reduce_export", "lb200_reduce_connect", "lb200_reduce_push",
            "lb200_reduce_rows_released", "lb200_reduce_sum", "lb200_reduce_result_ready", "lb200_reduce_synchronize",
            "lb200_reduce_destroy"]
@@ -366,6 +367,26 @@ def widen_24bit_host(plan, pcm):
     rc = plan.lib.lb200_widen_24bit(plan.h, pcm.ctypes.data, out.ctypes.data, n)
     if rc:
         raise Lb200Error(rc, "lb200_widen_24bit")
+    return out
+
+
+def widen_8bit_host(plan, pcm8):
+    """8-bit unsigned PCM -> int16 (rxin.c:1573-1583)"""
+    pcm8 = np.ascontiguousarray(pcm8, np.uint8)
+    out = np.zeros(pcm8.size, np.int16)
+    rc = plan.lib.lb200_widen_8bit(plan.h, C.c_void_p(pcm8.ctypes.data), C.c_void_p(out.ctypes.data), C.c_size_t(pcm8.size))
+    if rc:
+        raise Lb200Error(rc, "lb200_widen_8bit")
+    return out
+
+
+def float_to_int32_host(plan, z):
+    """32-bit float samples -> int32 (rxin.c:1624-1634)"""
+    z = np.ascontiguousarray(z, np.float32)
+    out = np.zeros(z.size, np.int32)
+    rc = plan.lib.lb200_float_to_int32(plan.h, C.c_void_p(z.ctypes.data), C.c_void_p(out.ctypes.data), C.c_size_t(z.size))
+    if rc:
+        raise Lb200Error(rc, "lb200_float_to_int32")
     return out
 
 

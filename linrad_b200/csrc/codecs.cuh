@@ -61,4 +61,37 @@ __global__ void __launch_bounds__(256) widen_24bit_kernel(const uint32_t* __rest
   }
 }
 
+// 8-bit unsigned PCM -> int16 (rxin.c:1573-1583): rxin_isho[j] = (rxin_char[j] << 8) - 32640,
+// stored to a short (the reference's signed-char promotion and the unsigned form agree modulo
+// 2^16).  Four samples per thread.
+__global__ void __launch_bounds__(256) widen_8bit_kernel(const uint32_t* __restrict__ in, uint2* __restrict__ out, size_t groups)
+{
+  for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < groups; g += (size_t)gridDim.x * 256) {
+    const uint32_t w = in[g];
+    const uint32_t s0 = (((w & 0xffu) << 8) - 32640u) & 0xffffu;
+    const uint32_t s1 = ((((w >> 8) & 0xffu) << 8) - 32640u) & 0xffffu;
+    const uint32_t s2 = ((((w >> 16) & 0xffu) << 8) - 32640u) & 0xffffu;
+    const uint32_t s3 = (((w >> 24) << 8) - 32640u) & 0xffffu;
+    out[g] = make_uint2(s0 | (s1 << 16), s2 | (s3 << 16));
+  }
+}
+
+// 32-bit float samples -> int32 (rxin.c:1624-1634): rxin_int[j] = 0x7fffffff * z[j], i.e. the float
+// product with (float)0x7fffffff = 2^31 truncated toward zero; what does not fit (|product| >= 2^31,
+// NaN) becomes 0x80000000, the "integer indefinite" the reference's cvttss2si returns on x86-64.
+__global__ void __launch_bounds__(256) float_to_int32_kernel(const float4* __restrict__ in, int4* __restrict__ out, size_t groups)
+{
+  for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < groups; g += (size_t)gridDim.x * 256) {
+    const float4 z = in[g];
+    const float v[4] = {z.x, z.y, z.z, z.w};
+    int r[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float t = __fmul_rn(2147483648.0f, v[i]);
+      r[i] = (t >= 2147483648.0f || t < -2147483648.0f || t != t) ? (int)0x80000000u : __float2int_rz(t);
+    }
+    out[g] = make_int4(r[0], r[1], r[2], r[3]);
+  }
+}
+
 }  // namespace lb

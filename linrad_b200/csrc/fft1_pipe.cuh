@@ -305,6 +305,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   __shared__ uint64_t bar_in;
   __shared__ PipeItem items[2];
   __shared__ int slot_ok[2];
+  __shared__ int a_arrived;                      // warps of this CTA that have stored their columns of the current item
   const Fft1K& p = q.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int* const head = q.sync;
@@ -318,6 +319,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   for (int i = tid; i < T1 * 5; i += 256) wbt[i] = q.Wn1[(i / 5) << (i % 5)];
   for (int i = tid; i < T2 * 5; i += 256) wbt[T1 * 5 + i] = q.Wn2[(i / 5) << (i % 5)];
   if (tid == 0) {
+    a_arrived = 0;
     mbar_init(&bar_in, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -373,33 +375,19 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
     }
   };
-  // thread 0: completion of a column item is published once per CTA, after a CTA barrier that all
-  // warps reach behind their Y stores (one fence per item instead of one per warp)
-  int pend_sig = -1;
-  auto flush_signal = [&]() {
-    if (pend_sig >= 0) {
-      __threadfence();
-      atomicAdd(doneA + pend_sig, C::NWARPS);
-      pend_sig = -1;
-    }
-  };
-  // an item whose input could not be prefetched: publish, wait for its producer, fetch
+  // an item whose input could not be prefetched: wait for its producer, fetch
   auto fetch_now = [&](const PipeItem& it) {
-    __syncthreads();                             // every warp is behind its stores of the item before
-    if (tid == 0) {
-      flush_signal();                            // ... which the awaited producer count may include
-      if (it.role == 1) pipe_wait(doneA + it.b, DONE_A, err);
-    }
-    __syncthreads();
+    if (tid == 0 && it.role == 1) pipe_wait(doneA + it.b, DONE_A, err);
+    __syncthreads();                             // (also: every warp has left the input buffer)
     issue_load(it);
   };
 
   // thread 0: the queue position of the NEXT item is claimed at the top of an item and its result
   // is only read right before the item's first CTA barrier, under the input wait and conversion.
-  // Readiness is kept as two watermarks (all transforms below a_upto have their columns in Y, all
-  // below b_upto have been read by their rows), advanced by relaxed loads that are in flight
-  // during the same time: no atomic or L2 round trip is waited for where a warp would be held up.
-  int a_upto = 0, b_upto = 0;
+  // Readiness of row items is kept as a watermark (all transforms below a_upto have their columns
+  // in Y), advanced by relaxed loads that are in flight during the same time: no atomic or L2
+  // round trip is waited for where a warp would be held up.
+  int a_upto = 0;
   if (tid == 0) items[0] = decode(atomicAdd(head, 1));       // ready = 0: fetched through fetch_now
   __syncthreads();
   PipeItem cur = items[0];
@@ -409,23 +397,26 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   bool stores_pending = false;                   // thread 0: TMA stores may still be reading `work`
 
   while (cur.role >= 0) {
-    // ---- thread 0: claim and watermark loads, in flight until barrier 1
-    int nidx = 0, wa0 = 0, wa1 = 0, wb0 = 0, wb1 = 0;
+    // ---- thread 0: claim, watermark probes and this item's slot counter, in flight until barrier 1
+    constexpr int NPROBE = 6;
+    int nidx = 0, wa[NPROBE], slot_cnt = 0;
     if (tid == 0) {
       nidx = atomicAdd(head, 1);
-      wa0 = a_upto < nb ? ld_relaxed(doneA + a_upto) : 0;
-      wa1 = a_upto + 1 < nb ? ld_relaxed(doneA + a_upto + 1) : 0;
-      wb0 = b_upto < nb ? ld_relaxed(doneB + b_upto) : 0;
-      wb1 = b_upto + 1 < nb ? ld_relaxed(doneB + b_upto + 1) : 0;
+#pragma unroll
+      for (int i = 0; i < NPROBE; i++) wa[i] = a_upto + i < nb ? ld_relaxed(doneA + a_upto + i) : 0;
+      if (cur.role == 0 && cur.b >= q.nslots) slot_cnt = ld_relaxed(doneB + (cur.b - q.nslots));
     }
     // thread 0, right before barrier 1: publish the next item and this item's slot state
     auto publish = [&]() {
-      if (wa0 >= DONE_A) { a_upto++; if (wa1 >= DONE_A) a_upto++; }
-      if (wb0 >= C::IB) { b_upto++; if (wb1 >= C::IB) b_upto++; }
+      int na = 0;
+#pragma unroll
+      for (int i = 0; i < NPROBE; i++)
+        if (na == i && wa[i] >= DONE_A) na++;
+      a_upto += na;
       PipeItem nx = decode(nidx);
       nx.ready = nx.role == 0 ? 1 : (nx.role == 1 && nx.b < a_upto ? 1 : 0);
       items[s ^ 1] = nx;
-      slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || cur.b - q.nslots < b_upto) ? 1 : 0;
+      slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || slot_cnt >= C::IB) ? 1 : 0;
     };
     const int tile = cur.j / NCH;
     const int c = cur.j - tile * NCH;
@@ -472,7 +463,6 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       __syncthreads();                            // barrier 1: the raw tile is consumed; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
       const int my_slot_ok = slot_ok[s];
-      if (tid == 0) flush_signal();               // the item before this one is in Y
       if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
       // inter-step twiddle W_N^(n2*(t+T1*e)) = base * step^e, step given by exact binary powers
       const float2 tw_base = __ldg(q.Wbig + n2 * t);
@@ -511,7 +501,19 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
 #pragma unroll
         for (int e = 0; e < 32; e++) st_global(Yp + e * T1, v[e]);
       }
-      if (tid == 0) pend_sig = cur.b;             // published behind the next CTA barrier
+      // completion: the last warp to get here publishes the item for all eight (release through the
+      // shared counter, one gpu-scope fence per item; nobody waits)
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        const int old = atomicAdd(&a_arrived, 1);
+        __threadfence_block();
+        if (old == C::NWARPS - 1) {
+          a_arrived = 0;
+          __threadfence();
+          atomicAdd(doneA + cur.b, C::NWARPS);
+        }
+      }
       if (nxt.role >= 0 && !nxt.ready) fetch_now(nxt);
       cur = nxt;
     } else {
@@ -548,7 +550,6 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         for (int e = 0; e < 32; e++) v[e] = u[e];
       }
       __syncthreads();                            // the input buffer is free again
-      if (tid == 0) flush_signal();               // (its fence sits behind the item's last barrier)
       if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
       {
         float2 wb[5];
@@ -637,11 +638,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     }
     s ^= 1;
   }
-  __syncthreads();
-  if (tid == 0) {
-    flush_signal();
-    bulk_wait_all();                              // shared memory must outlive the last TMA store
-  }
+  if (tid == 0) bulk_wait_all();                  // shared memory must outlive the last TMA store
 }
 #endif  // __CUDACC__
 

@@ -262,14 +262,46 @@ extern "C" int lb200_widen_24bit_dev(lb200_plan* plan, const void* pcm24, void* 
   return LB200_OK;
 }
 
+extern "C" int lb200_widen_8bit_dev(lb200_plan* plan, const void* pcm8, void* out, size_t nsamples)
+{
+  if (!plan || !pcm8 || !out || (nsamples & 3)) return LB200_ERR_BAD_ARG;
+  if (nsamples == 0) return LB200_OK;
+  cudaSetDevice(plan->device);
+  const size_t groups = nsamples / 4;
+  int grid = (int)((groups + 255) / 256);
+  if (grid > plan->sm_count * 16) grid = plan->sm_count * 16;
+  widen_8bit_kernel<<<grid, 256, 0, plan->stream>>>((const uint32_t*)pcm8, (uint2*)out, groups);
+  LB_CUDA(cudaGetLastError());
+  plan->launches++;
+  return LB200_OK;
+}
+
+extern "C" int lb200_float_to_int32_dev(lb200_plan* plan, const void* f32, void* out, size_t nsamples)
+{
+  if (!plan || !f32 || !out || (nsamples & 3)) return LB200_ERR_BAD_ARG;
+  if (nsamples == 0) return LB200_OK;
+  cudaSetDevice(plan->device);
+  const size_t groups = nsamples / 4;
+  int grid = (int)((groups + 255) / 256);
+  if (grid > plan->sm_count * 16) grid = plan->sm_count * 16;
+  float_to_int32_kernel<<<grid, 256, 0, plan->stream>>>((const float4*)f32, (int4*)out, groups);
+  LB_CUDA(cudaGetLastError());
+  plan->launches++;
+  return LB200_OK;
+}
+
 static int codec_host(lb200_plan* plan, const void* in, size_t in_bytes, void* out, size_t out_bytes, int which, size_t count)
 {
   int rc;
   if ((rc = wg_mirror(plan, plan->m_codec_in, in_bytes))) return rc;
   if ((rc = wg_mirror(plan, plan->m_codec_out, out_bytes))) return rc;
   if ((rc = wg_copy(plan, plan->m_codec_in.d, in, in_bytes, true))) return rc;
-  rc = which == 0 ? lb200_expand_rawdat_dev(plan, plan->m_codec_in.d, plan->m_codec_out.d, count)
-                  : lb200_widen_24bit_dev(plan, plan->m_codec_in.d, plan->m_codec_out.d, count);
+  switch (which) {
+    case 0: rc = lb200_expand_rawdat_dev(plan, plan->m_codec_in.d, plan->m_codec_out.d, count); break;
+    case 1: rc = lb200_widen_24bit_dev(plan, plan->m_codec_in.d, plan->m_codec_out.d, count); break;
+    case 2: rc = lb200_widen_8bit_dev(plan, plan->m_codec_in.d, plan->m_codec_out.d, count); break;
+    default: rc = lb200_float_to_int32_dev(plan, plan->m_codec_in.d, plan->m_codec_out.d, count); break;
+  }
   if (rc) return rc;
   if ((rc = wg_copy(plan, out, plan->m_codec_out.d, out_bytes, false))) return rc;
   LB_CUDA(cudaStreamSynchronize(plan->stream));
@@ -290,4 +322,20 @@ extern "C" int lb200_widen_24bit(lb200_plan* plan, const void* pcm24, void* out,
   if (nsamples == 0) return LB200_OK;
   cudaSetDevice(plan->device);
   return codec_host(plan, pcm24, nsamples * 3, out, nsamples * 4, 1, nsamples);
+}
+
+extern "C" int lb200_widen_8bit(lb200_plan* plan, const void* pcm8, void* out, size_t nsamples)
+{
+  if (!plan || !pcm8 || !out || (nsamples & 3)) return LB200_ERR_BAD_ARG;
+  if (nsamples == 0) return LB200_OK;
+  cudaSetDevice(plan->device);
+  return codec_host(plan, pcm8, nsamples, out, nsamples * 2, 2, nsamples);
+}
+
+extern "C" int lb200_float_to_int32(lb200_plan* plan, const void* f32, void* out, size_t nsamples)
+{
+  if (!plan || !f32 || !out || (nsamples & 3)) return LB200_ERR_BAD_ARG;
+  if (nsamples == 0) return LB200_OK;
+  cudaSetDevice(plan->device);
+  return codec_host(plan, f32, nsamples * 4, out, nsamples * 4, 3, nsamples);
 }

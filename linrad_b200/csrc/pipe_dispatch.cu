@@ -108,9 +108,9 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   // About 2 items per resident CTA are in flight (the one computed and the one prefetched).
   const int resident = plan->sm_count * 2;
   const int per_phase = IA + IB;
-  int lag = env_i("LB200_PIPE_LAG", (2 * resident + per_phase - 1) / per_phase + 1);
+  int lag = env_i("LB200_PIPE_LAG", (2 * resident + per_phase - 1) / per_phase + 2);
   if (lag < 1) lag = 1;
-  int slots = env_i("LB200_PIPE_SLOTS", 2 * lag);
+  int slots = env_i("LB200_PIPE_SLOTS", lag + (resident + per_phase - 1) / per_phase + 3);
   if (slots < lag + 1) slots = lag + 1;
   if (slots > nb) slots = nb;                                  // a short call never wraps the ring
   if (slots < 1) slots = 1;
@@ -120,7 +120,7 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
     plan->pipe_slots = 0;
     // allocate the steady-state depth at once so that the map is not rebuilt call after call
     int want = slots;
-    const int full = 2 * ((2 * resident + per_phase - 1) / per_phase + 1);
+    const int full = (2 * resident + per_phase - 1) / per_phase + 2 + (resident + per_phase - 1) / per_phase + 3;
     if (want < full && !getenv("LB200_PIPE_SLOTS")) want = full;
     e = cudaMalloc((void**)&plan->d_pipe_y, (size_t)want * nch * N * sizeof(float2));
     if (e != cudaSuccess) return e;

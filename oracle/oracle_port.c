@@ -59,6 +59,29 @@ void port_widen_24bit(const uint8_t *in, int32_t *out, size_t nsamples)
   }
 }
 
+/* 8-bit PCM widening of rx_file_input, rxin.c:1573-1583, with the reference's own types
+ * (rxin_char is a plain char pointer, rxin_isho a short pointer, fft1def.h:143-145):
+ *   rxin_isho[j]=(rxin_char[j]<<8)-32640; */
+void port_widen_8bit(const char *rxin_char, short int *rxin_isho, size_t nsamples)
+{
+  size_t j = nsamples;
+  while (j > 0) {
+    j--;
+    rxin_isho[j] = (short int)((rxin_char[j] << 8) - 32640);
+  }
+}
+
+/* float wav samples, rxin.c:1624-1634:  rxin_int[j]=0x7fffffff*z[j];  (int * float -> float,
+ * converted back with the host's truncating conversion; out of range gives 0x80000000 on x86-64) */
+void port_float_to_int32(const float *z, int *rxin_int, size_t nsamples)
+{
+  size_t j = nsamples;
+  while (j > 0) {
+    j--;
+    rxin_int[j] = 0x7fffffff * z[j];
+  }
+}
+
 /* the running single-precision phase sum of do_mix1 (mix1.c:146-153,172-186), literally */
 float port_phase_chain(float phase, float rot, int count, float *trace)
 {

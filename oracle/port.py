@@ -35,6 +35,8 @@ def clib():
         _lib.port_expand_rawdat.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.port_compress_rawdat.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.port_widen_24bit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.port_widen_8bit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.port_float_to_int32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.port_phase_chain.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p]
         _lib.port_phase_chain.restype = C.c_float
     return _lib
@@ -67,6 +69,22 @@ def compress_rawdat(words):
     words = np.ascontiguousarray(words, np.int32)
     out = np.zeros(words.size // 4 * 9, np.uint8)
     clib().port_compress_rawdat(words.ctypes.data, out.ctypes.data, words.nbytes)
+    return out
+
+
+def widen_8bit(b):
+    """rxin.c:1573-1583."""
+    b = np.ascontiguousarray(b, np.uint8)
+    out = np.zeros(b.size, np.int16)
+    clib().port_widen_8bit(b.ctypes.data, out.ctypes.data, out.size)
+    return out
+
+
+def float_to_int32(z):
+    """rxin.c:1624-1634 (the host's own float -> int conversion, i.e. the reference's on x86-64)."""
+    z = np.ascontiguousarray(z, np.float32)
+    out = np.zeros(z.size, np.int32)
+    clib().port_float_to_int32(z.ctypes.data, out.ctypes.data, out.size)
     return out
 
 

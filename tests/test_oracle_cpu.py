@@ -133,6 +133,22 @@ def test_rawdat_round_trip():
     assert np.array_equal(port.expand_rawdat(packed, 40)[:8], back[:8])
 
 
+def test_widen_8bit_known_answers():
+    """rxin.c:1573-1583: (0,255) -> (-32640, 32640), hand-computed"""
+    b = np.array([0, 1, 127, 128, 254, 255], np.uint8)
+    assert list(port.widen_8bit(b)) == [-32640, -32384, -128, 128, 32384, 32640]
+    allb = np.arange(256, dtype=np.uint8)
+    assert np.array_equal(port.widen_8bit(allb), (allb.astype(np.int32) * 256 - 32640).astype(np.int16))
+
+
+def test_float_to_int32_known_answers():
+    """rxin.c:1624-1634: 0x7fffffff*z through float; full scale and beyond become 0x80000000"""
+    z = np.array([0.0, 0.5, -0.5, 0.25, 1.0, -1.0, 2.0, -3.0, 1e-10, 0.99999994, np.nan, np.inf, -np.inf], np.float32)
+    got = port.float_to_int32(z)
+    want = [0, 2 ** 30, -2 ** 30, 2 ** 29, -2 ** 31, -2 ** 31, -2 ** 31, -2 ** 31, 0, 2147483520, -2 ** 31, -2 ** 31, -2 ** 31]
+    assert list(got) == want
+
+
 def test_widen_24bit():
     b = np.array([0x01, 0x02, 0x03, 0xff, 0xff, 0xff, 0x00, 0x00, 0x80], np.uint8)
     assert list(port.widen_24bit(b)) == [0x03020100, -256, -2**31]

@@ -93,7 +93,7 @@ def test_pipe_equals_legacy_all_sizes(n):
     assert np.isfinite(f1).all()
     if p0.size:
         strong = p0 > 1e-4 * p0.max()
-        assert (np.abs(p1 - p0)[strong] <= 2e-5 * p0[strong]).all(), "fft1_sumsq pipe vs legacy"
+        assert (np.abs(p1 - p0)[strong] <= 5e-5 * p0[strong] + 2e-6 * p0.max()).all(), "fft1_sumsq pipe vs legacy"
 
 
 @pytest.mark.parametrize("mode,ch", FORMATS)
@@ -109,7 +109,7 @@ def test_pipe_equals_legacy_formats(mode, ch, n):
     e = rel_rms(f1, f0)
     assert e <= 6e-7, f"fft1_float pipe vs legacy: rel rms {e}"
     strong = p0 > 1e-4 * p0.max()
-    assert (np.abs(p1 - p0)[strong] <= 2e-5 * p0[strong]).all()
+    assert (np.abs(p1 - p0)[strong] <= 5e-5 * p0[strong] + 2e-6 * p0.max()).all()
 
 
 @pytest.mark.parametrize("direction,first_x,xpoints", [(-1, 0, 0), (1, 3000, 20000), (-1, 700, 9000)])
@@ -127,7 +127,7 @@ def test_pipe_equals_legacy_direction_and_range(direction, first_x, xpoints):
     # bins outside the display range keep the raw fft1_b scale: compare on the common energy
     assert rel_rms(f1, f0) <= 6e-7
     strong = p0 > 1e-4 * p0.max()
-    assert (np.abs(p1 - p0)[strong] <= 2e-5 * p0[strong]).all()
+    assert (np.abs(p1 - p0)[strong] <= 5e-5 * p0[strong] + 2e-6 * p0.max()).all()
     assert np.array_equal(p1 == 0, p0 == 0), "bins outside the range must stay untouched in both"
 
 

@@ -134,6 +134,25 @@ def test_widen_24bit_bit_exact():
         plan.close()
 
 
+def test_widen_8bit_and_float_bit_exact():
+    """the other two file formats of rx_file_input (rxin.c:1573-1583, 1624-1634) against the C restatement
+    run on the host CPU (whose float -> int conversion is the reference's)"""
+    s = sizing.PathSetup(input_mode=IQ_DATA, rf_channels=1, ad_speed=96000, fft1_n=10, mix1_red_n=3)
+    plan = api.Plan(s)
+    try:
+        rng = np.random.default_rng(16)
+        allb = np.arange(256, dtype=np.uint8)
+        assert np.array_equal(api.widen_8bit_host(plan, allb), port.widen_8bit(allb))
+        for n in (4, 4096, 4 * 3333):
+            pcm = rng.integers(0, 256, n, dtype=np.uint8)
+            assert np.array_equal(api.widen_8bit_host(plan, pcm), port.widen_8bit(pcm))
+            z = rng.uniform(-1.2, 1.2, n).astype(np.float32)
+            z[::97] = np.array([1.0, -1.0, np.nan, np.inf, -np.inf, 0.99999994, -0.99999994, 1e-12], np.float32)[np.arange(z[::97].size) % 8]
+            assert np.array_equal(api.float_to_int32_host(plan, z), port.float_to_int32(z))
+    finally:
+        plan.close()
+
+
 def test_playback_chain_18bit_to_spectrum():
     """the playback front end end to end: 18-bit packed .raw payload -> expand_rawdat (GPU) ->
     timf1 -> fft1; equals fft1 of the oracle-expanded samples bit for bit"""
