@@ -351,19 +351,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     } else {
       const int c = it.j - tile * NCH;
       const int plane = slot_of(it.b) * NCH + c;
-      if (q.tma_in) {
-        if (tid == 0) {
-          // Y was written through the generic proxy (other SMs, seen complete through doneA): order
-          // it before the TMA unit's reads
-          asm volatile("fence.proxy.async;" ::: "memory");
-          mbar_expect_tx(&bar_in, 65536u);
-#pragma unroll
-          for (int bx = 0; bx < N2 / C::BOX_IN; bx++)
-            tma_load_3d(in + bx * (C::BOX_IN * TB * 8), &mapY, 2 * tile * TB, bx * C::BOX_IN, plane, &bar_in);
-        } else {
-          mbar_arrive(&bar_in);
-        }
-      } else {
+      {                                          // rows by cp.async (TMA loads: issue_b_tma, thread 0 alone)
         constexpr int CPR = TB * 8 / 16;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(q.Y + (size_t)plane * N + (size_t)tile * TB);
 #pragma unroll 4
@@ -375,46 +363,87 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
     }
   };
-  // an item whose input could not be prefetched: wait for its producer, fetch
-  auto fetch_now = [&](const PipeItem& it) {
-    if (tid == 0 && it.role == 1) pipe_wait(doneA + it.b, DONE_A, err);
-    __syncthreads();                             // (also: every warp has left the input buffer)
-    issue_load(it);
+  // Row items fetched by TMA need only thread 0: the others arrive on the barrier at the prefetch
+  // point whatever happens; thread 0 arrives (with the byte count) when the columns are complete --
+  // at the prefetch point if they already are, else at the end of the current item after waiting.
+  // Nobody else waits for that decision; they meet the data at the next item's input barrier.
+  // (cp.async fallback and column items: all threads copy, the decision is CTA-uniform.)
+  auto issue_b_tma = [&](const PipeItem& it) {      // thread 0
+    const int tile = it.j / NCH;
+    const int plane = slot_of(it.b) * NCH + (it.j - tile * NCH);
+    asm volatile("fence.proxy.async;" ::: "memory");
+    mbar_expect_tx(&bar_in, 65536u);
+#pragma unroll
+    for (int bx = 0; bx < N2 / C::BOX_IN; bx++)
+      tma_load_3d(in + bx * (C::BOX_IN * TB * 8), &mapY, 2 * tile * TB, bx * C::BOX_IN, plane, &bar_in);
+  };
+  bool b_pending = false;                        // thread 0: a row item's TMA load is still to be issued
+  int rd_next = 0;                               // thread 0: doneA of the next row item (exact, relaxed load)
+  // prefetch point: the input buffer is free, `nxt` is known to everybody
+  auto prefetch = [&](const PipeItem& it) {
+    if (it.role < 0) return;
+    if (it.role == 1 && q.tma_in) {
+      if (tid == 0) {
+        if (rd_next >= DONE_A) issue_b_tma(it);
+        else b_pending = true;
+      } else {
+        mbar_arrive(&bar_in);
+      }
+    } else if (it.ready) {
+      issue_load(it);
+    }
+  };
+  // end of an item: whatever of the next item's input could not be fetched at the prefetch point
+  auto fetch_rest = [&](const PipeItem& it) {
+    if (it.role < 0) return;
+    if (it.role == 1 && q.tma_in) {
+      if (tid == 0 && b_pending) {
+        pipe_wait(doneA + it.b, DONE_A, err);
+        issue_b_tma(it);
+        b_pending = false;
+      }
+    } else if (!it.ready) {
+      if (tid == 0 && it.role == 1) pipe_wait(doneA + it.b, DONE_A, err);
+      __syncthreads();
+      issue_load(it);
+    }
   };
 
   // thread 0: the queue position of the NEXT item is claimed at the top of an item and its result
-  // is only read right before the item's first CTA barrier, under the input wait and conversion.
-  // Readiness of row items is kept as a watermark (all transforms below a_upto have their columns
-  // in Y), advanced by relaxed loads that are in flight during the same time: no atomic or L2
-  // round trip is waited for where a warp would be held up.
-  int a_upto = 0;
-  if (tid == 0) items[0] = decode(atomicAdd(head, 1));       // ready = 0: fetched through fetch_now
+  // is only read right before the item's first CTA barrier, under the input wait and conversion;
+  // the exact readiness load of a row item is issued there and read at the prefetch point.  No
+  // atomic or L2 round trip is waited for where a warp would be held up.
+  if (tid == 0) items[0] = decode(atomicAdd(head, 1));       // ready = 0
   __syncthreads();
   PipeItem cur = items[0];
-  if (cur.role >= 0) fetch_now(cur);
+  if (cur.role == 1 && q.tma_in) {
+    if (tid == 0) { b_pending = true; } else { mbar_arrive(&bar_in); }
+  }
+  fetch_rest(cur);
   uint32_t par = 0;
   int s = 0;
   bool stores_pending = false;                   // thread 0: TMA stores may still be reading `work`
 
   while (cur.role >= 0) {
-    // ---- thread 0: claim, watermark probes and this item's slot counter, in flight until barrier 1
-    constexpr int NPROBE = 6;
-    int nidx = 0, wa[NPROBE], slot_cnt = 0;
+    // ---- thread 0: claim and this item's slot counter, in flight until barrier 1
+    int nidx = 0, slot_cnt = 0;
     if (tid == 0) {
       nidx = atomicAdd(head, 1);
-#pragma unroll
-      for (int i = 0; i < NPROBE; i++) wa[i] = a_upto + i < nb ? ld_relaxed(doneA + a_upto + i) : 0;
       if (cur.role == 0 && cur.b >= q.nslots) slot_cnt = ld_relaxed(doneB + (cur.b - q.nslots));
     }
     // thread 0, right before barrier 1: publish the next item and this item's slot state
     auto publish = [&]() {
-      int na = 0;
-#pragma unroll
-      for (int i = 0; i < NPROBE; i++)
-        if (na == i && wa[i] >= DONE_A) na++;
-      a_upto += na;
       PipeItem nx = decode(nidx);
-      nx.ready = nx.role == 0 ? 1 : (nx.role == 1 && nx.b < a_upto ? 1 : 0);
+      if (nx.role == 1) {
+        if (q.tma_in) {
+          rd_next = ld_relaxed(doneA + nx.b);     // read at the prefetch point
+          nx.ready = 0;
+        } else {
+          nx.ready = ld_relaxed(doneA + nx.b) >= DONE_A ? 1 : 0;
+        }
+      } else {
+        nx.ready = nx.role == 0 ? 1 : 0;
+      }
       items[s ^ 1] = nx;
       slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || slot_cnt >= C::IB) ? 1 : 0;
     };
@@ -463,7 +492,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       __syncthreads();                            // barrier 1: the raw tile is consumed; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
       const int my_slot_ok = slot_ok[s];
-      if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
+      prefetch(nxt);
       // inter-step twiddle W_N^(n2*(t+T1*e)) = base * step^e, step given by exact binary powers
       const float2 tw_base = __ldg(q.Wbig + n2 * t);
       float2 tw_sb[5];
@@ -514,7 +543,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           atomicAdd(doneA + cur.b, C::NWARPS);
         }
       }
-      if (nxt.role >= 0 && !nxt.ready) fetch_now(nxt);
+      fetch_rest(nxt);
       cur = nxt;
     } else {
       // =============================== role B: TB rows of transform cur.b ======================
@@ -550,7 +579,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         for (int e = 0; e < 32; e++) v[e] = u[e];
       }
       __syncthreads();                            // the input buffer is free again
-      if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
+      prefetch(nxt);
       {
         float2 wb[5];
 #pragma unroll
@@ -633,7 +662,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           }
         }
       }
-      if (nxt.role >= 0 && !nxt.ready) fetch_now(nxt);
+      fetch_rest(nxt);
       cur = nxt;
     }
     s ^= 1;

@@ -127,3 +127,38 @@ class CudaStream:
 
     def close(self):
         self.plan.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Parity report: every comparison against the reference also records its PLAIN figures (no noise
+# floor allowance), so that the widened tolerances of the tests can be judged:
+#   worst_plain  = max over bins of |got - ref| / (1e-4 * ref)      (north_star bound = 1.0)
+#   frac_over    = fraction of bins with |got - ref| > 1e-4 * ref
+# and, where the reference has two float versions for the set-up (fft_cntrl rows 6 and 7), the same
+# two figures between the reference's OWN versions on the same input.
+# Lines go to $LB200_PARITY_REPORT (default gpurun_out/parity_report.jsonl when that directory exists).
+def power_plain_figures(got, ref, tol=1e-4):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    ok = ref > 0
+    if not ok.any():
+        return 0.0, 0.0
+    r = np.abs(got - ref)[ok] / (tol * ref[ok])
+    return float(r.max()), float((r > 1.0).mean())
+
+
+def parity_record(**fields):
+    import json
+    import os
+    path = os.environ.get("LB200_PARITY_REPORT")
+    if not path:
+        d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        if not os.path.isdir(d):
+            return
+        path = os.path.join(d, "parity_report.jsonl")
+    fields["test"] = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    try:
+        with open(path, "a") as f:
+            f.write(json.dumps(fields) + "\n")
+    except OSError:
+        pass

@@ -8,7 +8,8 @@ import pytest
 from linrad_b200 import sizing
 from linrad_b200.synth import make_timf1
 from oracle import refwrap
-from tests.helpers import CONFIGS, CudaStream, rel_rms, run_reference, IQ_DATA, DWORD_INPUT, TWO_CHANNELS
+from tests.helpers import (CONFIGS, CudaStream, rel_rms, run_reference, IQ_DATA, DWORD_INPUT, TWO_CHANNELS,
+                           power_plain_figures, parity_record)
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refwrap.available(), reason="oracle/_ref not built")]
 
@@ -89,6 +90,32 @@ def _compare(kw, nblocks, selbins, chunk, seed=1, ext=None, power_slack=1.0, **o
         # fft1_sumsq: every completed row, per bin; index bookkeeping bit-exact
         rows = (nblocks // s.avg1num)
         assert cs.sumsq_pa == ref["sumsq_pa"] and cs.sumsq_counter == ref["sumsq_counter"]
+        # the reference's own spread on the same input: the other float version (rows 6 / 7 of
+        # fft_cntrl exist for one-channel IQ up to 65536 points), recorded next to our figures
+        ref2 = None
+        if kwr.get("version") in (6, 7) and s.rf_channels == 1 and (s.input_mode & IQ_DATA) and not ext and rows > 0:
+            try:
+                ref2 = run_reference(dict(kwr, version=13 - kwr["version"]), raw, [], nblocks)
+            except Exception:
+                ref2 = None
+        rep = dict(kind="fft1_sumsq", fft1_n=s.fft1_n, mode=s.input_mode, rows=min(rows, 8), fft1_rel_rms=e, worst_allow=0.0,
+                   worst_plain=0.0, frac_over_plain=0.0, ref_spread_worst_plain=None, ref_spread_frac_over=None, ref_spread_worst_allow=None)
+        for r in range(min(rows, 8)):
+            a = cs.sumsq[r * N + lo: r * N + hi + 1]
+            b = ref["sumsq"][r * N + lo: r * N + hi + 1]
+            ok, worst = power_ok(a, b, s.avg1num)
+            wp, fo = power_plain_figures(a, b, TOL_POWER)
+            rep["worst_allow"] = max(rep["worst_allow"], worst)
+            rep["worst_plain"] = max(rep["worst_plain"], wp)
+            rep["frac_over_plain"] = max(rep["frac_over_plain"], fo)
+            if ref2 is not None:
+                b2 = ref2["sumsq"][r * N + lo: r * N + hi + 1]
+                wp2, fo2 = power_plain_figures(b2, b, TOL_POWER)
+                rep["ref_spread_worst_plain"] = max(rep["ref_spread_worst_plain"] or 0.0, wp2)
+                rep["ref_spread_frac_over"] = max(rep["ref_spread_frac_over"] or 0.0, fo2)
+                rep["ref_spread_worst_allow"] = max(rep["ref_spread_worst_allow"] or 0.0, power_ok(b2, b, s.avg1num)[1])
+        parity_record(**rep)
+        print("parity:", rep)
         for r in range(min(rows, 8)):
             a = cs.sumsq[r * N + lo: r * N + hi + 1]
             b = ref["sumsq"][r * N + lo: r * N + hi + 1]

@@ -126,9 +126,13 @@ def test_pipe_equals_legacy_direction_and_range(direction, first_x, xpoints):
         f1, p1 = _run(s, rawb, nblocks, chunk=5)
     # bins outside the display range keep the raw fft1_b scale: compare on the common energy
     assert rel_rms(f1, f0) <= 6e-7
-    strong = p0 > 1e-4 * p0.max()
-    assert (np.abs(p1 - p0)[strong] <= 5e-5 * p0[strong] + 2e-6 * p0.max()).all()
     assert np.array_equal(p1 == 0, p0 == 0), "bins outside the range must stay untouched in both"
+    strong = p0 > 1e-4 * p0.max()
+    bad = np.abs(p1 - p0) > 5e-5 * p0 + 2e-6 * p0.max()
+    bad &= strong
+    where = np.argwhere(bad)[:8]
+    assert not bad.any(), ("fft1_sumsq pipe vs legacy", bad.sum(), where.tolist(), [(float(p0[tuple(w)]), float(p1[tuple(w)])) for w in where],
+                           s.fft1_first_point, s.fft1_last_point)
 
 
 VARIANTS = [

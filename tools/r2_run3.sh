@@ -2,7 +2,7 @@
 # round 2: pipeline iteration -- pipe tests, A/B bench lines at configs[3], ncu of the pipe and mix1 kernels
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out
-T=${TAG:-r2d}
+T=${TAG:-r2e}
 timeout 900 python -m pytest tests/test_pipe_gpu.py tests/test_wide_graph_gpu.py -x -q > $O/${T}_pipe_tests.log 2>&1
 echo "pipe tests rc=$?" >> $O/${T}_pipe_tests.log
 tail -3 $O/${T}_pipe_tests.log
