@@ -14,6 +14,10 @@
  *           library stages them through its own device mirrors (H2D/D2H inside the call).
  * All calls on one plan are serialised on the plan's CUDA stream; different plans are
  * independent (one plan per fft1b worker thread, like the cuFFT handles of wcw.c:552-576).
+ * A plan is NOT re-entrant: it must not be entered from two host threads at the same time (its
+ * mirrors, event pool and counters are unguarded).  A host that drives one plan from two threads
+ * -- Linrad's wideband thread calls fft1_b while the narrowband thread calls fft1_mix1_fixed --
+ * takes a lock per plan around every entry, as lb200_shim.c does.
  *
  * Return value: 0 on success, else an LB200_ERR_* code.  The shim forwards non-zero codes
  * to lirerr() (lxsys.c:495); texts for errors.lir are listed in INTEGRATION.md.

@@ -49,6 +49,7 @@ struct Fft1PipeK {
   int tma_in;            // role B input by TMA tensor load (else cp.async)
   int tma_out;           // role B output by TMA tensor store (one channel / zbuf only; else streaming stores)
   int prefetch_ahead;    // L2 prefetch distance in transforms (0 = off)
+  int stats;             // debug: accumulate wait statistics behind the completion counters
   uint32_t out_blk0;     // tma_out: index of the call's first output block in the tensor map's outermost dimension
   uint32_t out_nblk;     // ... and the extent of that dimension (ring wrap)
 };
@@ -304,16 +305,28 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   float2* const wbt = reinterpret_cast<float2*>(smem_raw + C::IN_BYTES + C::WORK_BYTES);
   __shared__ uint64_t bar_in;
   __shared__ PipeItem items[2];
+  __shared__ PipeItem stash_sm;                  // an item taken but not runnable yet (run after a detour)
   __shared__ int slot_ok[2];
   __shared__ int a_arrived;                      // warps of this CTA that have stored their columns of the current item
   const Fft1K& p = q.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int* const head = q.sync;
+  // sync block: [0] column-queue head, [1] error flag, [2] row-queue head, [3] a_mark (all transforms
+  // below it have their columns in Y), [4] b_mark (all below it have been read by their rows),
+  // [8 ..) doneA[nblocks], doneB[nblocks], then 8 debug counters
+  int* const headA = q.sync;
   int* const err = q.sync + 1;
-  int* const doneA = q.sync + 2;
-  int* const doneB = q.sync + 2 + p.nblocks;
+  int* const headB = q.sync + 2;
+  int* const a_mark = q.sync + 3;
+  int* const b_mark = q.sync + 4;
+  int* const doneA = q.sync + 8;
+  int* const doneB = q.sync + 8 + p.nblocks;
+  int* const stats = q.sync + 8 + 2 * p.nblocks;  // only written when q.stats != 0
+  long long st_wait_in = 0, st_wait_dep = 0, st_wait_slot = 0;
+  int st_items = 0, st_b = 0, st_b_deferred = 0, st_slot_late = 0;
+  const long long st_t0 = clock64();
   const int nb = p.nblocks;
-  const int total = nb * (C::IA + C::IB);
+  const int totalA = nb * C::IA, totalB = nb * C::IB;
+  const int prefer = (int)(blockIdx.x & 1);        // preferred role: even CTAs columns, odd CTAs rows
 
   // last-pass twiddles: the five exact binary powers of w = exp(-2 pi i t / M) per lane position
   for (int i = tid; i < T1 * 5; i += 256) wbt[i] = q.Wn1[(i / 5) << (i % 5)];
@@ -325,7 +338,6 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   }
 
   // ---- helpers ---------------------------------------------------------------------------------
-  auto decode = [&](int i) { return pipe_decode(i < total ? i : total, nb, q.lag, C::IA, C::IB); };
   auto slot_of = [&](int b) { return b % q.nslots; };
   // fetch the input of an item into `in`; called by all threads, the item's dependency is satisfied
   auto issue_load = [&](const PipeItem& it) {
@@ -363,89 +375,160 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
     }
   };
-  // Row items fetched by TMA need only thread 0: the others arrive on the barrier at the prefetch
-  // point whatever happens; thread 0 arrives (with the byte count) when the columns are complete --
-  // at the prefetch point if they already are, else at the end of the current item after waiting.
-  // Nobody else waits for that decision; they meet the data at the next item's input barrier.
-  // (cp.async fallback and column items: all threads copy, the decision is CTA-uniform.)
+  // ---- scheduling -------------------------------------------------------------------------------
+  // Two queues in transform order: column items (role 0) and row items (role 1).  A column item is
+  // runnable when the Y slot of its transform has been read by the rows of transform b - nslots
+  // (b - nslots < b_mark), a row item when all columns of its transform are in Y (b < a_mark).  The
+  // marks are advanced by whoever completes a transform.  Every CTA prefers one role and claims
+  // from that queue; an item that is not runnable is put aside (stash) and an item of the OTHER
+  // queue is taken first, so a CTA never sits on work that others wait for: at the start and
+  // whenever the rows catch up with the columns everybody transforms columns, when the Y ring is
+  // full everybody transforms rows.
+  auto runnable = [&](const PipeItem& it, int am, int bm) {
+    return it.role == 0 ? (it.b < q.nslots || it.b - q.nslots < bm) : (it.role == 1 ? it.b < am : false);
+  };
+  auto make_item = [&](int role, int idx) {
+    PipeItem it;
+    it.role = role;
+    it.ready = 0;
+    if (role == 0) { it.b = idx / C::IA; it.j = idx - it.b * C::IA; }
+    else { it.b = idx / C::IB; it.j = idx - it.b * C::IB; }
+    return it;
+  };
+  // thread 0, blocking: take an item of `role` (or of the other role when that queue is empty); role -1 = nothing left
+  auto claim_blocking = [&](int role) {
+    for (int k = 0; k < 2; k++) {
+      const int r = k == 0 ? role : 1 - role;
+      if (ld_relaxed(r == 0 ? headA : headB) < (r == 0 ? totalA : totalB)) {
+        const int idx = atomicAdd(r == 0 ? headA : headB, 1);
+        if (idx < (r == 0 ? totalA : totalB)) return make_item(r, idx);
+      }
+    }
+    PipeItem none;
+    none.role = -1; none.b = 0; none.j = 0; none.ready = 0;
+    return none;
+  };
+  // after a completion: move a mark over every leading transform whose counter is full
+  auto advance_mark = [&](int* mark, const int* done, int target) {
+    int m = ld_relaxed(mark);
+    const int m0 = m;
+    while (m < nb && ld_relaxed(done + m) >= target) m++;
+    if (m > m0) {
+      __threadfence();
+      atomicMax(mark, m);
+    }
+  };
   auto issue_b_tma = [&](const PipeItem& it) {      // thread 0
     const int tile = it.j / NCH;
     const int plane = slot_of(it.b) * NCH + (it.j - tile * NCH);
+    // Y was written through the generic proxy (other SMs, seen complete through a_mark): order it
+    // before the TMA unit's reads
     asm volatile("fence.proxy.async;" ::: "memory");
     mbar_expect_tx(&bar_in, 65536u);
 #pragma unroll
     for (int bx = 0; bx < N2 / C::BOX_IN; bx++)
       tma_load_3d(in + bx * (C::BOX_IN * TB * 8), &mapY, 2 * tile * TB, bx * C::BOX_IN, plane, &bar_in);
   };
-  bool b_pending = false;                        // thread 0: a row item's TMA load is still to be issued
-  int rd_next = 0;                               // thread 0: doneA of the next row item (exact, relaxed load)
-  // prefetch point: the input buffer is free, `nxt` is known to everybody
-  auto prefetch = [&](const PipeItem& it) {
-    if (it.role < 0) return;
+  // fetch the input of a runnable item; all threads
+  auto fetch = [&](const PipeItem& it) {
     if (it.role == 1 && q.tma_in) {
-      if (tid == 0) {
-        if (rd_next >= DONE_A) issue_b_tma(it);
-        else b_pending = true;
-      } else {
-        mbar_arrive(&bar_in);
-      }
-    } else if (it.ready) {
+      if (tid == 0) issue_b_tma(it);
+      else mbar_arrive(&bar_in);
+    } else {
       issue_load(it);
     }
   };
-  // end of an item: whatever of the next item's input could not be fetched at the prefetch point
-  auto fetch_rest = [&](const PipeItem& it) {
-    if (it.role < 0) return;
-    if (it.role == 1 && q.tma_in) {
-      if (tid == 0 && b_pending) {
-        pipe_wait(doneA + it.b, DONE_A, err);
-        issue_b_tma(it);
-        b_pending = false;
+  // prefetch point: the input buffer is free and `nxt` is known to everybody
+  auto prefetch = [&](const PipeItem& it) {
+    if (it.role >= 0 && it.ready) fetch(it);
+  };
+  // end of an item whose successor was not runnable when it was published: settle what comes next
+  // (the successor once it has become runnable, else a detour through the other queue) and fetch it
+  auto settle = [&](PipeItem& nxt_io, int sidx) {
+    if (nxt_io.role < 0 || nxt_io.ready) return;
+    if (tid == 0) {
+      const long long w0 = clock64();
+      PipeItem it = nxt_io;
+      for (;;) {
+        const int am = ld_relaxed(a_mark), bm = ld_relaxed(b_mark);
+        if (runnable(it, am, bm)) break;
+        if (stash_sm.role >= 0) {
+          if (runnable(stash_sm, am, bm)) {         // the item put aside earlier has become runnable: that one first
+            const PipeItem t = stash_sm;
+            stash_sm = it;
+            it = t;
+            break;
+          }
+        } else {
+          // detour: take an item of the other queue (of this queue when the other is empty); run it
+          // first if it is runnable, else keep both and wait for whichever becomes runnable
+          const PipeItem other = claim_blocking(1 - it.role);
+          if (other.role >= 0) {
+            if (runnable(other, ld_relaxed(a_mark), ld_relaxed(b_mark))) {
+              stash_sm = it;
+              it = other;
+              break;
+            }
+            stash_sm = other;
+          }
+        }
+        __nanosleep(200);
+        if (*reinterpret_cast<volatile int*>(err)) break;
+        if (clock64() - w0 > (1ll << 31)) { atomicExch(err, 3); break; }
       }
-    } else if (!it.ready) {
-      if (tid == 0 && it.role == 1) pipe_wait(doneA + it.b, DONE_A, err);
-      __syncthreads();
-      issue_load(it);
+      (void)ld_acquire(a_mark);
+      it.ready = 1;
+      items[sidx] = it;
+      st_wait_dep += clock64() - w0;
+      st_b_deferred++;
     }
+    __syncthreads();
+    nxt_io = items[sidx];
+    fetch(nxt_io);
   };
 
-  // thread 0: the queue position of the NEXT item is claimed at the top of an item and its result
-  // is only read right before the item's first CTA barrier, under the input wait and conversion;
-  // the exact readiness load of a row item is issued there and read at the prefetch point.  No
-  // atomic or L2 round trip is waited for where a warp would be held up.
-  if (tid == 0) items[0] = decode(atomicAdd(head, 1));       // ready = 0
+  if (tid == 0) {
+    stash_sm.role = -1;
+    PipeItem first = claim_blocking(prefer);
+    items[0] = first;                              // ready = 0: settled below
+  }
   __syncthreads();
   PipeItem cur = items[0];
-  if (cur.role == 1 && q.tma_in) {
-    if (tid == 0) { b_pending = true; } else { mbar_arrive(&bar_in); }
-  }
-  fetch_rest(cur);
+  settle(cur, 0);
   uint32_t par = 0;
   int s = 0;
   bool stores_pending = false;                   // thread 0: TMA stores may still be reading `work`
 
   while (cur.role >= 0) {
-    // ---- thread 0: claim and this item's slot counter, in flight until barrier 1
-    int nidx = 0, slot_cnt = 0;
+    // ---- thread 0: the next item -- the stash if there is one, else a new claim from the preferred
+    // queue -- and the two marks; all in flight until barrier 1
+    int nidx = 0, am = 0, bm = 0, nrole = prefer;
+    bool from_stash = false;
     if (tid == 0) {
-      nidx = atomicAdd(head, 1);
-      if (cur.role == 0 && cur.b >= q.nslots) slot_cnt = ld_relaxed(doneB + (cur.b - q.nslots));
+      from_stash = stash_sm.role >= 0;
+      if (!from_stash) {
+        // prefer the own role while its queue lasts (the peek may be stale: re-checked on the claimed index)
+        nrole = prefer;
+        nidx = atomicAdd(nrole == 0 ? headA : headB, 1);
+      }
+      am = ld_relaxed(a_mark);
+      bm = ld_relaxed(b_mark);
     }
     // thread 0, right before barrier 1: publish the next item and this item's slot state
     auto publish = [&]() {
-      PipeItem nx = decode(nidx);
-      if (nx.role == 1) {
-        if (q.tma_in) {
-          rd_next = ld_relaxed(doneA + nx.b);     // read at the prefetch point
-          nx.ready = 0;
-        } else {
-          nx.ready = ld_relaxed(doneA + nx.b) >= DONE_A ? 1 : 0;
-        }
+      PipeItem nx;
+      if (from_stash) {
+        nx = stash_sm;
+        stash_sm.role = -1;
+      } else if (nidx < (nrole == 0 ? totalA : totalB)) {
+        nx = make_item(nrole, nidx);
       } else {
-        nx.ready = nx.role == 0 ? 1 : 0;
+        nx = claim_blocking(1 - nrole);             // own queue exhausted (end of the call)
       }
+      nx.ready = runnable(nx, am, bm) ? 1 : 0;
+      if (nx.role == 1) st_b++;
       items[s ^ 1] = nx;
-      slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || slot_cnt >= C::IB) ? 1 : 0;
+      slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || cur.b - q.nslots < bm) ? 1 : 0;
     };
     const int tile = cur.j / NCH;
     const int c = cur.j - tile * NCH;
@@ -470,7 +553,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
 #pragma unroll
         for (int e = 0; e < 32; e++) wv[e] = __ldg(wp + e * T1);
       }
-      pipe_mbar_wait(&bar_in, par, err);
+      { const long long w0 = clock64(); pipe_mbar_wait(&bar_in, par, err); if (tid == 0) { st_wait_in += clock64() - w0; st_items++; } }
       par ^= 1;
       {
         const unsigned char* rp = in + t * C::PITCH_A + col * FRAME;
@@ -522,8 +605,10 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       apply_power_twiddles<32>(v, tw_base, tw_sb);
       // ---- the slot must have been read by the rows of transform b - nslots
       if (!my_slot_ok) {
-        if (lane == 0) pipe_wait(doneB + (cur.b - q.nslots), C::IB, err);
+        const long long w0 = clock64();
+        if (lane == 0) pipe_wait(b_mark, cur.b - q.nslots + 1, err);
         __syncwarp();
+        if (tid == 0) { st_wait_slot += clock64() - w0; st_slot_late++; }
       }
       {
         float2* Yp = q.Y + (size_t)(slot_of(cur.b) * NCH + c) * N + (size_t)n2 * N1 + t;
@@ -540,15 +625,14 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         if (old == C::NWARPS - 1) {
           a_arrived = 0;
           __threadfence();
-          atomicAdd(doneA + cur.b, C::NWARPS);
+          if (atomicAdd(doneA + cur.b, C::NWARPS) + C::NWARPS == DONE_A) advance_mark(a_mark, doneA, DONE_A);
         }
       }
-      fetch_rest(nxt);
-      cur = nxt;
+      { PipeItem n2 = nxt; settle(n2, s ^ 1); cur = n2; }
     } else {
       // =============================== role B: TB rows of transform cur.b ======================
       const int r = tid & (TB - 1), t = tid / TB;
-      pipe_mbar_wait(&bar_in, par, err);
+      { const long long w0 = clock64(); pipe_mbar_wait(&bar_in, par, err); if (tid == 0) { st_wait_in += clock64() - w0; st_items++; } }
       par ^= 1;
       {
         const float2* ip = reinterpret_cast<const float2*>(in) + t * TB + r;
@@ -564,7 +648,6 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
       __syncthreads();                            // barrier 1: the Y tile is in registers; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
-      if (tid == 0) atomicAdd(doneB + cur.b, 1);  // the tile is in registers: its share of the slot may be overwritten
       // ---- row transforms: one exchange through the (now free) input buffer, all rows at once
       pass0<T2>(v);
       {
@@ -580,6 +663,9 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
       __syncthreads();                            // the input buffer is free again
       prefetch(nxt);
+      // the tile is in registers: its share of the Y slot may be overwritten (behind the item's last
+      // barrier: the atomic's round trip holds up nobody)
+      if (tid == 0 && atomicAdd(doneB + cur.b, 1) + 1 == C::IB) advance_mark(b_mark, doneB, C::IB);
       {
         float2 wb[5];
 #pragma unroll
@@ -662,12 +748,21 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           }
         }
       }
-      fetch_rest(nxt);
-      cur = nxt;
+      { PipeItem n2 = nxt; settle(n2, s ^ 1); cur = n2; }
     }
     s ^= 1;
   }
   if (tid == 0) bulk_wait_all();                  // shared memory must outlive the last TMA store
+  if (tid == 0 && q.stats) {
+    atomicAdd(stats + 0, st_items);
+    atomicAdd(stats + 1, st_b);
+    atomicAdd(stats + 2, st_b_deferred);
+    atomicAdd(stats + 3, st_slot_late);
+    atomicAdd(stats + 4, (int)(st_wait_in >> 10));
+    atomicAdd(stats + 5, (int)(st_wait_dep >> 10));
+    atomicAdd(stats + 6, (int)(st_wait_slot >> 10));
+    atomicAdd(stats + 7, (int)((clock64() - st_t0) >> 10));
+  }
 }
 #endif  // __CUDACC__
 

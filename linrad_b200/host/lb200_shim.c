@@ -20,6 +20,7 @@
  */
 #include <string.h>
 #include <stdlib.h>
+#include <pthread.h>
 #include "globdef.h"
 #include "uidef.h"
 #include "fft1def.h"
@@ -32,6 +33,12 @@
 #define LB200_SHIM_MAX_THREADS MAX_FFT1_THREADS      /* thrdef.h:106 */
 
 static lb200_plan *shim_plan[LB200_SHIM_MAX_THREADS];
+/* A plan is not re-entrant (linrad_b200.h), and Linrad drives plan 0 from two threads: fft1_b on the
+ * wideband thread (wcw.c:1036) and fft1_mix1_fixed/_afc on the narrowband thread (wcw.c:1700,1712).
+ * They share the plan on purpose -- mix1 finds the spectra fft1_b left in the plan's device mirror --
+ * so every entry takes the plan's lock. */
+static pthread_mutex_t shim_lock[LB200_SHIM_MAX_THREADS];
+static int shim_locks_ready;
 static float *shim_power;          /* max_fft1n rows of fft1_size floats, indexed like fft1_float blocks */
 static float *shim_window;         /* natural-order copy of fft1_window */
 static float *shim_corr;           /* fft1_correlation_flag == 1: rows of 2*fft1_size floats, like shim_power */
@@ -48,6 +55,23 @@ int lb200_shim_open(int no_of_threads)
 {
 int i, k, mo;
 lb200_config c;
+if(shim_locks_ready == 0)
+  {
+  for(i=0; i<LB200_SHIM_MAX_THREADS; i++)pthread_mutex_init(&shim_lock[i],NULL);
+  shim_locks_ready=1;
+  }
+/* What the library reproduces: the fft1 versions that take their N frames fft1_interleave_points */
+/* before timf1p_ref (fft1.c:700, 425; fft1_re.c:44).  The "twin"/"quad" versions that run two */
+/* transforms side by side start I samples earlier (fft1.c:2980, 1047: fft_cntrl[].parall_fft == 2), */
+/* and of the real-input versions only the split-radix one (window mode 2, fft1_re.c) is covered. */
+if(fft_cntrl[FFT1_CURMODE].parall_fft != 1){shim_fail(LB200_ERR_UNSUPPORTED); return -1;}
+if( (ui.rx_input_mode&IQ_DATA) == 0 && fft_cntrl[FFT1_CURMODE].window != 2)
+  {
+  shim_fail(LB200_ERR_UNSUPPORTED);
+  return -1;
+  }
+/* fft1_correlation_flag >= 2 is the double precision mixer of mix1.c:275-452 */
+if(fft1_correlation_flag >= 2){shim_fail(LB200_ERR_UNSUPPORTED); return -1;}
 memset(&c,0,sizeof(c));
 c.abi_version=LB200_ABI_VERSION;
 c.device=0;
@@ -143,7 +167,9 @@ if(fft1_correlation_flag == 1)
   a.corr_rows=&shim_corr[(size_t)((out-fft1_float)/fft1_block)*2*(size_t)fft1_size];
 if(shim_xy != NULL)
   a.xypower_rows=&shim_xy[(size_t)((out-fft1_float)/fft1_block)*4*(size_t)fft1_size];
+pthread_mutex_lock(&shim_lock[gpu_handle_number]);
 rc=lb200_fft1(shim_plan[gpu_handle_number],&a);
+pthread_mutex_unlock(&shim_lock[gpu_handle_number]);
 if(rc != LB200_OK)shim_fail(rc);
 }
 
@@ -160,7 +186,9 @@ if(fft1afc_flag > 0)
 /* fft1.c:4203-4426: AFC runs from fft1, so fft1_c also leaves the per-transform powers behind */
 /* (fft1_power, or fft1_xypower for two channels).  Spur elimination works on fft1_float on */
 /* the host between the filter and the power step and is not part of the library. */
-  if(no_of_spurs > 0){shim_fail(LB200_ERR_UNSUPPORTED); return;}
+/* The spur search of fft1.c:4426-4505 (spursearch_powersum / spursearch_xysum) is not done here */
+/* either, so with it enabled no spur would ever be found: refuse instead of silently disabling it. */
+  if(no_of_spurs > 0 || genparm[MAX_NO_OF_SPURS] > 0){shim_fail(LB200_ERR_UNSUPPORTED); return;}
   ffts_na=fft1_nb;
   ffts_nm=fft1_nm;
   if(ui.rx_rf_channels == 1)
@@ -244,7 +272,9 @@ a.state=st;
 a.timf3_float.base=timf3_float;
 a.timf3_float.size=(size_t)timf3_size;
 a.timf3_pa=(uint32_t)timf3_pa;
+pthread_mutex_lock(&shim_lock[0]);
 rc=lb200_mix1(shim_plan[0],&a);
+pthread_mutex_unlock(&shim_lock[0]);
 if(rc != LB200_OK){shim_fail(rc); return;}
 for(ss=0; ss<k; ss++)
   {
@@ -297,7 +327,9 @@ a.state=st;
 a.timf3_float.base=timf3_float;
 a.timf3_float.size=(size_t)timf3_size;
 a.timf3_pa=(uint32_t)timf3_pa;
+pthread_mutex_lock(&shim_lock[0]);
 rc=lb200_mix1(shim_plan[0],&a);
+pthread_mutex_unlock(&shim_lock[0]);
 if(rc != LB200_OK){shim_fail(rc); return;}
 for(ss=0; ss<k; ss++)
   {
