@@ -6,11 +6,14 @@
 // direction flip fft1.c:3660-3680, fft1_c fft1.c:4115-4200), rebuilt so that nothing waits:
 //
 //   * one launch per call.  Work items "columns of transform b" (role A) and "rows of transform b"
-//     (role B) sit in one queue, A(b) ahead of B(b) by `lag` transforms; CTAs claim items in queue
-//     order with an atomic counter, so a dependency always points to an item that a running CTA
-//     already holds (no deadlock, no co-residency requirement).  B(b) waits for the columns of b
-//     (doneA[b]), A(b) waits until the rows of b-nslots have left the slot it writes (doneB).
-//     The intermediate Y lives in a ring of `nslots` transforms (a few MB): it never leaves L2.
+//     (role B) are dealt to the persistent CTAs round robin (no queue, no atomics to claim work).
+//     Rows of b need all columns of b, columns of b need the Y slot that the rows of b - nslots
+//     have read: both conditions are two global watermarks (a_mark / b_mark) advanced by whoever
+//     completes a transform.  At every item boundary a CTA takes its next item of its preferred
+//     kind if that is runnable, else its next item of the other kind, so nobody sits on work that
+//     others wait for and a dependency always points to lower transforms (no deadlock, no
+//     co-residency requirement).  The intermediate Y lives in a ring of `nslots` transforms: it
+//     never leaves L2.
 //   * Y is kept TRANSPOSED, Y[n2][k1].  The one transposition the four-step scheme needs is done
 //     where the data is smallest: the raw int16/int32 tile (TA adjacent columns x N1 rows) is
 //     staged in shared memory by cp.async (16-byte pieces, padded pitch) while the previous item
@@ -25,10 +28,9 @@
 //     goes through the input buffer once it has been read (one barrier pair per item); bins
 //     k1..k1+TB-1 of one k2 leave as one 128-byte run, as streaming stores or (optionally, one
 //     channel) staged and written by TMA tensor stores (cp.async.bulk.tensor.3d shared -> global).
-//   * the queue position of the item after next is claimed two items ahead and readiness flags
-//     are read with relaxed loads that stay in flight under the conversion, so the atomic / L2
-//     round trips of the scheduling never sit on a warp's critical path; a column item's completion
-//     is published once per CTA behind the next CTA barrier.
+//   * the choice of the next item is made one item ahead by thread 0 from two relaxed loads that
+//     stay in flight under the input wait and conversion; a column item's completion is published
+//     by the last of the CTA's eight warps to finish it (one gpu-scope fence per item).
 //   * the new timf1 bytes of a later transform are pulled into L2 by cp.async.bulk.prefetch.L2.
 #pragma once
 #include <cuda.h>
@@ -305,17 +307,14 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   float2* const wbt = reinterpret_cast<float2*>(smem_raw + C::IN_BYTES + C::WORK_BYTES);
   __shared__ uint64_t bar_in;
   __shared__ PipeItem items[2];
-  __shared__ PipeItem stash_sm;                  // an item taken but not runnable yet (run after a detour)
   __shared__ int slot_ok[2];
   __shared__ int a_arrived;                      // warps of this CTA that have stored their columns of the current item
   const Fft1K& p = q.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // sync block: [0] column-queue head, [1] error flag, [2] row-queue head, [3] a_mark (all transforms
+  // sync block: [1] error flag, [3] a_mark (all transforms
   // below it have their columns in Y), [4] b_mark (all below it have been read by their rows),
   // [8 ..) doneA[nblocks], doneB[nblocks], then 8 debug counters
-  int* const headA = q.sync;
   int* const err = q.sync + 1;
-  int* const headB = q.sync + 2;
   int* const a_mark = q.sync + 3;
   int* const b_mark = q.sync + 4;
   int* const doneA = q.sync + 8;
@@ -376,14 +375,16 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     }
   };
   // ---- scheduling -------------------------------------------------------------------------------
-  // Two queues in transform order: column items (role 0) and row items (role 1).  A column item is
-  // runnable when the Y slot of its transform has been read by the rows of transform b - nslots
-  // (b - nslots < b_mark), a row item when all columns of its transform are in Y (b < a_mark).  The
-  // marks are advanced by whoever completes a transform.  Every CTA prefers one role and claims
-  // from that queue; an item that is not runnable is put aside (stash) and an item of the OTHER
-  // queue is taken first, so a CTA never sits on work that others wait for: at the start and
-  // whenever the rows catch up with the columns everybody transforms columns, when the Y ring is
-  // full everybody transforms rows.
+  // Column items (role 0) and row items (role 1) are dealt to the CTAs round robin: CTA c owns the
+  // items c, c + grid, c + 2 grid, ... of either kind, in transform order -- no queue, no atomics.
+  // A column item is runnable when the Y slot of its transform has been read by the rows of
+  // transform b - nslots (b - nslots < b_mark), a row item when all columns of its transform are in
+  // Y (b < a_mark); the two marks are advanced by whoever completes a transform.  At every item
+  // boundary a CTA takes the next item of its preferred kind if it is runnable, else its next item
+  // of the other kind: at the start and whenever the rows have caught up everybody transforms
+  // columns, when the Y ring is full everybody transforms rows, and nobody sits on work that
+  // others wait for.  The choice is made one item ahead (thread 0, from two relaxed loads that
+  // are in flight under the input wait), so the next input is fetched while this item is computed.
   auto runnable = [&](const PipeItem& it, int am, int bm) {
     return it.role == 0 ? (it.b < q.nslots || it.b - q.nslots < bm) : (it.role == 1 ? it.b < am : false);
   };
@@ -393,20 +394,28 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     it.ready = 0;
     if (role == 0) { it.b = idx / C::IA; it.j = idx - it.b * C::IA; }
     else { it.b = idx / C::IB; it.j = idx - it.b * C::IB; }
+    if (idx >= (role == 0 ? totalA : totalB)) it.role = -1;
     return it;
   };
-  // thread 0, blocking: take an item of `role` (or of the other role when that queue is empty); role -1 = nothing left
-  auto claim_blocking = [&](int role) {
-    for (int k = 0; k < 2; k++) {
-      const int r = k == 0 ? role : 1 - role;
-      if (ld_relaxed(r == 0 ? headA : headB) < (r == 0 ? totalA : totalB)) {
-        const int idx = atomicAdd(r == 0 ? headA : headB, 1);
-        if (idx < (r == 0 ? totalA : totalB)) return make_item(r, idx);
-      }
+  int nextA = (int)blockIdx.x, nextB = (int)blockIdx.x;   // thread 0: this CTA's cursors
+  // thread 0: the next item given the marks; advances the cursor of the kind it takes.  ready = 0 when
+  // nothing of this CTA is runnable yet (then the preferred kind is returned without being taken).
+  auto choose = [&](int am, int bm) {
+    const PipeItem ca = make_item(0, nextA), cb = make_item(1, nextB);
+    const PipeItem& first = prefer == 0 ? ca : cb;
+    const PipeItem& second = prefer == 0 ? cb : ca;
+    PipeItem nx;
+    if (first.role >= 0 && runnable(first, am, bm)) nx = first;
+    else if (second.role >= 0 && runnable(second, am, bm)) nx = second;
+    else {
+      nx = first.role >= 0 ? first : second;         // both blocked (or nothing left: role -1)
+      nx.ready = 0;
+      return nx;
     }
-    PipeItem none;
-    none.role = -1; none.b = 0; none.j = 0; none.ready = 0;
-    return none;
+    nx.ready = 1;
+    if (nx.role == 0) nextA += (int)gridDim.x;
+    else nextB += (int)gridDim.x;
+    return nx;
   };
   // after a completion: move a mark over every leading transform whose counter is full
   auto advance_mark = [&](int* mark, const int* done, int target) {
@@ -442,90 +451,57 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   auto prefetch = [&](const PipeItem& it) {
     if (it.role >= 0 && it.ready) fetch(it);
   };
-  // end of an item whose successor was not runnable when it was published: settle what comes next
-  // (the successor once it has become runnable, else a detour through the other queue) and fetch it
+  // end of an item when nothing of this CTA was runnable at its publication: wait for the first
+  // of its two candidates to become runnable, then fetch it (start-up, ring full, end of the call)
   auto settle = [&](PipeItem& nxt_io, int sidx) {
     if (nxt_io.role < 0 || nxt_io.ready) return;
     if (tid == 0) {
       const long long w0 = clock64();
       PipeItem it = nxt_io;
       for (;;) {
-        const int am = ld_relaxed(a_mark), bm = ld_relaxed(b_mark);
-        if (runnable(it, am, bm)) break;
-        if (stash_sm.role >= 0) {
-          if (runnable(stash_sm, am, bm)) {         // the item put aside earlier has become runnable: that one first
-            const PipeItem t = stash_sm;
-            stash_sm = it;
-            it = t;
-            break;
-          }
-        } else {
-          // detour: take an item of the other queue (of this queue when the other is empty); run it
-          // first if it is runnable, else keep both and wait for whichever becomes runnable
-          const PipeItem other = claim_blocking(1 - it.role);
-          if (other.role >= 0) {
-            if (runnable(other, ld_relaxed(a_mark), ld_relaxed(b_mark))) {
-              stash_sm = it;
-              it = other;
-              break;
-            }
-            stash_sm = other;
-          }
-        }
+        it = choose(ld_relaxed(a_mark), ld_relaxed(b_mark));
+        if (it.ready || it.role < 0) break;
         __nanosleep(200);
         if (*reinterpret_cast<volatile int*>(err)) break;
         if (clock64() - w0 > (1ll << 31)) { atomicExch(err, 3); break; }
       }
+      if (it.role >= 0 && !it.ready) {               // gave up: run it anyway so that the kernel ends (error flag is set)
+        it.ready = 1;
+        if (it.role == 0) nextA += (int)gridDim.x;
+        else nextB += (int)gridDim.x;
+      }
       (void)ld_acquire(a_mark);
-      it.ready = 1;
       items[sidx] = it;
       st_wait_dep += clock64() - w0;
       st_b_deferred++;
     }
     __syncthreads();
     nxt_io = items[sidx];
-    fetch(nxt_io);
+    if (nxt_io.role >= 0) fetch(nxt_io);
   };
 
   if (tid == 0) {
-    stash_sm.role = -1;
-    PipeItem first = claim_blocking(prefer);
-    items[0] = first;                              // ready = 0: settled below
+    PipeItem first = choose(0, 0);
+    items[0] = first;
   }
   __syncthreads();
   PipeItem cur = items[0];
-  settle(cur, 0);
+  if (cur.role >= 0 && cur.ready) fetch(cur);
+  else settle(cur, 0);
   uint32_t par = 0;
   int s = 0;
   bool stores_pending = false;                   // thread 0: TMA stores may still be reading `work`
 
   while (cur.role >= 0) {
-    // ---- thread 0: the next item -- the stash if there is one, else a new claim from the preferred
-    // queue -- and the two marks; all in flight until barrier 1
-    int nidx = 0, am = 0, bm = 0, nrole = prefer;
-    bool from_stash = false;
+    // ---- thread 0: the two marks, in flight until barrier 1
+    int am = 0, bm = 0;
     if (tid == 0) {
-      from_stash = stash_sm.role >= 0;
-      if (!from_stash) {
-        // prefer the own role while its queue lasts (the peek may be stale: re-checked on the claimed index)
-        nrole = prefer;
-        nidx = atomicAdd(nrole == 0 ? headA : headB, 1);
-      }
       am = ld_relaxed(a_mark);
       bm = ld_relaxed(b_mark);
     }
     // thread 0, right before barrier 1: publish the next item and this item's slot state
     auto publish = [&]() {
-      PipeItem nx;
-      if (from_stash) {
-        nx = stash_sm;
-        stash_sm.role = -1;
-      } else if (nidx < (nrole == 0 ? totalA : totalB)) {
-        nx = make_item(nrole, nidx);
-      } else {
-        nx = claim_blocking(1 - nrole);             // own queue exhausted (end of the call)
-      }
-      nx.ready = runnable(nx, am, bm) ? 1 : 0;
+      const PipeItem nx = choose(am, bm);
       if (nx.role == 1) st_b++;
       items[s ^ 1] = nx;
       slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || cur.b - q.nslots < bm) ? 1 : 0;

@@ -127,12 +127,21 @@ def test_pipe_equals_legacy_direction_and_range(direction, first_x, xpoints):
     # bins outside the display range keep the raw fft1_b scale: compare on the common energy
     assert rel_rms(f1, f0) <= 6e-7
     assert np.array_equal(p1 == 0, p0 == 0), "bins outside the range must stay untouched in both"
-    strong = p0 > 1e-4 * p0.max()
-    bad = np.abs(p1 - p0) > 5e-5 * p0 + 2e-6 * p0.max()
-    bad &= strong
+    # Two correctly rounded float32 transforms of different structure differ, in every bin, by a few
+    # ulps of the STRONGEST line of the whole spectrum -- which may lie outside the display range
+    # (those bins keep the raw fft1_b scale: bring them to the in-range scale with the uniform gain).
+    N, lo, hi = s.fft1_size, s.fft1_first_point, s.fft1_last_point
+    amp = np.hypot(f0[:, 0::2], f0[:, 1::2]).astype(np.float64)
+    gain = float(s.filtercorr[2 * (N // 2)])
+    amp[:, :lo] *= gain
+    amp[:, hi + 1:] *= gain
+    a_peak, a_rms = amp.max(), np.sqrt((amp ** 2).mean())
+    eps = max(8 * np.sqrt(np.log2(N)) * 2.0 ** -23 * a_rms, 4 * 2.0 ** -23 * a_peak)
+    allow = 5e-5 * p0 + 2 * np.sqrt(s.avg1num * p0.astype(np.float64)) * eps + s.avg1num * eps ** 2
+    bad = (np.abs(p1.astype(np.float64) - p0) > allow) & (p0 > 0)
     where = np.argwhere(bad)[:8]
-    assert not bad.any(), ("fft1_sumsq pipe vs legacy", bad.sum(), where.tolist(), [(float(p0[tuple(w)]), float(p1[tuple(w)])) for w in where],
-                           s.fft1_first_point, s.fft1_last_point)
+    assert not bad.any(), ("fft1_sumsq pipe vs legacy", int(bad.sum()), where.tolist(),
+                           [(float(p0[tuple(w)]), float(p1[tuple(w)]), float(allow[tuple(w)])) for w in where], lo, hi)
 
 
 VARIANTS = [
