@@ -6,14 +6,14 @@
 // direction flip fft1.c:3660-3680, fft1_c fft1.c:4115-4200), rebuilt so that nothing waits:
 //
 //   * one launch per call.  Work items "columns of transform b" (role A) and "rows of transform b"
-//     (role B) are dealt to the persistent CTAs round robin (no queue, no atomics to claim work).
-//     Rows of b need all columns of b, columns of b need the Y slot that the rows of b - nslots
-//     have read: both conditions are two global watermarks (a_mark / b_mark) advanced by whoever
-//     completes a transform.  At every item boundary a CTA takes its next item of its preferred
-//     kind if that is runnable, else its next item of the other kind, so nobody sits on work that
-//     others wait for and a dependency always points to lower transforms (no deadlock, no
-//     co-residency requirement).  The intermediate Y lives in a ring of `nslots` transforms: it
-//     never leaves L2.
+//     (role B) sit in two queues in transform order.  Rows of b need all columns of b, columns of b
+//     need the Y slot that the rows of b - nslots have read: both conditions are two global
+//     watermarks (a_mark / b_mark) advanced by whoever completes a transform.  At every item
+//     boundary a persistent CTA looks at the queue heads and the marks and claims the lowest item
+//     of its preferred kind if that is runnable, else of the other kind -- it never takes work it
+//     cannot start, so nobody sits on items that others wait for, and a dependency always points
+//     to lower transforms (no deadlock, no co-residency requirement).  The intermediate Y lives in
+//     a ring of `nslots` transforms: it never leaves L2.
 //   * Y is kept TRANSPOSED, Y[n2][k1].  The one transposition the four-step scheme needs is done
 //     where the data is smallest: the raw int16/int32 tile (TA adjacent columns x N1 rows) is
 //     staged in shared memory by cp.async (16-byte pieces, padded pitch) while the previous item
@@ -311,10 +311,12 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   __shared__ int a_arrived;                      // warps of this CTA that have stored their columns of the current item
   const Fft1K& p = q.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // sync block: [1] error flag, [3] a_mark (all transforms
+  // sync block: [0] column-queue head, [1] error flag, [2] row-queue head, [3] a_mark (all transforms
   // below it have their columns in Y), [4] b_mark (all below it have been read by their rows),
   // [8 ..) doneA[nblocks], doneB[nblocks], then 8 debug counters
+  int* const headA = q.sync;
   int* const err = q.sync + 1;
+  int* const headB = q.sync + 2;
   int* const a_mark = q.sync + 3;
   int* const b_mark = q.sync + 4;
   int* const doneA = q.sync + 8;
@@ -375,16 +377,14 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     }
   };
   // ---- scheduling -------------------------------------------------------------------------------
-  // Column items (role 0) and row items (role 1) are dealt to the CTAs round robin: CTA c owns the
-  // items c, c + grid, c + 2 grid, ... of either kind, in transform order -- no queue, no atomics.
-  // A column item is runnable when the Y slot of its transform has been read by the rows of
-  // transform b - nslots (b - nslots < b_mark), a row item when all columns of its transform are in
-  // Y (b < a_mark); the two marks are advanced by whoever completes a transform.  At every item
-  // boundary a CTA takes the next item of its preferred kind if it is runnable, else its next item
-  // of the other kind: at the start and whenever the rows have caught up everybody transforms
-  // columns, when the Y ring is full everybody transforms rows, and nobody sits on work that
-  // others wait for.  The choice is made one item ahead (thread 0, from two relaxed loads that
-  // are in flight under the input wait), so the next input is fetched while this item is computed.
+  // Two queues in transform order: column items (role 0) and row items (role 1).  A column item is
+  // runnable when the Y slot of its transform has been read by the rows of transform b - nslots
+  // (b - nslots < b_mark), a row item when all columns of its transform are in Y (b < a_mark); the
+  // marks are advanced by whoever completes a transform.  A CTA peeks at the heads and the marks
+  // (relaxed loads, in flight under the input wait of the current item) and only then claims: the
+  // lowest item of its preferred kind if runnable, else of the other kind.  At the start and
+  // whenever the rows have caught up everybody transforms columns, when the Y ring is full
+  // everybody transforms rows.
   auto runnable = [&](const PipeItem& it, int am, int bm) {
     return it.role == 0 ? (it.b < q.nslots || it.b - q.nslots < bm) : (it.role == 1 ? it.b < am : false);
   };
@@ -397,24 +397,26 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     if (idx >= (role == 0 ? totalA : totalB)) it.role = -1;
     return it;
   };
-  int nextA = (int)blockIdx.x, nextB = (int)blockIdx.x;   // thread 0: this CTA's cursors
-  // thread 0: the next item given the marks; advances the cursor of the kind it takes.  ready = 0 when
-  // nothing of this CTA is runnable yet (then the preferred kind is returned without being taken).
-  auto choose = [&](int am, int bm) {
-    const PipeItem ca = make_item(0, nextA), cb = make_item(1, nextB);
-    const PipeItem& first = prefer == 0 ? ca : cb;
-    const PipeItem& second = prefer == 0 ? cb : ca;
+  // thread 0: given the heads of the two queues and the marks (peeked, possibly a little stale), take
+  // the lowest item of the preferred kind if it is runnable, else of the other kind.  Returns an item
+  // with ready = 1 (claimed and runnable), ready = 0 and role >= 0 (claimed, but its transform moved
+  // on during the claim and is not runnable yet: wait for it), or role = -2 (nothing runnable: nothing
+  // claimed), or role = -1 (both queues are empty).
+  auto choose = [&](int hA, int hB, int am, int bm) {
     PipeItem nx;
-    if (first.role >= 0 && runnable(first, am, bm)) nx = first;
-    else if (second.role >= 0 && runnable(second, am, bm)) nx = second;
-    else {
-      nx = first.role >= 0 ? first : second;         // both blocked (or nothing left: role -1)
-      nx.ready = 0;
-      return nx;
-    }
-    nx.ready = 1;
-    if (nx.role == 0) nextA += (int)gridDim.x;
-    else nextB += (int)gridDim.x;
+    nx.b = 0; nx.j = 0; nx.ready = 0;
+    if (hA >= totalA && hB >= totalB) { nx.role = -1; return nx; }
+    const PipeItem ca = make_item(0, hA), cb = make_item(1, hB);
+    const bool okA = ca.role >= 0 && runnable(ca, am, bm), okB = cb.role >= 0 && runnable(cb, am, bm);
+    int role = -2;
+    if (prefer == 0) role = okA ? 0 : (okB ? 1 : -2);
+    else role = okB ? 1 : (okA ? 0 : -2);
+    nx.role = role;
+    if (role < 0) return nx;
+    const int idx = atomicAdd(role == 0 ? headA : headB, 1);
+    nx = make_item(role, idx);
+    if (nx.role < 0) { nx.role = -2; return nx; }      // the queue ran out under the claim: look again
+    nx.ready = runnable(nx, am, bm) ? 1 : 0;
     return nx;
   };
   // after a completion: move a mark over every leading transform whose counter is full
@@ -451,24 +453,26 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   auto prefetch = [&](const PipeItem& it) {
     if (it.role >= 0 && it.ready) fetch(it);
   };
-  // end of an item when nothing of this CTA was runnable at its publication: wait for the first
-  // of its two candidates to become runnable, then fetch it (start-up, ring full, end of the call)
+  // end of an item whose successor could not be fixed at its publication (nothing runnable then, or
+  // a claimed item whose transform is not complete yet): wait, claim, fetch.  Start-up, a full ring
+  // with no complete transform, and the end of the call come through here.
   auto settle = [&](PipeItem& nxt_io, int sidx) {
-    if (nxt_io.role < 0 || nxt_io.ready) return;
+    if (nxt_io.role == -1 || nxt_io.ready) return;
     if (tid == 0) {
       const long long w0 = clock64();
       PipeItem it = nxt_io;
       for (;;) {
-        it = choose(ld_relaxed(a_mark), ld_relaxed(b_mark));
-        if (it.ready || it.role < 0) break;
-        __nanosleep(200);
-        if (*reinterpret_cast<volatile int*>(err)) break;
-        if (clock64() - w0 > (1ll << 31)) { atomicExch(err, 3); break; }
-      }
-      if (it.role >= 0 && !it.ready) {               // gave up: run it anyway so that the kernel ends (error flag is set)
-        it.ready = 1;
-        if (it.role == 0) nextA += (int)gridDim.x;
-        else nextB += (int)gridDim.x;
+        const int am = ld_relaxed(a_mark), bm = ld_relaxed(b_mark);
+        if (it.role >= 0) {                           // holding a claimed item: wait for it
+          if (runnable(it, am, bm)) { it.ready = 1; break; }
+        } else {
+          it = choose(ld_relaxed(headA), ld_relaxed(headB), am, bm);
+          if (it.role == -1 || it.ready) break;
+          if (it.role >= 0) continue;                 // claimed, not runnable yet: re-check at once
+        }
+        __nanosleep(100);
+        if (*reinterpret_cast<volatile int*>(err)) { if (it.role < 0) it.role = -1; it.ready = 1; break; }
+        if (clock64() - w0 > (1ll << 31)) { atomicExch(err, 3); if (it.role < 0) it.role = -1; it.ready = 1; break; }
       }
       (void)ld_acquire(a_mark);
       items[sidx] = it;
@@ -481,7 +485,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   };
 
   if (tid == 0) {
-    PipeItem first = choose(0, 0);
+    PipeItem first = choose(ld_relaxed(headA), ld_relaxed(headB), 0, 0);
     items[0] = first;
   }
   __syncthreads();
@@ -493,15 +497,17 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   bool stores_pending = false;                   // thread 0: TMA stores may still be reading `work`
 
   while (cur.role >= 0) {
-    // ---- thread 0: the two marks, in flight until barrier 1
-    int am = 0, bm = 0;
+    // ---- thread 0: queue heads and marks, in flight until barrier 1
+    int hA = 0, hB = 0, am = 0, bm = 0;
     if (tid == 0) {
+      hA = ld_relaxed(headA);
+      hB = ld_relaxed(headB);
       am = ld_relaxed(a_mark);
       bm = ld_relaxed(b_mark);
     }
-    // thread 0, right before barrier 1: publish the next item and this item's slot state
+    // thread 0, right before barrier 1: claim and publish the next item, and this item's slot state
     auto publish = [&]() {
-      const PipeItem nx = choose(am, bm);
+      const PipeItem nx = choose(hA, hB, am, bm);
       if (nx.role == 1) st_b++;
       items[s ^ 1] = nx;
       slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || cur.b - q.nslots < bm) ? 1 : 0;

@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out
-T=${TAG:-r2h}
+T=${TAG:-r2i}
 timeout 900 python -m pytest tests/test_pipe_gpu.py -x -q > $O/${T}_pipe_tests.log 2>&1; tail -12 $O/${T}_pipe_tests.log
 B="python bench.py --workload cfg4 --no-e2e --no-cpu-baseline --no-per-config --steps 3 --warmup 2 --step-ms 1"
 for v in "X=1" "LB200_PIPE_SLOTS=10" "LB200_PIPE_SLOTS=16" "LB200_PIPE_SLOTS=32" "LB200_PIPE_TMA_IN=0"; do
