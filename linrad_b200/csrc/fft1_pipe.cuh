@@ -6,14 +6,11 @@
 // direction flip fft1.c:3660-3680, fft1_c fft1.c:4115-4200), rebuilt so that nothing waits:
 //
 //   * one launch per call.  Work items "columns of transform b" (role A) and "rows of transform b"
-//     (role B) sit in two queues in transform order.  Rows of b need all columns of b, columns of b
-//     need the Y slot that the rows of b - nslots have read: both conditions are two global
-//     watermarks (a_mark / b_mark) advanced by whoever completes a transform.  At every item
-//     boundary a persistent CTA looks at the queue heads and the marks and claims the lowest item
-//     of its preferred kind if that is runnable, else of the other kind -- it never takes work it
-//     cannot start, so nobody sits on items that others wait for, and a dependency always points
-//     to lower transforms (no deadlock, no co-residency requirement).  The intermediate Y lives in
-//     a ring of `nslots` transforms: it never leaves L2.
+//     (role B) sit in one queue, A(b) ahead of B(b) by `lag` transforms; CTAs claim items in queue
+//     order with an atomic counter, so a dependency always points to an item that a running CTA
+//     already holds (no deadlock, no co-residency requirement).  B(b) waits for the columns of b
+//     (doneA[b]), A(b) waits until the rows of b-nslots have left the slot it writes (doneB).
+//     The intermediate Y lives in a ring of `nslots` transforms (a few MB): it never leaves L2.
 //   * Y is kept TRANSPOSED, Y[n2][k1].  The one transposition the four-step scheme needs is done
 //     where the data is smallest: the raw int16/int32 tile (TA adjacent columns x N1 rows) is
 //     staged in shared memory by cp.async (16-byte pieces, padded pitch) while the previous item
@@ -28,9 +25,10 @@
 //     goes through the input buffer once it has been read (one barrier pair per item); bins
 //     k1..k1+TB-1 of one k2 leave as one 128-byte run, as streaming stores or (optionally, one
 //     channel) staged and written by TMA tensor stores (cp.async.bulk.tensor.3d shared -> global).
-//   * the choice of the next item is made one item ahead by thread 0 from two relaxed loads that
-//     stay in flight under the input wait and conversion; a column item's completion is published
-//     by the last of the CTA's eight warps to finish it (one gpu-scope fence per item).
+//   * the queue position of the item after next is claimed two items ahead and readiness flags
+//     are read with relaxed loads that stay in flight under the conversion, so the atomic / L2
+//     round trips of the scheduling never sit on a warp's critical path; a column item's completion
+//     is published once per CTA behind the next CTA barrier.
 //   * the new timf1 bytes of a later transform are pulled into L2 by cp.async.bulk.prefetch.L2.
 #pragma once
 #include <cuda.h>
@@ -118,7 +116,10 @@ LB_D void pipe_wait(const int* ctr, int target, int* err)
   (void)ld_acquire(ctr);
 }
 
-// mbarrier wait that cannot hang either (a tensor map the TMA unit rejects would never complete_tx)
+// mbarrier wait that cannot hang either (a tensor map the TMA unit rejects would never complete_tx).
+// The waiting warp is suspended by the hardware (try_wait with a time hint) and looks at the clock
+// and the error flag only every few hundred wake-ups: warps that wait for late input must not take
+// issue slots or L2 bandwidth from the other CTA of the SM.
 LB_D void pipe_mbar_wait(uint64_t* bar, uint32_t parity, int* err)
 {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
@@ -127,14 +128,16 @@ LB_D void pipe_mbar_wait(uint64_t* bar, uint32_t parity, int* err)
                : "=r"(done) : "r"(a), "r"(parity) : "memory");
   if (done) return;
   const long long t0 = clock64();
-  for (;;) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  for (uint32_t n = 1;; n++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity), "r"(20000u) : "memory");
     if (done) return;
-    if (*reinterpret_cast<volatile int*>(err)) return;
-    if (clock64() - t0 > (1ll << 31)) {
-      atomicExch(err, 2);
-      return;
+    if ((n & 255u) == 0) {
+      if (*reinterpret_cast<volatile int*>(err)) return;
+      if (clock64() - t0 > (1ll << 31)) {
+        atomicExch(err, 2);
+        return;
+      }
     }
   }
 }
@@ -311,23 +314,16 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   __shared__ int a_arrived;                      // warps of this CTA that have stored their columns of the current item
   const Fft1K& p = q.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // sync block: [0] column-queue head, [1] error flag, [2] row-queue head, [3] a_mark (all transforms
-  // below it have their columns in Y), [4] b_mark (all below it have been read by their rows),
-  // [8 ..) doneA[nblocks], doneB[nblocks], then 8 debug counters
-  int* const headA = q.sync;
+  int* const head = q.sync;
   int* const err = q.sync + 1;
-  int* const headB = q.sync + 2;
-  int* const a_mark = q.sync + 3;
-  int* const b_mark = q.sync + 4;
-  int* const doneA = q.sync + 8;
-  int* const doneB = q.sync + 8 + p.nblocks;
-  int* const stats = q.sync + 8 + 2 * p.nblocks;  // only written when q.stats != 0
+  int* const doneA = q.sync + 2;
+  int* const doneB = q.sync + 2 + p.nblocks;
+  int* const stats = q.sync + 2 + 2 * p.nblocks;  // 8 counters, only written when q.stats != 0
   long long st_wait_in = 0, st_wait_dep = 0, st_wait_slot = 0;
   int st_items = 0, st_b = 0, st_b_deferred = 0, st_slot_late = 0;
   const long long st_t0 = clock64();
   const int nb = p.nblocks;
-  const int totalA = nb * C::IA, totalB = nb * C::IB;
-  const int prefer = (int)(blockIdx.x & 1);        // preferred role: even CTAs columns, odd CTAs rows
+  const int total = nb * (C::IA + C::IB);
 
   // last-pass twiddles: the five exact binary powers of w = exp(-2 pi i t / M) per lane position
   for (int i = tid; i < T1 * 5; i += 256) wbt[i] = q.Wn1[(i / 5) << (i % 5)];
@@ -339,6 +335,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   }
 
   // ---- helpers ---------------------------------------------------------------------------------
+  auto decode = [&](int i) { return pipe_decode(i < total ? i : total, nb, q.lag, C::IA, C::IB); };
   auto slot_of = [&](int b) { return b % q.nslots; };
   // fetch the input of an item into `in`; called by all threads, the item's dependency is satisfied
   auto issue_load = [&](const PipeItem& it) {
@@ -376,141 +373,92 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
     }
   };
-  // ---- scheduling -------------------------------------------------------------------------------
-  // Two queues in transform order: column items (role 0) and row items (role 1).  A column item is
-  // runnable when the Y slot of its transform has been read by the rows of transform b - nslots
-  // (b - nslots < b_mark), a row item when all columns of its transform are in Y (b < a_mark); the
-  // marks are advanced by whoever completes a transform.  A CTA peeks at the heads and the marks
-  // (relaxed loads, in flight under the input wait of the current item) and only then claims: the
-  // lowest item of its preferred kind if runnable, else of the other kind.  At the start and
-  // whenever the rows have caught up everybody transforms columns, when the Y ring is full
-  // everybody transforms rows.
-  auto runnable = [&](const PipeItem& it, int am, int bm) {
-    return it.role == 0 ? (it.b < q.nslots || it.b - q.nslots < bm) : (it.role == 1 ? it.b < am : false);
-  };
-  auto make_item = [&](int role, int idx) {
-    PipeItem it;
-    it.role = role;
-    it.ready = 0;
-    if (role == 0) { it.b = idx / C::IA; it.j = idx - it.b * C::IA; }
-    else { it.b = idx / C::IB; it.j = idx - it.b * C::IB; }
-    if (idx >= (role == 0 ? totalA : totalB)) it.role = -1;
-    return it;
-  };
-  // thread 0: given the heads of the two queues and the marks (peeked, possibly a little stale), take
-  // the lowest item of the preferred kind if it is runnable, else of the other kind.  Returns an item
-  // with ready = 1 (claimed and runnable), ready = 0 and role >= 0 (claimed, but its transform moved
-  // on during the claim and is not runnable yet: wait for it), or role = -2 (nothing runnable: nothing
-  // claimed), or role = -1 (both queues are empty).
-  auto choose = [&](int hA, int hB, int am, int bm) {
-    PipeItem nx;
-    nx.b = 0; nx.j = 0; nx.ready = 0;
-    if (hA >= totalA && hB >= totalB) { nx.role = -1; return nx; }
-    const PipeItem ca = make_item(0, hA), cb = make_item(1, hB);
-    const bool okA = ca.role >= 0 && runnable(ca, am, bm), okB = cb.role >= 0 && runnable(cb, am, bm);
-    int role = -2;
-    if (prefer == 0) role = okA ? 0 : (okB ? 1 : -2);
-    else role = okB ? 1 : (okA ? 0 : -2);
-    nx.role = role;
-    if (role < 0) return nx;
-    const int idx = atomicAdd(role == 0 ? headA : headB, 1);
-    nx = make_item(role, idx);
-    if (nx.role < 0) { nx.role = -2; return nx; }      // the queue ran out under the claim: look again
-    nx.ready = runnable(nx, am, bm) ? 1 : 0;
-    return nx;
-  };
-  // after a completion: move a mark over every leading transform whose counter is full
-  auto advance_mark = [&](int* mark, const int* done, int target) {
-    int m = ld_relaxed(mark);
-    const int m0 = m;
-    while (m < nb && ld_relaxed(done + m) >= target) m++;
-    if (m > m0) {
-      __threadfence();
-      atomicMax(mark, m);
-    }
-  };
+  // Row items fetched by TMA need only thread 0: the others arrive on the barrier at the prefetch
+  // point whatever happens; thread 0 arrives (with the byte count) when the columns are complete --
+  // at the prefetch point if they already are, else at the end of the current item after waiting.
+  // Nobody else waits for that decision; they meet the data at the next item's input barrier.
+  // (cp.async fallback and column items: all threads copy, the decision is CTA-uniform.)
   auto issue_b_tma = [&](const PipeItem& it) {      // thread 0
     const int tile = it.j / NCH;
     const int plane = slot_of(it.b) * NCH + (it.j - tile * NCH);
-    // Y was written through the generic proxy (other SMs, seen complete through a_mark): order it
-    // before the TMA unit's reads
     asm volatile("fence.proxy.async;" ::: "memory");
     mbar_expect_tx(&bar_in, 65536u);
 #pragma unroll
     for (int bx = 0; bx < N2 / C::BOX_IN; bx++)
       tma_load_3d(in + bx * (C::BOX_IN * TB * 8), &mapY, 2 * tile * TB, bx * C::BOX_IN, plane, &bar_in);
   };
-  // fetch the input of a runnable item; all threads
-  auto fetch = [&](const PipeItem& it) {
+  bool b_pending = false;                        // thread 0: a row item's TMA load is still to be issued
+  int rd_next = 0;                               // thread 0: doneA of the next row item (exact, relaxed load)
+  // prefetch point: the input buffer is free, `nxt` is known to everybody
+  auto prefetch = [&](const PipeItem& it) {
+    if (it.role < 0) return;
     if (it.role == 1 && q.tma_in) {
-      if (tid == 0) issue_b_tma(it);
-      else mbar_arrive(&bar_in);
-    } else {
+      if (tid == 0) {
+        st_b++;
+        if (rd_next >= DONE_A) issue_b_tma(it);
+        else { b_pending = true; st_b_deferred++; }
+      } else {
+        mbar_arrive(&bar_in);
+      }
+    } else if (it.ready) {
       issue_load(it);
     }
   };
-  // prefetch point: the input buffer is free and `nxt` is known to everybody
-  auto prefetch = [&](const PipeItem& it) {
-    if (it.role >= 0 && it.ready) fetch(it);
-  };
-  // end of an item whose successor could not be fixed at its publication (nothing runnable then, or
-  // a claimed item whose transform is not complete yet): wait, claim, fetch.  Start-up, a full ring
-  // with no complete transform, and the end of the call come through here.
-  auto settle = [&](PipeItem& nxt_io, int sidx) {
-    if (nxt_io.role == -1 || nxt_io.ready) return;
-    if (tid == 0) {
-      const long long w0 = clock64();
-      PipeItem it = nxt_io;
-      for (;;) {
-        const int am = ld_relaxed(a_mark), bm = ld_relaxed(b_mark);
-        if (it.role >= 0) {                           // holding a claimed item: wait for it
-          if (runnable(it, am, bm)) { it.ready = 1; break; }
-        } else {
-          it = choose(ld_relaxed(headA), ld_relaxed(headB), am, bm);
-          if (it.role == -1 || it.ready) break;
-          if (it.role >= 0) continue;                 // claimed, not runnable yet: re-check at once
-        }
-        __nanosleep(100);
-        if (*reinterpret_cast<volatile int*>(err)) { if (it.role < 0) it.role = -1; it.ready = 1; break; }
-        if (clock64() - w0 > (1ll << 31)) { atomicExch(err, 3); if (it.role < 0) it.role = -1; it.ready = 1; break; }
+  // end of an item: whatever of the next item's input could not be fetched at the prefetch point
+  auto fetch_rest = [&](const PipeItem& it) {
+    if (it.role < 0) return;
+    if (it.role == 1 && q.tma_in) {
+      if (tid == 0 && b_pending) {
+        const long long w0 = clock64();
+        pipe_wait(doneA + it.b, DONE_A, err);
+        st_wait_dep += clock64() - w0;
+        issue_b_tma(it);
+        b_pending = false;
       }
-      (void)ld_acquire(a_mark);
-      items[sidx] = it;
-      st_wait_dep += clock64() - w0;
-      st_b_deferred++;
+    } else if (!it.ready) {
+      if (tid == 0 && it.role == 1) pipe_wait(doneA + it.b, DONE_A, err);
+      __syncthreads();
+      issue_load(it);
     }
-    __syncthreads();
-    nxt_io = items[sidx];
-    if (nxt_io.role >= 0) fetch(nxt_io);
   };
 
-  if (tid == 0) {
-    PipeItem first = choose(ld_relaxed(headA), ld_relaxed(headB), 0, 0);
-    items[0] = first;
-  }
+  // thread 0: the queue position of the NEXT item is claimed at the top of an item and its result
+  // is only read right before the item's first CTA barrier, under the input wait and conversion;
+  // the exact readiness load of a row item is issued there and read at the prefetch point.  No
+  // atomic or L2 round trip is waited for where a warp would be held up.
+  if (tid == 0) items[0] = decode(atomicAdd(head, 1));       // ready = 0
   __syncthreads();
   PipeItem cur = items[0];
-  if (cur.role >= 0 && cur.ready) fetch(cur);
-  else settle(cur, 0);
+  if (cur.role == 1 && q.tma_in) {
+    if (tid == 0) { b_pending = true; } else { mbar_arrive(&bar_in); }
+  }
+  fetch_rest(cur);
   uint32_t par = 0;
   int s = 0;
   bool stores_pending = false;                   // thread 0: TMA stores may still be reading `work`
 
   while (cur.role >= 0) {
-    // ---- thread 0: queue heads and marks, in flight until barrier 1
-    int hA = 0, hB = 0, am = 0, bm = 0;
+    // ---- thread 0: claim and this item's slot counter, in flight until barrier 1
+    int nidx = 0, slot_cnt = 0;
     if (tid == 0) {
-      hA = ld_relaxed(headA);
-      hB = ld_relaxed(headB);
-      am = ld_relaxed(a_mark);
-      bm = ld_relaxed(b_mark);
+      nidx = atomicAdd(head, 1);
+      if (cur.role == 0 && cur.b >= q.nslots) slot_cnt = ld_relaxed(doneB + (cur.b - q.nslots));
     }
-    // thread 0, right before barrier 1: claim and publish the next item, and this item's slot state
+    // thread 0, right before barrier 1: publish the next item and this item's slot state
     auto publish = [&]() {
-      const PipeItem nx = choose(hA, hB, am, bm);
-      if (nx.role == 1) st_b++;
+      PipeItem nx = decode(nidx);
+      if (nx.role == 1) {
+        if (q.tma_in) {
+          rd_next = ld_relaxed(doneA + nx.b);     // read at the prefetch point
+          nx.ready = 0;
+        } else {
+          nx.ready = ld_relaxed(doneA + nx.b) >= DONE_A ? 1 : 0;
+        }
+      } else {
+        nx.ready = nx.role == 0 ? 1 : 0;
+      }
       items[s ^ 1] = nx;
-      slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || cur.b - q.nslots < bm) ? 1 : 0;
+      slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || slot_cnt >= C::IB) ? 1 : 0;
     };
     const int tile = cur.j / NCH;
     const int c = cur.j - tile * NCH;
@@ -588,7 +536,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       // ---- the slot must have been read by the rows of transform b - nslots
       if (!my_slot_ok) {
         const long long w0 = clock64();
-        if (lane == 0) pipe_wait(b_mark, cur.b - q.nslots + 1, err);
+        if (lane == 0) pipe_wait(doneB + (cur.b - q.nslots), C::IB, err);
         __syncwarp();
         if (tid == 0) { st_wait_slot += clock64() - w0; st_slot_late++; }
       }
@@ -607,10 +555,11 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         if (old == C::NWARPS - 1) {
           a_arrived = 0;
           __threadfence();
-          if (atomicAdd(doneA + cur.b, C::NWARPS) + C::NWARPS == DONE_A) advance_mark(a_mark, doneA, DONE_A);
+          atomicAdd(doneA + cur.b, C::NWARPS);
         }
       }
-      { PipeItem n2 = nxt; settle(n2, s ^ 1); cur = n2; }
+      fetch_rest(nxt);
+      cur = nxt;
     } else {
       // =============================== role B: TB rows of transform cur.b ======================
       const int r = tid & (TB - 1), t = tid / TB;
@@ -630,6 +579,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
       __syncthreads();                            // barrier 1: the Y tile is in registers; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
+      if (tid == 0) atomicAdd(doneB + cur.b, 1);  // the tile is in registers: its share of the slot may be overwritten
       // ---- row transforms: one exchange through the (now free) input buffer, all rows at once
       pass0<T2>(v);
       {
@@ -645,9 +595,6 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
       __syncthreads();                            // the input buffer is free again
       prefetch(nxt);
-      // the tile is in registers: its share of the Y slot may be overwritten (behind the item's last
-      // barrier: the atomic's round trip holds up nobody)
-      if (tid == 0 && atomicAdd(doneB + cur.b, 1) + 1 == C::IB) advance_mark(b_mark, doneB, C::IB);
       {
         float2 wb[5];
 #pragma unroll
@@ -730,7 +677,8 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           }
         }
       }
-      { PipeItem n2 = nxt; settle(n2, s ^ 1); cur = n2; }
+      fetch_rest(nxt);
+      cur = nxt;
     }
     s ^= 1;
   }

@@ -104,16 +104,15 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   const int nch = plan->nch;
   const int nb = k.nblocks;
 
-  // ---- depth of the Y ring.  Column items run ahead of the row items of the same transform by what is
-  // in flight: about one transform per IA resident CTAs on either side.  A full ring does not idle
-  // anybody (column CTAs turn to rows), so the depth only has to cover the in-flight work.
+  // ---- queue lag and ring depth: a dependency should be long satisfied when its consumer is claimed.
+  // About 2 items per resident CTA are in flight (the one computed and the one prefetched).
   const int resident = plan->sm_count * 2;
   const int per_phase = IA + IB;
-  (void)per_phase;
-  const int lag = 0;
-  const int full_slots = (resident + IA - 1) / IA + (resident + IB - 1) / IB + 2;
-  int slots = env_i("LB200_PIPE_SLOTS", full_slots);
-  if (slots < 2) slots = 2;
+  const int depth = (2 * resident + per_phase - 1) / per_phase;   // phases covered by what is in flight
+  int lag = env_i("LB200_PIPE_LAG", depth + 3);
+  if (lag < 1) lag = 1;
+  int slots = env_i("LB200_PIPE_SLOTS", lag + depth + 3);
+  if (slots < lag + 1) slots = lag + 1;
   if (slots > nb) slots = nb;                                  // a short call never wraps the ring
   if (slots < 1) slots = 1;
   if (plan->pipe_slots < slots || !plan->d_pipe_y) {
@@ -122,13 +121,14 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
     plan->pipe_slots = 0;
     // allocate the steady-state depth at once so that the map is not rebuilt call after call
     int want = slots;
-    if (want < full_slots && !getenv("LB200_PIPE_SLOTS")) want = full_slots;
+    const int full = 2 * (depth + 3);
+    if (want < full && !getenv("LB200_PIPE_SLOTS")) want = full;
     e = cudaMalloc((void**)&plan->d_pipe_y, (size_t)want * nch * N * sizeof(float2));
     if (e != cudaSuccess) return e;
     plan->pipe_slots = want;
     if (!encode_map(plan->map_y, plan->d_pipe_y, ln1, ln2, (size_t)want * nch, TB, box_in)) memset(plan->map_y, 0, sizeof(plan->map_y));
   }
-  const size_t need_ints = 8 + 2 * (size_t)nb + 8;
+  const size_t need_ints = 2 + 2 * (size_t)nb + 8;
   if (plan->pipe_sync_ints < need_ints) {
     if (plan->d_pipe_sync) {
       if (lb_fft1_pipe_status(plan)) fprintf(stderr, "[lb200] four-step pipeline: a dependency wait timed out in an earlier call\n");
@@ -145,7 +145,7 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   // head and counters start at zero; the error flag [1] is sticky until read back
   e = cudaMemsetAsync(plan->d_pipe_sync, 0, sizeof(int), plan->stream);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(plan->d_pipe_sync + 2, 0, (6 + 2 * (size_t)nb + 8) * sizeof(int), plan->stream);
+  e = cudaMemsetAsync(plan->d_pipe_sync + 2, 0, (2 * (size_t)nb + 8) * sizeof(int), plan->stream);
   if (e != cudaSuccess) return e;
   plan->pipe_checked = false;
 
@@ -211,7 +211,7 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
     // debug (LB200_PIPE_STATS=1): wait statistics of this launch, summed over CTAs (thread 0 of each)
     int st[8];
     cudaStreamSynchronize(plan->stream);
-    cudaMemcpy(st, plan->d_pipe_sync + 8 + 2 * (size_t)nb, sizeof(st), cudaMemcpyDeviceToHost);
+    cudaMemcpy(st, plan->d_pipe_sync + 2 + 2 * (size_t)nb, sizeof(st), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[lb200 pipe] grid %d lag %d slots %d: items %d, row items %d (deferred %d), late slots %d; kcycles per CTA: total %.0f, "
                     "input wait %.1f, dependency wait %.1f, slot wait %.1f\n",
             grid, lag, slots, st[0], st[1], st[2], st[3], st[7] * 1.024 / grid, st[4] * 1.024 / grid, st[5] * 1.024 / grid, st[6] * 1.024 / grid);
