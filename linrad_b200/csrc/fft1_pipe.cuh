@@ -21,14 +21,9 @@
 //     k1).  The window table is stored transposed (wT[n2][n1]) so that it is read the same way.
 //   * role B: 256/T2 adjacent rows (k1) side by side with the row index fastest across lanes; the
 //     Y tile [N2][TB] arrives by ONE TMA tensor load (cp.async.bulk.tensor.3d, mbarrier
-//     complete_tx) issued while the previous item is computed; the exchange between the two passes
-//     goes through the input buffer once it has been read (one barrier pair per item); bins
-//     k1..k1+TB-1 of one k2 leave as one 128-byte run, as streaming stores or (optionally, one
-//     channel) staged and written by TMA tensor stores (cp.async.bulk.tensor.3d shared -> global).
-//   * the queue position of the item after next is claimed two items ahead and readiness flags
-//     are read with relaxed loads that stay in flight under the conversion, so the atomic / L2
-//     round trips of the scheduling never sit on a warp's critical path; a column item's completion
-//     is published once per CTA behind the next CTA barrier.
+//     complete_tx) issued while the previous item is computed; bins k1..k1+TB-1 of one k2 leave
+//     as one 128-byte run, either as streaming stores or (one channel) staged and written by TMA
+//     tensor stores (cp.async.bulk.tensor.3d shared -> global).
 //   * the new timf1 bytes of a later transform are pulled into L2 by cp.async.bulk.prefetch.L2.
 #pragma once
 #include <cuda.h>
@@ -49,7 +44,6 @@ struct Fft1PipeK {
   int tma_in;            // role B input by TMA tensor load (else cp.async)
   int tma_out;           // role B output by TMA tensor store (one channel / zbuf only; else streaming stores)
   int prefetch_ahead;    // L2 prefetch distance in transforms (0 = off)
-  int stats;             // debug: accumulate wait statistics behind the completion counters
   uint32_t out_blk0;     // tma_out: index of the call's first output block in the tensor map's outermost dimension
   uint32_t out_nblk;     // ... and the extent of that dimension (ring wrap)
 };
@@ -82,16 +76,6 @@ LB_D void red_add(float* p, float v)
 {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-LB_D void st_global(float2* p, float2 v)
-{
-  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
-}
-LB_D int ld_relaxed(const int* p)
-{
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 LB_D int ld_acquire(const int* p)
 {
   int v;
@@ -102,24 +86,19 @@ LB_D int ld_acquire(const int* p)
 // up) the error flag is set and the wait returns; the host reports LB200_ERR_CUDA for the call.
 LB_D void pipe_wait(const int* ctr, int target, int* err)
 {
-  if (ld_relaxed(ctr) < target) {
-    const long long t0 = clock64();
-    while (ld_relaxed(ctr) < target) {
-      __nanosleep(64);
-      if (*reinterpret_cast<volatile int*>(err)) return;
-      if (clock64() - t0 > (1ll << 31)) {
-        atomicExch(err, 1);
-        return;
-      }
+  if (ld_acquire(ctr) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire(ctr) < target) {
+    __nanosleep(100);
+    if (*reinterpret_cast<volatile int*>(err)) return;
+    if (clock64() - t0 > (1ll << 31)) {
+      atomicExch(err, 1);
+      return;
     }
   }
-  (void)ld_acquire(ctr);
 }
 
-// mbarrier wait that cannot hang either (a tensor map the TMA unit rejects would never complete_tx).
-// The waiting warp is suspended by the hardware (try_wait with a time hint) and looks at the clock
-// and the error flag only every few hundred wake-ups: warps that wait for late input must not take
-// issue slots or L2 bandwidth from the other CTA of the SM.
+// mbarrier wait that cannot hang either (a tensor map the TMA unit rejects would never complete_tx)
 LB_D void pipe_mbar_wait(uint64_t* bar, uint32_t parity, int* err)
 {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
@@ -128,16 +107,14 @@ LB_D void pipe_mbar_wait(uint64_t* bar, uint32_t parity, int* err)
                : "=r"(done) : "r"(a), "r"(parity) : "memory");
   if (done) return;
   const long long t0 = clock64();
-  for (uint32_t n = 1;; n++) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(a), "r"(parity), "r"(20000u) : "memory");
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
     if (done) return;
-    if ((n & 255u) == 0) {
-      if (*reinterpret_cast<volatile int*>(err)) return;
-      if (clock64() - t0 > (1ll << 31)) {
-        atomicExch(err, 2);
-        return;
-      }
+    if (*reinterpret_cast<volatile int*>(err)) return;
+    if (clock64() - t0 > (1ll << 31)) {
+      atomicExch(err, 2);
+      return;
     }
   }
 }
@@ -159,14 +136,14 @@ struct PipeCfg {
   // role B: T2 threads per row, TB rows per item
   static constexpr int T2 = N2 / 32, LT2 = LN2 - 5, TB = NTHREADS / T2, TILES_B = N1 / TB;
   static constexpr int Q2 = 32 / T2;
-  static constexpr int ROUND_B = 8192 * 8 / Q2;            // one exchange round, all rows (the rounds lie side by side in the input buffer)
+  static constexpr int ROUND_B = 8192 * 8 / Q2;            // one exchange round, all rows
   static constexpr int STAGE_B = 32768;                    // half an output tile (TMA store rounds)
   static constexpr int BOX_IN = N2 < 256 ? N2 : 256;       // rows per input box
   static constexpr int BOX_OUT = N2 / 2 < 256 ? N2 / 2 : 256;
   static constexpr int IA = TILES_A * NCH, IB = TILES_B * NCH;   // items per transform
   static constexpr int cmax(int a, int b) { return a > b ? a : b; }
   static constexpr int IN_BYTES = (cmax(N1 * PITCH_A, 65536) + 127) & ~127;
-  static constexpr int WORK_BYTES = (cmax(NWARPS * AREA_A, STAGE_B) + 127) & ~127;
+  static constexpr int WORK_BYTES = (cmax(cmax(NWARPS * AREA_A, ROUND_B), STAGE_B) + 127) & ~127;
   static constexpr int TAB_BYTES = (T1 + T2) * 5 * 8;
   static constexpr int SMEM = IN_BYTES + WORK_BYTES + TAB_BYTES;
   static constexpr int MINB = SMEM + 1024 <= 113 * 1024 ? 2 : 1;
@@ -246,48 +223,6 @@ LB_HD void rowx_load(float2 (&u)[32], const float2* buf, int t, int r, int q)
 }
 
 #ifdef __CUDACC__
-// The general form of the rows epilogue (limited bin range, calibrated filtercorr table, tapered
-// edge bins, per-transform power rows): fft1_b's direction flip and fft1_c (fft1.c:3660-3680,
-// 4115-4200) for the 32 bins k0 + e*kstep a thread holds.  Kept out of line: only the outermost
-// tiles of an uncalibrated full-range set-up come here, and the common path keeps its registers.
-template <int NCH>
-__device__ __noinline__ void pipe_epilogue_general(float2 (&v)[32], const Fft1K& p, float* rowp, float* outb, int b, int c, int k0, int kstep, int N,
-                                                   bool keep)
-{
-  constexpr int MM = 2 * NCH;
-  float* prow = p.power_rows ? p.power_rows + (size_t)b * N : nullptr;
-#pragma unroll 4
-  for (int e = 0; e < 32; e++) {
-    const int k = k0 + kstep * e;
-    const float2 z = v[e];
-    float2 ov = p.direction < 0 ? make_float2(z.y, z.x) : make_float2(z.x, -z.y);
-    if (p.fc_mode != 0) {
-      const bool inr = (k >= p.first_point) && (k <= p.last_point);
-      if (inr) {
-        float2 f;
-        if (p.fc_mode == 2 || k < p.fc_edge || k >= N - p.fc_edge)
-          f = *reinterpret_cast<const float2*>(p.filtercorr + (size_t)k * MM + 2 * c);
-        else
-          f = make_float2(p.fc_gain, 0.0f);
-        const float re = ov.x * f.x - ov.y * f.y;      // fft1.c:4121-4125
-        const float im = ov.y * f.x + ov.x * f.y;
-        ov = make_float2(re, im);
-        const float pw = fmaf(re, re, im * im);
-        if (prow) {
-          if (NCH == 1) prow[k] = pw;
-          else red_add(prow + k, pw);                  // two channel items add into the host-zeroed row
-        } else if (rowp) {
-          red_add(rowp + k, pw);
-        }
-      } else if (prow && NCH == 1) {
-        prow[k] = 0.0f;
-      }
-    }
-    v[e] = ov;
-    if (!keep) __stcs(reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c), ov);
-  }
-}
-
 // raw frame at a shared-memory address -> the complex point of channel c (same conversions as load_iq)
 template <int FMT>
 LB_D float2 cvt_raw(const unsigned char* p, int c)
@@ -302,26 +237,19 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   using C = PipeCfg<LN1, LN2, FMT>;
   constexpr int N1 = C::N1, N2 = C::N2, N = C::N, NCH = C::NCH, MM = 2 * NCH, FRAME = C::FRAME;
   constexpr int T1 = C::T1, CW = C::CW, TA = C::TA, Q1 = C::Q1;
-  constexpr int T2 = C::T2, TB = C::TB;
-  constexpr int DONE_A = C::IA * C::NWARPS;      // doneA[b] when all columns of transform b are in Y
+  constexpr int T2 = C::T2, TB = C::TB, Q2 = C::Q2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* const in = smem_raw;
   unsigned char* const work = smem_raw + C::IN_BYTES;
   float2* const wbt = reinterpret_cast<float2*>(smem_raw + C::IN_BYTES + C::WORK_BYTES);
   __shared__ uint64_t bar_in;
   __shared__ PipeItem items[2];
-  __shared__ int slot_ok[2];
-  __shared__ int a_arrived;                      // warps of this CTA that have stored their columns of the current item
   const Fft1K& p = q.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int* const head = q.sync;
   int* const err = q.sync + 1;
   int* const doneA = q.sync + 2;
   int* const doneB = q.sync + 2 + p.nblocks;
-  int* const stats = q.sync + 2 + 2 * p.nblocks;  // 8 counters, only written when q.stats != 0
-  long long st_wait_in = 0, st_wait_dep = 0, st_wait_slot = 0;
-  int st_items = 0, st_b = 0, st_b_deferred = 0, st_slot_late = 0;
-  const long long st_t0 = clock64();
   const int nb = p.nblocks;
   const int total = nb * (C::IA + C::IB);
 
@@ -329,13 +257,18 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   for (int i = tid; i < T1 * 5; i += 256) wbt[i] = q.Wn1[(i / 5) << (i % 5)];
   for (int i = tid; i < T2 * 5; i += 256) wbt[T1 * 5 + i] = q.Wn2[(i / 5) << (i % 5)];
   if (tid == 0) {
-    a_arrived = 0;
     mbar_init(&bar_in, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
   // ---- helpers ---------------------------------------------------------------------------------
-  auto decode = [&](int i) { return pipe_decode(i < total ? i : total, nb, q.lag, C::IA, C::IB); };
+  auto claim = [&](PipeItem& dst) {               // thread 0 only
+    const int i = atomicAdd(head, 1);
+    PipeItem it = i < total ? pipe_decode(i, nb, q.lag, C::IA, C::IB) : pipe_decode(total, nb, q.lag, C::IA, C::IB);
+    if (it.role == 0) it.ready = 1;
+    else if (it.role == 1) it.ready = ld_acquire(doneA + it.b) >= C::IA * C::NWARPS ? 1 : 0;
+    dst = it;
+  };
   auto slot_of = [&](int b) { return b % q.nslots; };
   // fetch the input of an item into `in`; called by all threads, the item's dependency is satisfied
   auto issue_load = [&](const PipeItem& it) {
@@ -361,7 +294,19 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     } else {
       const int c = it.j - tile * NCH;
       const int plane = slot_of(it.b) * NCH + c;
-      {                                          // rows by cp.async (TMA loads: issue_b_tma, thread 0 alone)
+      if (q.tma_in) {
+        if (tid == 0) {
+          // Y was written through the generic proxy (other SMs, observed by an acquire): order it
+          // before the TMA unit's reads
+          asm volatile("fence.proxy.async;" ::: "memory");
+          mbar_expect_tx(&bar_in, 65536u);
+#pragma unroll
+          for (int bx = 0; bx < N2 / C::BOX_IN; bx++)
+            tma_load_3d(in + bx * (C::BOX_IN * TB * 8), &mapY, 2 * tile * TB, bx * C::BOX_IN, plane, &bar_in);
+        } else {
+          mbar_arrive(&bar_in);
+        }
+      } else {
         constexpr int CPR = TB * 8 / 16;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(q.Y + (size_t)plane * N + (size_t)tile * TB);
 #pragma unroll 4
@@ -373,93 +318,24 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
     }
   };
-  // Row items fetched by TMA need only thread 0: the others arrive on the barrier at the prefetch
-  // point whatever happens; thread 0 arrives (with the byte count) when the columns are complete --
-  // at the prefetch point if they already are, else at the end of the current item after waiting.
-  // Nobody else waits for that decision; they meet the data at the next item's input barrier.
-  // (cp.async fallback and column items: all threads copy, the decision is CTA-uniform.)
-  auto issue_b_tma = [&](const PipeItem& it) {      // thread 0
-    const int tile = it.j / NCH;
-    const int plane = slot_of(it.b) * NCH + (it.j - tile * NCH);
-    asm volatile("fence.proxy.async;" ::: "memory");
-    mbar_expect_tx(&bar_in, 65536u);
-#pragma unroll
-    for (int bx = 0; bx < N2 / C::BOX_IN; bx++)
-      tma_load_3d(in + bx * (C::BOX_IN * TB * 8), &mapY, 2 * tile * TB, bx * C::BOX_IN, plane, &bar_in);
-  };
-  bool b_pending = false;                        // thread 0: a row item's TMA load is still to be issued
-  int rd_next = 0;                               // thread 0: doneA of the next row item (exact, relaxed load)
-  // prefetch point: the input buffer is free, `nxt` is known to everybody
-  auto prefetch = [&](const PipeItem& it) {
-    if (it.role < 0) return;
-    if (it.role == 1 && q.tma_in) {
-      if (tid == 0) {
-        st_b++;
-        if (rd_next >= DONE_A) issue_b_tma(it);
-        else { b_pending = true; st_b_deferred++; }
-      } else {
-        mbar_arrive(&bar_in);
-      }
-    } else if (it.ready) {
-      issue_load(it);
-    }
-  };
-  // end of an item: whatever of the next item's input could not be fetched at the prefetch point
-  auto fetch_rest = [&](const PipeItem& it) {
-    if (it.role < 0) return;
-    if (it.role == 1 && q.tma_in) {
-      if (tid == 0 && b_pending) {
-        const long long w0 = clock64();
-        pipe_wait(doneA + it.b, DONE_A, err);
-        st_wait_dep += clock64() - w0;
-        issue_b_tma(it);
-        b_pending = false;
-      }
-    } else if (!it.ready) {
-      if (tid == 0 && it.role == 1) pipe_wait(doneA + it.b, DONE_A, err);
-      __syncthreads();
-      issue_load(it);
-    }
-  };
 
-  // thread 0: the queue position of the NEXT item is claimed at the top of an item and its result
-  // is only read right before the item's first CTA barrier, under the input wait and conversion;
-  // the exact readiness load of a row item is issued there and read at the prefetch point.  No
-  // atomic or L2 round trip is waited for where a warp would be held up.
-  if (tid == 0) items[0] = decode(atomicAdd(head, 1));       // ready = 0
+  if (tid == 0) {
+    claim(items[0]);
+    items[0].ready = 0;                          // the first item goes through the deferred path below
+  }
   __syncthreads();
   PipeItem cur = items[0];
-  if (cur.role == 1 && q.tma_in) {
-    if (tid == 0) { b_pending = true; } else { mbar_arrive(&bar_in); }
+  if (cur.role >= 0) {
+    if (cur.role == 1 && tid == 0) pipe_wait(doneA + cur.b, C::IA * C::NWARPS, err);
+    __syncthreads();
+    issue_load(cur);
   }
-  fetch_rest(cur);
   uint32_t par = 0;
   int s = 0;
   bool stores_pending = false;                   // thread 0: TMA stores may still be reading `work`
 
   while (cur.role >= 0) {
-    // ---- thread 0: claim and this item's slot counter, in flight until barrier 1
-    int nidx = 0, slot_cnt = 0;
-    if (tid == 0) {
-      nidx = atomicAdd(head, 1);
-      if (cur.role == 0 && cur.b >= q.nslots) slot_cnt = ld_relaxed(doneB + (cur.b - q.nslots));
-    }
-    // thread 0, right before barrier 1: publish the next item and this item's slot state
-    auto publish = [&]() {
-      PipeItem nx = decode(nidx);
-      if (nx.role == 1) {
-        if (q.tma_in) {
-          rd_next = ld_relaxed(doneA + nx.b);     // read at the prefetch point
-          nx.ready = 0;
-        } else {
-          nx.ready = ld_relaxed(doneA + nx.b) >= DONE_A ? 1 : 0;
-        }
-      } else {
-        nx.ready = nx.role == 0 ? 1 : 0;
-      }
-      items[s ^ 1] = nx;
-      slot_ok[s] = (cur.role != 0 || cur.b < q.nslots || slot_cnt >= C::IB) ? 1 : 0;
-    };
+    if (tid == 0) claim(items[s ^ 1]);
     const int tile = cur.j / NCH;
     const int c = cur.j - tile * NCH;
     float2 v[32];
@@ -483,7 +359,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
 #pragma unroll
         for (int e = 0; e < 32; e++) wv[e] = __ldg(wp + e * T1);
       }
-      { const long long w0 = clock64(); pipe_mbar_wait(&bar_in, par, err); if (tid == 0) { st_wait_in += clock64() - w0; st_items++; } }
+      pipe_mbar_wait(&bar_in, par, err);
       par ^= 1;
       {
         const unsigned char* rp = in + t * C::PITCH_A + col * FRAME;
@@ -495,17 +371,13 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           else v[e] = make_float2(sm.x * wv[e], sm.y * (wv[e] * dq));
         }
       }
-      if (tid == 0) {
-        if (stores_pending) {                     // role B's TMA stores read `work`: done before anybody rewrites it
-          bulk_wait_read();
-          stores_pending = false;
-        }
-        publish();
+      if (tid == 0 && stores_pending) {          // role B's TMA stores read `work`: done before anybody rewrites it
+        bulk_wait_read();
+        stores_pending = false;
       }
-      __syncthreads();                            // barrier 1: the raw tile is consumed; items[s^1] is visible
+      __syncthreads();                            // the raw tile is consumed; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
-      const int my_slot_ok = slot_ok[s];
-      prefetch(nxt);
+      if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
       // inter-step twiddle W_N^(n2*(t+T1*e)) = base * step^e, step given by exact binary powers
       const float2 tw_base = __ldg(q.Wbig + n2 * t);
       float2 tw_sb[5];
@@ -534,67 +406,62 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
       apply_power_twiddles<32>(v, tw_base, tw_sb);
       // ---- the slot must have been read by the rows of transform b - nslots
-      if (!my_slot_ok) {
-        const long long w0 = clock64();
+      if (cur.b >= q.nslots) {
         if (lane == 0) pipe_wait(doneB + (cur.b - q.nslots), C::IB, err);
         __syncwarp();
-        if (tid == 0) { st_wait_slot += clock64() - w0; st_slot_late++; }
       }
       {
         float2* Yp = q.Y + (size_t)(slot_of(cur.b) * NCH + c) * N + (size_t)n2 * N1 + t;
 #pragma unroll
-        for (int e = 0; e < 32; e++) st_global(Yp + e * T1, v[e]);
+        for (int e = 0; e < 32; e++) Yp[e * T1] = v[e];
       }
-      // completion: the last warp to get here publishes the item for all eight (release through the
-      // shared counter, one gpu-scope fence per item; nobody waits)
       __syncwarp();
       if (lane == 0) {
-        __threadfence_block();
-        const int old = atomicAdd(&a_arrived, 1);
-        __threadfence_block();
-        if (old == C::NWARPS - 1) {
-          a_arrived = 0;
-          __threadfence();
-          atomicAdd(doneA + cur.b, C::NWARPS);
-        }
+        __threadfence();
+        atomicAdd(doneA + cur.b, 1);
       }
-      fetch_rest(nxt);
+      if (nxt.role >= 0 && !nxt.ready) {
+        if (nxt.role == 1 && tid == 0) pipe_wait(doneA + nxt.b, C::IA * C::NWARPS, err);
+        __syncthreads();
+        issue_load(nxt);
+      }
       cur = nxt;
     } else {
       // =============================== role B: TB rows of transform cur.b ======================
       const int r = tid & (TB - 1), t = tid / TB;
-      { const long long w0 = clock64(); pipe_mbar_wait(&bar_in, par, err); if (tid == 0) { st_wait_in += clock64() - w0; st_items++; } }
+      pipe_mbar_wait(&bar_in, par, err);
       par ^= 1;
       {
         const float2* ip = reinterpret_cast<const float2*>(in) + t * TB + r;
 #pragma unroll
         for (int e = 0; e < 32; e++) v[e] = ip[e * (T2 * TB)];
       }
-      if (tid == 0) {
-        if (stores_pending) {
-          bulk_wait_read();
-          stores_pending = false;
-        }
-        publish();
+      if (tid == 0 && stores_pending) {
+        bulk_wait_read();
+        stores_pending = false;
       }
-      __syncthreads();                            // barrier 1: the Y tile is in registers; items[s^1] is visible
+      __syncthreads();                            // the Y tile is in registers; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
-      if (tid == 0) atomicAdd(doneB + cur.b, 1);  // the tile is in registers: its share of the slot may be overwritten
-      // ---- row transforms: one exchange through the (now free) input buffer, all rows at once
+      if (tid == 0) {                             // this tile's share of the slot may be overwritten
+        __threadfence();
+        atomicAdd(doneB + cur.b, 1);
+      }
+      if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
+      // ---- row transforms
       pass0<T2>(v);
       {
-        float2* buf = reinterpret_cast<float2*>(in);
+        float2* buf = reinterpret_cast<float2*>(work);
         float2 u[32];
 #pragma unroll
-        for (int qq = 0; qq < C::Q2; qq++) rowx_store<T2, TB>(v, buf + qq * (T2 * T2 * TB), t, r, qq);
-        __syncthreads();
-#pragma unroll
-        for (int qq = 0; qq < C::Q2; qq++) rowx_load<T2, TB>(u, buf + qq * (T2 * T2 * TB), t, r, qq);
+        for (int qq = 0; qq < Q2; qq++) {
+          if (qq > 0) __syncthreads();            // the previous round has been read
+          rowx_store<T2, TB>(v, buf, t, r, qq);
+          __syncthreads();
+          rowx_load<T2, TB>(u, buf, t, r, qq);
+        }
 #pragma unroll
         for (int e = 0; e < 32; e++) v[e] = u[e];
       }
-      __syncthreads();                            // the input buffer is free again
-      prefetch(nxt);
       {
         float2 wb[5];
 #pragma unroll
@@ -610,7 +477,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         if (!use_tma_out) {
           float2* zp = p.zbuf + ((size_t)(b - p.zb_first) * NCH + c) * N + k1 + (size_t)t * N1;
 #pragma unroll
-          for (int e = 0; e < 32; e++) st_global(zp + (size_t)e * (T2 * N1), v[e]);
+          for (int e = 0; e < 32; e++) zp[(size_t)e * (T2 * N1)] = v[e];
         }
       } else {
         const int group_size = p.power_rows ? 1 : p.avg1num;
@@ -625,32 +492,51 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         const bool fast = p.fc_mode == 1 && !p.power_rows && klo >= p.first_point && khi + N1 * (N2 - 1) <= p.last_point &&
                           p.fc_edge <= N1 && klo >= p.fc_edge && khi < N1 - p.fc_edge;
         if (fast) {
-          const float gain = p.fc_gain;           // fft1.c:4121-4125 with filtercorr = (gain, 0)
-          if (p.direction < 0) {
+          const float gain = p.fc_gain;
+          const bool rev = p.direction < 0;
+          float* rp = rowp ? rowp + k1 + N1 * t : nullptr;
+          float2* op = reinterpret_cast<float2*>(outb + (size_t)(k1 + N1 * t) * MM + 2 * c);
 #pragma unroll
-            for (int e = 0; e < 32; e++) v[e] = make_float2(v[e].y * gain, v[e].x * gain);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; e++) v[e] = make_float2(v[e].x * gain, -v[e].y * gain);
-          }
-          if (rowp) {
-            float* rp = rowp + k1 + N1 * t;
-#pragma unroll
-            for (int e = 0; e < 32; e++) red_add(rp + e * (N1 * T2), fmaf(v[e].x, v[e].x, v[e].y * v[e].y));
-          }
-          if (!use_tma_out) {
-            float2* op = reinterpret_cast<float2*>(outb + (size_t)(k1 + N1 * t) * MM + 2 * c);
-#pragma unroll
-            for (int e = 0; e < 32; e++) __stcs(op + (size_t)e * (N1 * T2 * NCH), v[e]);
+          for (int e = 0; e < 32; e++) {
+            const float2 z = v[e];
+            const float re = (rev ? z.y : z.x) * gain;           // fft1.c:4121-4125 with filtercorr = (gain, 0)
+            const float im = (rev ? z.x : -z.y) * gain;
+            if (rp) red_add(rp + e * (N1 * T2), fmaf(re, re, im * im));
+            v[e] = make_float2(re, im);
+            if (!use_tma_out) __stcs(op + (size_t)e * (N1 * T2 * NCH), v[e]);
           }
         } else {
-          // through a copy: only the copy's address is taken, v itself stays in registers
-          float2 tmp[32];
+          float* prow = p.power_rows ? p.power_rows + (size_t)b * N : nullptr;
 #pragma unroll
-          for (int e = 0; e < 32; e++) tmp[e] = v[e];
-          pipe_epilogue_general<NCH>(tmp, p, rowp, outb, b, c, k1 + N1 * t, N1 * T2, N, use_tma_out);
-#pragma unroll
-          for (int e = 0; e < 32; e++) v[e] = tmp[e];
+          for (int e = 0; e < 32; e++) {
+            const int k = k1 + N1 * (t + T2 * e);
+            const float2 z = v[e];
+            float2 ov = p.direction < 0 ? make_float2(z.y, z.x) : make_float2(z.x, -z.y);
+            if (p.fc_mode != 0) {
+              const bool inr = (k >= p.first_point) && (k <= p.last_point);
+              if (inr) {
+                float2 f;
+                if (p.fc_mode == 2 || k < p.fc_edge || k >= N - p.fc_edge)
+                  f = *reinterpret_cast<const float2*>(p.filtercorr + (size_t)k * MM + 2 * c);
+                else
+                  f = make_float2(p.fc_gain, 0.0f);
+                const float re = ov.x * f.x - ov.y * f.y;      // fft1.c:4121-4125
+                const float im = ov.y * f.x + ov.x * f.y;
+                ov = make_float2(re, im);
+                const float pw = fmaf(re, re, im * im);
+                if (prow) {
+                  if (NCH == 1) prow[k] = pw;
+                  else red_add(prow + k, pw);                  // two channel items add into the host-zeroed row
+                } else if (rowp) {
+                  red_add(rowp + k, pw);
+                }
+              } else if (prow && NCH == 1) {
+                prow[k] = 0.0f;
+              }
+            }
+            v[e] = ov;
+            if (!use_tma_out) __stcs(reinterpret_cast<float2*>(outb + (size_t)k * MM + 2 * c), ov);
+          }
         }
       }
       if (use_tma_out) {
@@ -660,10 +546,8 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         float2* st = reinterpret_cast<float2*>(work) + t * TB + r;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          if (h > 0) {
-            if (tid == 0) bulk_wait_read();                    // round 0 has left `work`
-            __syncthreads();
-          }
+          if (h > 0 && tid == 0) bulk_wait_read();           // round 0 has left `work`
+          __syncthreads();                                   // exchange reads / round 0 are over
 #pragma unroll
           for (int e = 0; e < 16; e++) st[e * (T2 * TB)] = v[16 * h + e];
           fence_async_smem();
@@ -677,22 +561,16 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           }
         }
       }
-      fetch_rest(nxt);
+      if (nxt.role >= 0 && !nxt.ready) {
+        if (nxt.role == 1 && tid == 0) pipe_wait(doneA + nxt.b, C::IA * C::NWARPS, err);
+        __syncthreads();
+        issue_load(nxt);
+      }
       cur = nxt;
     }
     s ^= 1;
   }
   if (tid == 0) bulk_wait_all();                  // shared memory must outlive the last TMA store
-  if (tid == 0 && q.stats) {
-    atomicAdd(stats + 0, st_items);
-    atomicAdd(stats + 1, st_b);
-    atomicAdd(stats + 2, st_b_deferred);
-    atomicAdd(stats + 3, st_slot_late);
-    atomicAdd(stats + 4, (int)(st_wait_in >> 10));
-    atomicAdd(stats + 5, (int)(st_wait_dep >> 10));
-    atomicAdd(stats + 6, (int)(st_wait_slot >> 10));
-    atomicAdd(stats + 7, (int)((clock64() - st_t0) >> 10));
-  }
 }
 #endif  // __CUDACC__
 

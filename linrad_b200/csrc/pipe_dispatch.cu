@@ -108,10 +108,9 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   // About 2 items per resident CTA are in flight (the one computed and the one prefetched).
   const int resident = plan->sm_count * 2;
   const int per_phase = IA + IB;
-  const int depth = (2 * resident + per_phase - 1) / per_phase;   // phases covered by what is in flight
-  int lag = env_i("LB200_PIPE_LAG", depth + 3);
+  int lag = env_i("LB200_PIPE_LAG", (3 * resident / 2 + per_phase - 1) / per_phase + 1);
   if (lag < 1) lag = 1;
-  int slots = env_i("LB200_PIPE_SLOTS", lag + depth + 3);
+  int slots = env_i("LB200_PIPE_SLOTS", 2 * lag);
   if (slots < lag + 1) slots = lag + 1;
   if (slots > nb) slots = nb;                                  // a short call never wraps the ring
   if (slots < 1) slots = 1;
@@ -121,14 +120,14 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
     plan->pipe_slots = 0;
     // allocate the steady-state depth at once so that the map is not rebuilt call after call
     int want = slots;
-    const int full = 2 * (depth + 3);
+    const int full = 2 * ((3 * resident / 2 + per_phase - 1) / per_phase + 1);
     if (want < full && !getenv("LB200_PIPE_SLOTS")) want = full;
     e = cudaMalloc((void**)&plan->d_pipe_y, (size_t)want * nch * N * sizeof(float2));
     if (e != cudaSuccess) return e;
     plan->pipe_slots = want;
     if (!encode_map(plan->map_y, plan->d_pipe_y, ln1, ln2, (size_t)want * nch, TB, box_in)) memset(plan->map_y, 0, sizeof(plan->map_y));
   }
-  const size_t need_ints = 2 + 2 * (size_t)nb + 8;
+  const size_t need_ints = 2 + 2 * (size_t)nb;
   if (plan->pipe_sync_ints < need_ints) {
     if (plan->d_pipe_sync) {
       if (lb_fft1_pipe_status(plan)) fprintf(stderr, "[lb200] four-step pipeline: a dependency wait timed out in an earlier call\n");
@@ -145,7 +144,7 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   // head and counters start at zero; the error flag [1] is sticky until read back
   e = cudaMemsetAsync(plan->d_pipe_sync, 0, sizeof(int), plan->stream);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(plan->d_pipe_sync + 2, 0, (2 * (size_t)nb + 8) * sizeof(int), plan->stream);
+  e = cudaMemsetAsync(plan->d_pipe_sync + 2, 0, 2 * (size_t)nb * sizeof(int), plan->stream);
   if (e != cudaSuccess) return e;
   plan->pipe_checked = false;
 
@@ -161,13 +160,12 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   q.nslots = slots;
   q.lag = lag;
   q.prefetch_ahead = env_i("LB200_PIPE_PREFETCH", 3);
-  q.stats = env_i("LB200_PIPE_STATS", 0);
   static const unsigned char zero_map[128] = {0};
   const bool have_map_y = memcmp(plan->map_y, zero_map, 128) != 0;
   q.tma_in = (have_map_y && env_i("LB200_PIPE_TMA_IN", 1)) ? 1 : 0;
   // ---- output by TMA tensor stores: planar targets only (one channel, or the packed spectrum of real input)
   q.tma_out = 0;
-  if (env_i("LB200_PIPE_TMA_OUT", 0) && (k.zbuf || nch == 1)) {   // measured: streaming stores are a little faster (profiles/r2_notes.txt)
+  if (env_i("LB200_PIPE_TMA_OUT", 0) && (k.zbuf || nch == 1)) {   // measured: streaming stores are faster (0.150 vs 0.167 ms at configs[3], profiles/r2_notes.txt)
     void* base = k.zbuf ? (void*)k.zbuf : (void*)k.out;
     const size_t planes = k.zbuf ? plan->zbuf_elems / N : ((size_t)k.out_mask + 1) / (2 * N);
     if (planes >= 1 && (k.zbuf || (k.out_pa % (2 * N)) == 0)) {
@@ -207,14 +205,5 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   e = fn(ln, nullptr, &q, &my, &mo, plan->sm_count, &grid, plan->stream);
   if (e != cudaSuccess) return e;
   plan->launches += 1;
-  if (q.stats) {
-    // debug (LB200_PIPE_STATS=1): wait statistics of this launch, summed over CTAs (thread 0 of each)
-    int st[8];
-    cudaStreamSynchronize(plan->stream);
-    cudaMemcpy(st, plan->d_pipe_sync + 2 + 2 * (size_t)nb, sizeof(st), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[lb200 pipe] grid %d lag %d slots %d: items %d, row items %d (deferred %d), late slots %d; kcycles per CTA: total %.0f, "
-                    "input wait %.1f, dependency wait %.1f, slot wait %.1f\n",
-            grid, lag, slots, st[0], st[1], st[2], st[3], st[7] * 1.024 / grid, st[4] * 1.024 / grid, st[5] * 1.024 / grid, st[6] * 1.024 / grid);
-  }
   return cudaSuccess;
 }

@@ -130,7 +130,7 @@ def test_pipe_equals_legacy_direction_and_range(direction, first_x, xpoints):
     # bins outside the display range keep the raw fft1_b scale: compare on the common energy
     e_all = rel_rms(f1, f0)
     per_block = [rel_rms(f1[b], f0[b]) for b in range(nblocks)]
-    assert e_all <= 6e-7, (e_all, per_block)
+    assert e_all <= 2e-6, (e_all, per_block)     # (the post kernel's in-place pair update doubles the rounding steps)
     assert np.array_equal(p1 == 0, p0 == 0), "bins outside the range must stay untouched in both"
     # Two correctly rounded float32 transforms of different structure differ, in every bin, by a few
     # ulps of the STRONGEST line of the whole spectrum -- which may lie outside the display range
@@ -153,9 +153,10 @@ VARIANTS = [
     dict(LB200_PIPE_TMA_IN=0, LB200_PIPE_TMA_OUT=0),
     dict(LB200_PIPE_TMA_IN=1, LB200_PIPE_TMA_OUT=0),
     dict(LB200_PIPE_TMA_IN=0, LB200_PIPE_TMA_OUT=1),
-    dict(LB200_PIPE_SLOTS=2),
-    dict(LB200_PIPE_SLOTS=3, LB200_PIPE_PREFETCH=0),
-    dict(LB200_PIPE_SLOTS=64),
+    dict(LB200_PIPE_TMA_IN=1, LB200_PIPE_TMA_OUT=1),
+    dict(LB200_PIPE_LAG=1, LB200_PIPE_SLOTS=2),
+    dict(LB200_PIPE_LAG=2, LB200_PIPE_SLOTS=3, LB200_PIPE_PREFETCH=0),
+    dict(LB200_PIPE_LAG=40, LB200_PIPE_SLOTS=64),
 ]
 
 
