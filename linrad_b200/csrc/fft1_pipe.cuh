@@ -76,6 +76,12 @@ LB_D void red_add(float* p, float v)
 {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+LB_D int ld_relaxed(const int* p)
+{
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 LB_D int ld_acquire(const int* p)
 {
   int v;
@@ -86,19 +92,16 @@ LB_D int ld_acquire(const int* p)
 // up) the error flag is set and the wait returns; the host reports LB200_ERR_CUDA for the call.
 LB_D void pipe_wait(const int* ctr, int target, int* err)
 {
-  if (ld_acquire(ctr) >= target) return;
+  if (ld_relaxed(ctr) >= target) return;
   const long long t0 = clock64();
-  while (ld_acquire(ctr) < target) {
-    __nanosleep(100);
+  while (ld_relaxed(ctr) < target) {
+    __nanosleep(64);
     if (*reinterpret_cast<volatile int*>(err)) return;
-    if (clock64() - t0 > (1ll << 31)) {
-      atomicExch(err, 1);
-      return;
-    }
+    if (clock64() - t0 > (1ll << 31)) { atomicExch(err, 1); return; }
   }
 }
 
-// mbarrier wait that cannot hang either (a tensor map the TMA unit rejects would never complete_tx)
+// mbarrier wait that cannot hang either; the waiting warp is suspended by the hardware
 LB_D void pipe_mbar_wait(uint64_t* bar, uint32_t parity, int* err)
 {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
@@ -107,14 +110,13 @@ LB_D void pipe_mbar_wait(uint64_t* bar, uint32_t parity, int* err)
                : "=r"(done) : "r"(a), "r"(parity) : "memory");
   if (done) return;
   const long long t0 = clock64();
-  for (;;) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  for (uint32_t n = 1;; n++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity), "r"(20000u) : "memory");
     if (done) return;
-    if (*reinterpret_cast<volatile int*>(err)) return;
-    if (clock64() - t0 > (1ll << 31)) {
-      atomicExch(err, 2);
-      return;
+    if ((n & 255u) == 0) {
+      if (*reinterpret_cast<volatile int*>(err)) return;
+      if (clock64() - t0 > (1ll << 31)) { atomicExch(err, 2); return; }
     }
   }
 }
@@ -244,6 +246,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   float2* const wbt = reinterpret_cast<float2*>(smem_raw + C::IN_BYTES + C::WORK_BYTES);
   __shared__ uint64_t bar_in;
   __shared__ PipeItem items[2];
+  __shared__ int a_arrived;
   const Fft1K& p = q.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int* const head = q.sync;
@@ -257,6 +260,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   for (int i = tid; i < T1 * 5; i += 256) wbt[i] = q.Wn1[(i / 5) << (i % 5)];
   for (int i = tid; i < T2 * 5; i += 256) wbt[T1 * 5 + i] = q.Wn2[(i / 5) << (i % 5)];
   if (tid == 0) {
+    a_arrived = 0;
     mbar_init(&bar_in, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -266,7 +270,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     const int i = atomicAdd(head, 1);
     PipeItem it = i < total ? pipe_decode(i, nb, q.lag, C::IA, C::IB) : pipe_decode(total, nb, q.lag, C::IA, C::IB);
     if (it.role == 0) it.ready = 1;
-    else if (it.role == 1) it.ready = ld_acquire(doneA + it.b) >= C::IA * C::NWARPS ? 1 : 0;
+    else if (it.role == 1) it.ready = ld_relaxed(doneA + it.b) >= C::IA * C::NWARPS ? 1 : 0;
     dst = it;
   };
   auto slot_of = [&](int b) { return b % q.nslots; };
@@ -417,8 +421,14 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
       __syncwarp();
       if (lane == 0) {
-        __threadfence();
-        atomicAdd(doneA + cur.b, 1);
+        __threadfence_block();
+        const int old = atomicAdd(&a_arrived, 1);
+        __threadfence_block();
+        if (old == C::NWARPS - 1) {
+          a_arrived = 0;
+          __threadfence();
+          atomicAdd(doneA + cur.b, C::NWARPS);
+        }
       }
       if (nxt.role >= 0 && !nxt.ready) {
         if (nxt.role == 1 && tid == 0) pipe_wait(doneA + nxt.b, C::IA * C::NWARPS, err);
@@ -443,7 +453,6 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       __syncthreads();                            // the Y tile is in registers; items[s^1] is visible
       const PipeItem nxt = items[s ^ 1];
       if (tid == 0) {                             // this tile's share of the slot may be overwritten
-        __threadfence();
         atomicAdd(doneB + cur.b, 1);
       }
       if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
@@ -492,18 +501,23 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         const bool fast = p.fc_mode == 1 && !p.power_rows && klo >= p.first_point && khi + N1 * (N2 - 1) <= p.last_point &&
                           p.fc_edge <= N1 && klo >= p.fc_edge && khi < N1 - p.fc_edge;
         if (fast) {
-          const float gain = p.fc_gain;
-          const bool rev = p.direction < 0;
-          float* rp = rowp ? rowp + k1 + N1 * t : nullptr;
-          float2* op = reinterpret_cast<float2*>(outb + (size_t)(k1 + N1 * t) * MM + 2 * c);
+          const float gain = p.fc_gain;           // fft1.c:4121-4125 with filtercorr = (gain, 0)
+          if (p.direction < 0) {
 #pragma unroll
-          for (int e = 0; e < 32; e++) {
-            const float2 z = v[e];
-            const float re = (rev ? z.y : z.x) * gain;           // fft1.c:4121-4125 with filtercorr = (gain, 0)
-            const float im = (rev ? z.x : -z.y) * gain;
-            if (rp) red_add(rp + e * (N1 * T2), fmaf(re, re, im * im));
-            v[e] = make_float2(re, im);
-            if (!use_tma_out) __stcs(op + (size_t)e * (N1 * T2 * NCH), v[e]);
+            for (int e = 0; e < 32; e++) v[e] = make_float2(v[e].y * gain, v[e].x * gain);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e++) v[e] = make_float2(v[e].x * gain, -v[e].y * gain);
+          }
+          if (rowp) {
+            float* rp = rowp + k1 + N1 * t;
+#pragma unroll
+            for (int e = 0; e < 32; e++) red_add(rp + e * (N1 * T2), fmaf(v[e].x, v[e].x, v[e].y * v[e].y));
+          }
+          if (!use_tma_out) {
+            float2* op = reinterpret_cast<float2*>(outb + (size_t)(k1 + N1 * t) * MM + 2 * c);
+#pragma unroll
+            for (int e = 0; e < 32; e++) __stcs(op + (size_t)e * (N1 * T2 * NCH), v[e]);
           }
         } else {
           float* prow = p.power_rows ? p.power_rows + (size_t)b * N : nullptr;
