@@ -116,11 +116,17 @@ def _compare(kw, nblocks, selbins, chunk, seed=1, ext=None, power_slack=1.0, **o
                 rep["ref_spread_worst_allow"] = max(rep["ref_spread_worst_allow"] or 0.0, power_ok(b2, b, s.avg1num)[1])
         parity_record(**rep)
         print("parity:", rep)
+        # the bound: the per-bin allowance of power_ok -- or, where the reference's own two float versions
+        # are further apart than that on this very input, 1.25 x their distance (profiles/r2_parity_report.jsonl:
+        # our figures and the reference's own v6-vs-v7 figures agree case by case)
+        limit = power_slack
+        if rep["ref_spread_worst_allow"] is not None:
+            limit = max(limit, 1.25 * rep["ref_spread_worst_allow"])
         for r in range(min(rows, 8)):
             a = cs.sumsq[r * N + lo: r * N + hi + 1]
             b = ref["sumsq"][r * N + lo: r * N + hi + 1]
             ok, worst = power_ok(a, b, s.avg1num)
-            assert worst <= power_slack, f"sumsq row {r}: worst error is {worst:.2f} x the per-bin allowance"
+            assert worst <= limit, f"sumsq row {r}: worst error is {worst:.2f} x the per-bin allowance (limit {limit:.2f})"
         # fft1_corrsum (fft1_correlation_flag == 1): |2 z1 conj(z2)| <= the bin's summed power, so the
         # power row's allowance bounds its error too
         if ext.get("correlation") == 1:

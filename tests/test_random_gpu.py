@@ -66,7 +66,7 @@ def _case(seed):
 @pytest.mark.parametrize("seed", range(96))
 def test_random_configuration(seed):
     kw, nblocks, sel, chunk, over, ext, M = _case(seed)
-    # power_slack: the per-bin power allowance is a 4..5 sigma bound on the difference of two
-    # correctly rounded float32 transforms; over ~10^5 bins of 48 random set-ups a few excursions
-    # just beyond it are expected (the hand-picked cases keep the plain bound)
-    _compare(kw, nblocks, sel, chunk, seed=seed + 1, ext=ext, power_slack=1.5, **over)
+    # same bound as the hand-picked cases (no extra slack): the per-bin allowance, or 1.25 x the distance of
+    # the reference's own two float versions on the same input where that is larger (seed 23: ours 1.18,
+    # the reference's own 1.26 allowances; profiles/r2_parity_report.jsonl)
+    _compare(kw, nblocks, sel, chunk, seed=seed + 1, ext=ext, **over)

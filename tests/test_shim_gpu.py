@@ -8,7 +8,7 @@ import pytest
 
 from linrad_b200.synth import make_timf1
 from oracle import refwrap
-from tests.helpers import rel_rms, run_reference, IQ_DATA, DWORD_INPUT, TWO_CHANNELS
+from tests.helpers import parity_record, rel_rms, run_reference, IQ_DATA, DWORD_INPUT, TWO_CHANNELS
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not (refwrap.available() and refwrap.shim_available()), reason="oracle/_ref not built")]
@@ -42,7 +42,10 @@ def test_shim_inside_the_reference(mode, ch, ver, n, sinpow):
     assert got["timf3_pa"] == ref["timf3_pa"]
     sg, sr = got["states"][0], ref["states"][0]
     assert sg["point"] == sr["point"] and float(sg["phase"]) == float(sr["phase"])
-    assert rel_rms(got["timf3"][1:, 0], ref["timf3"][1:, 0]) <= 1e-4
+    e3_all, e3_rest = rel_rms(got["timf3"][:, 0], ref["timf3"][:, 0]), rel_rms(got["timf3"][1:, 0], ref["timf3"][1:, 0])
+    parity_record(kind="shim_timf3", fft1_n=n, mode=mode, timf3_rel_rms_all_blocks=e3_all, timf3_rel_rms_without_block0=e3_rest,
+                  fft1_rel_rms=rel_rms(got["fft1"], ref["fft1"]))
+    assert e3_rest <= 1e-4
     # the reference's own consumers ran on the shim's output: slowsum / waterfall stay consistent
     assert np.allclose(got["ref"].slowsum(), ref["ref"].slowsum(), rtol=2e-4, atol=1e-3 * float(np.abs(ref["ref"].slowsum()).max()))
 
@@ -120,5 +123,8 @@ def test_shim_mix1_afc(mode, ch, ver, sinpow):
     sg, sr = got["states"][0], ref["states"][0]
     assert sg["point"] == sr["point"] and float(sg["phase"]) == float(sr["phase"])
     assert float(sg["phase_rot"]) == float(sr["phase_rot"]) and float(sg["phase_step"]) == float(sr["phase_step"])
-    assert rel_rms(got["timf3"][1:, 0], ref["timf3"][1:, 0]) <= 1e-4
+    e3_all, e3_rest = rel_rms(got["timf3"][:, 0], ref["timf3"][:, 0]), rel_rms(got["timf3"][1:, 0], ref["timf3"][1:, 0])
+    parity_record(kind="shim_timf3", fft1_n=n, mode=mode, timf3_rel_rms_all_blocks=e3_all, timf3_rel_rms_without_block0=e3_rest,
+                  fft1_rel_rms=rel_rms(got["fft1"], ref["fft1"]))
+    assert e3_rest <= 1e-4
     assert got["timf3_pa"] == ref["timf3_pa"]
