@@ -651,6 +651,11 @@ def main():
         reference_arm(args, rank, world)
         return
 
+    # ONE JSON line on stdout: libraries that print to file descriptor 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -709,7 +714,8 @@ def main():
             "roofline": m["roofline"], "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": m["launches"],
             "clocks": m["clocks"], "per_config": per_config,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

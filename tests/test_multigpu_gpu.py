@@ -29,5 +29,9 @@ def test_reduce_and_time_block_sharding_on_real_devices(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):                  # keep the whole transcript of the ranks (pytest abbreviates it)
+        with open(os.path.join(out_dir, f"mgpu_worker_{world}.log"), "w") as f:
+            f.write(r.stdout + "\n---- stderr ----\n" + r.stderr)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert "MGPU_OK" in r.stdout, r.stdout[-3000:]
