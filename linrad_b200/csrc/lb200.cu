@@ -537,6 +537,12 @@ static int ensure_mirror(lb200_plan* plan, HostMirror& m, const void* host, size
 {
   if (m.d && m.bytes == bytes && m.host == host) return 0;
   if (m.d) { cudaFree(m.d); m.d = nullptr; }
+  // the mirror moves to another host buffer: the old one is no longer ours to keep page-locked (it may
+  // have been freed already, and a stale registration would clash with whatever is mapped there next)
+  if (m.host && m.host != host && plan->registered.count(m.host)) {
+    if (cudaHostUnregister(const_cast<void*>(m.host)) != cudaSuccess) cudaGetLastError();
+    plan->registered.erase(m.host);
+  }
   LB_CUDA(cudaMalloc(&m.d, bytes));
   LB_CUDA(cudaMemsetAsync(m.d, 0, bytes, plan->stream));
   m.bytes = bytes;

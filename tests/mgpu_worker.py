@@ -55,11 +55,12 @@ def main():
     d_out = torch.zeros(rows * N, dtype=torch.float32, device=dev)
     stream = torch.cuda.ExternalStream(plan.stream, device=dev)
     raws = []
+    timf1, fft1, sumsq, _, _ = rings(s, nblocks, 0)          # Linrad-style: the rings live as long as the plan
     for rd in range(rounds):
         raw = make_timf1(s.input_mode, 1, N, nblocks, s.fft1_new_points, seed=1000 * rd + rank)
         rawb = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)[: nblocks * s.timf1_blockbytes]
         raws.append(rawb)
-        timf1, fft1, sumsq, _, _ = rings(s, nblocks, 0)
+        timf1[:] = 0
         timf1[: rawb.size] = rawb
         plan.fft1_host(timf1=timf1, ref=0, nblocks=nblocks, fft1=fft1, fft1_pa=0, apply_fc=True, sumsq=sumsq, sumsq_pa=0, counter=0)
         mine.append(sumsq[: rows * N].copy())
