@@ -605,6 +605,45 @@ def run_e2e(wl, args, dist):
         lazy["api"] = "same, fft1_float kept in the device mirror (LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE); fft1_sumsq and timf3 come back"
         e2e["spectrum_on_device"] = lazy
 
+    # what the host interface itself can carry with every GPU of the run copying at the same time:
+    # bare pinned-memory copies, both directions at once (e2e above is bound by this, not by the kernels)
+    try:
+        nbytes = 256 << 20
+        hp_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        hp_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dv_in = torch.empty(nbytes, dtype=torch.uint8, device=wl.dev)
+        dv_out = torch.empty(nbytes, dtype=torch.uint8, device=wl.dev)
+        s_a, s_b = torch.cuda.Stream(device=wl.dev), torch.cuda.Stream(device=wl.dev)
+
+        def both(reps):
+            for _ in range(reps):
+                with torch.cuda.stream(s_a):
+                    dv_in.copy_(hp_in, non_blocking=True)
+                with torch.cuda.stream(s_b):
+                    hp_out.copy_(dv_out, non_blocking=True)
+            s_a.synchronize()
+            s_b.synchronize()
+
+        both(1)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        both(4)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=wl.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        gbs = 4 * nbytes / dt / 1e9
+        bytes_per_sample = (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / (Be * spt)
+        e2e["pcie_probe"] = {"concurrent_gpus": world, "GBps_per_gpu_each_direction": gbs, "GBps_all_gpus_both_directions": 2 * gbs * world,
+                             "e2e_bytes_per_sample": bytes_per_sample,
+                             "e2e_ceiling_Msamples_per_s": 2 * gbs * 1e9 * world / bytes_per_sample / 1e6,
+                             "what": "256 MiB pinned copies H2D and D2H at the same time on every GPU of the run, slowest rank"}
+        del hp_in, hp_out, dv_in, dv_out
+    except Exception as ex:
+        e2e["pcie_probe"] = {"error": str(ex)}
+
     # Linrad-sized calls: one transform per call, as the shim issues them (real-time use)
     def one_block(i):
         plan2.fft1_host(timf1=h_timf1.numpy(), ref=(i % Be) * s.timf1_blockbytes, nblocks=1, fft1=h_fft1.numpy(),

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LB200_ABI_VERSION 2
+#define LB200_ABI_VERSION 3
 
 /* ui.rx_input_mode bits used by the path (globdef.h:277-279) */
 #define LB200_DWORD_INPUT 1
@@ -95,6 +95,9 @@ typedef struct lb200_config {
   float pg_ch2_c1, pg_ch2_c2;   /* pol_graph.c:165-173; (1, 0) = off.  Two-channel IQ input only:
                                    ch2 *= (c1 - i c2) on bins [first_sym_point, N - first_sym_point)
                                    (fft1.c:4064-4080) */
+  /* --- second FFT front end (ABI 3) -------------------------------------------------- */
+  const float *fft1_inverted_window; /* fft1_inverted_window, make_window(3,...) buf.c:1313: fft1_size/2+1 floats, or
+                                   NULL (no second FFT, or FIRST_FFT_SINPOW 0 / 2 where it is not used) */
 } lb200_config;
 
 /* Ring-buffer descriptor: base pointer + power-of-two size (the reference's xxx_mask+1).
@@ -183,6 +186,28 @@ int lb200_fft1(lb200_plan *plan, const lb200_fft1_args *a);
 /* fft1_mix1_fixed (mix1.c:995) incl. set_mix1_phases (mix1.c:781) and do_mix1 (mix1.c:55) */
 int lb200_mix1_dev(lb200_plan *plan, const lb200_mix1_args *a);
 int lb200_mix1(lb200_plan *plan, const lb200_mix1_args *a);
+
+/* ---- second FFT front end: make_timf2 (timf2.c:31-208), float path (swfloat) ----------------------
+ * Every transform of fft1_float is split by liminfo (0: weak, else strong; fft1_update_liminfo keeps
+ * that table on the host, sellim.c:738), both halves are transformed back to the time domain
+ * (fft1back_one / fft1back_two) and laid into the timf2 ring by fft1back_fp_finish (timf2.c:970):
+ * sample layout [weak re, im, strong re, im] (two channels: [w1 re, im, w2 re, im, s1 re, im, s2 re, im]),
+ * |weak|^2 into timf2_pwr_float.  With the sin^2 window the first half of a transform is ADDED onto
+ * the second half of its predecessor, which the previous call left at timf2_pa.  fft1 sizes 2^7..2^14. */
+typedef struct lb200_timf2_args {
+  lb200_ring fft1_float;        /* source spectra (post fft1_c) */
+  uint32_t fft1_px;             /* float index of the first transform (timf2.c:37) */
+  int nblocks;
+  const float *liminfo;         /* fft1_size floats: HOST for lb200_make_timf2, DEVICE for lb200_make_timf2_dev */
+  lb200_ring timf2_float;       /* timf2_float, timf2_mask+1 floats */
+  float *timf2_pwr_float;       /* timf2_float.size / (4*rx_rf_channels) floats */
+  uint32_t timf2_pa;            /* timf2_pa on entry; the caller advances it by nblocks*timf2_input_block */
+  int first_bckfft_att_n;       /* genparm[FIRST_BCKFFT_ATT_N] */
+  int *fft1_lowlevel_points;    /* HOST, optional: fft1_lowlevel_points (the same for every transform of the call;
+                                   host-buffer variant only) */
+} lb200_timf2_args;
+int lb200_make_timf2_dev(lb200_plan *plan, const lb200_timf2_args *a);
+int lb200_make_timf2(lb200_plan *plan, const lb200_timf2_args *a);
 
 /* ---- wide-graph consumers of fft1_sumsq -------------------------------------------------- */
 /* what update_fft1_slowsum / fft1_waterfall read from the wide-graph setup (WG_PARMS

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LB200_LIB") or os.path.join(_HERE, "liblinrad_b200.so")   # LB200_LIB: A/B builds of the same ABI
 
-LB200_ABI_VERSION = 2
+LB200_ABI_VERSION = 3
 ERR = {0: "OK", 3100: "NO_DEVICE", 3101: "CUDA", 3102: "BAD_CONFIG", 3103: "UNSUPPORTED", 3104: "BAD_ARG",
        1211: "MIX1_RANGE_LOW", 1212: "MIX1_RANGE_HIGH"}
 
@@ -24,6 +24,7 @@ EXPORTS = ["lb200_create", "lb200_destroy", "lb200_strerror", "lb200_abi_version
            "lb200_fft1_waterfall", "lb200_expand_rawdat_dev", "lb200_expand_rawdat", "lb200_widen_24bit_dev",
            "lb200_widen_24bit", "lb200_raw_header_parse", "lb200_raw_block_bytes",
            "lb200_widen_8bit_dev", "lb200_widen_8bit", "lb200_float_to_int32_dev", "lb200_float_to_int32",
+           "lb200_make_timf2_dev", "lb200_make_timf2",
            "lb200_reduce_create", "lb200_reduce_export", "lb200_reduce_connect", "lb200_reduce_push",
            "lb200_reduce_rows_released", "lb200_reduce_sum", "lb200_reduce_result_ready", "lb200_reduce_synchronize",
            "lb200_reduce_destroy"]
@@ -49,6 +50,7 @@ class Config(C.Structure):
         ("fftx_points_per_hz", C.c_float), ("mix1_lowest_fq", C.c_float), ("mix1_highest_fq", C.c_float),
         ("max_batch", C.c_int),
         ("pg_ch2_c1", C.c_float), ("pg_ch2_c2", C.c_float),
+        ("fft1_inverted_window", C.c_void_p),
     ]
 
 
@@ -90,6 +92,14 @@ class Mix1Args(C.Structure):
     _fields_ = [
         ("fft1_float", Ring), ("fft1_px", C.c_uint32), ("nblocks", C.c_int), ("no_of_channels", C.c_int),
         ("state", C.POINTER(Mix1State)), ("timf3_float", Ring), ("timf3_pa", C.c_uint32),
+    ]
+
+
+class Timf2Args(C.Structure):
+    _fields_ = [
+        ("fft1_float", Ring), ("fft1_px", C.c_uint32), ("nblocks", C.c_int), ("liminfo", C.c_void_p),
+        ("timf2_float", Ring), ("timf2_pwr_float", C.c_void_p), ("timf2_pa", C.c_uint32),
+        ("first_bckfft_att_n", C.c_int), ("fft1_lowlevel_points", C.POINTER(C.c_int)),
     ]
 
 
@@ -166,14 +176,14 @@ def _ptr(a):
 
 
 def make_config(setup, device=0, window=None, filtercorr=None, max_batch=0, foldcorr=None, sample_shift=0,
-                pg_ch2=(1.0, 0.0)):
+                pg_ch2=(1.0, 0.0), inverted_window=None):
     """Build an lb200_config from a sizing.PathSetup.  `window`/`filtercorr` override the tables
     (e.g. with the reference's own, taken from the oracle in the parity tests).  Returns
     (Config, keepalive) -- keepalive holds the numpy tables until lb200_create has copied them."""
     keep = dict(
         window=_f32(window if window is not None else setup.window),
         filtercorr=_f32(filtercorr if filtercorr is not None else setup.filtercorr),
-        foldcorr=_f32(foldcorr),
+        foldcorr=_f32(foldcorr), invwin=_f32(inverted_window),
         fqwin=_f32(setup.mix1_fqwin), mwin=_f32(setup.mix1_window),
         cos2=_f32(setup.mix1_cos2win), sin2=_f32(setup.mix1_sin2win))
     cfg = Config()
@@ -203,6 +213,7 @@ def make_config(setup, device=0, window=None, filtercorr=None, max_batch=0, fold
     cfg.mix1_highest_fq = setup.mix1_highest_fq
     cfg.max_batch = max_batch
     cfg.pg_ch2_c1, cfg.pg_ch2_c2 = float(pg_ch2[0]), float(pg_ch2[1])
+    cfg.fft1_inverted_window = _ptr(keep["invwin"])
     return cfg, keep
 
 
@@ -210,10 +221,11 @@ class Plan:
     """Thin handle around lb200_plan."""
 
     def __init__(self, setup, device=0, window=None, filtercorr=None, max_batch=0, foldcorr=None, sample_shift=0,
-                 pg_ch2=(1.0, 0.0)):
+                 pg_ch2=(1.0, 0.0), inverted_window=None):
         self.lib = load_library()
         self.setup = setup
-        self.cfg, keep = make_config(setup, device, window, filtercorr, max_batch, foldcorr, sample_shift, pg_ch2)
+        self.cfg, keep = make_config(setup, device, window, filtercorr, max_batch, foldcorr, sample_shift, pg_ch2,
+                                     inverted_window)
         h = C.c_void_p()
         rc = self.lib.lb200_create(C.byref(self.cfg), C.byref(h))
         if rc:
@@ -368,6 +380,27 @@ def widen_24bit_host(plan, pcm):
     if rc:
         raise Lb200Error(rc, "lb200_widen_24bit")
     return out
+
+
+def make_timf2_host(plan, *, fft1, fft1_px, nblocks, liminfo, timf2, timf2_pwr, timf2_pa, att_n=0):
+    """make_timf2 (timf2.c:31) on numpy host rings; returns fft1_lowlevel_points"""
+    a = Timf2Args()
+    a.fft1_float = Ring(fft1.ctypes.data, fft1.size)
+    a.fft1_px = fft1_px
+    a.nblocks = nblocks
+    lim = np.ascontiguousarray(liminfo, np.float32)
+    a.liminfo = lim.ctypes.data
+    a.timf2_float = Ring(timf2.ctypes.data, timf2.size)
+    a.timf2_pwr_float = timf2_pwr.ctypes.data
+    a.timf2_pa = timf2_pa
+    a.first_bckfft_att_n = att_n
+    low = C.c_int(0)
+    a.fft1_lowlevel_points = C.pointer(low)
+    plan.lib.lb200_make_timf2.argtypes = [C.c_void_p, C.POINTER(Timf2Args)]
+    rc = plan.lib.lb200_make_timf2(plan.h, C.byref(a))
+    if rc:
+        raise Lb200Error(rc, "lb200_make_timf2")
+    return low.value
 
 
 def widen_8bit_host(plan, pcm8):

@@ -237,6 +237,25 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
     }
   }
 
+  // ---- make_timf2: inverted window and the pass-1 twiddle table of the back transform
+  if (cfg->fft1_inverted_window)
+    if ((rc = upload(plan, (void**)&plan->d_invwin, cfg->fft1_inverted_window, sizeof(float) * (plan->N / 2 + 1)))) return fail(rc);
+  if (cfg->fft1_n > 10 && cfg->fft1_n <= 14) {
+    if (plan->d_tab1) {
+      plan->d_tab1_any = plan->d_tab1;
+    } else {
+      const int R0 = plan->N >> 10;
+      std::vector<float4> tab((size_t)16 * R0);
+      for (int q = 0; q < 16; q++)
+        for (int k = 0; k < R0; k++) {
+          const double a0 = -2.0 * LB_PI * (double)(k * (2 * q)) / (32.0 * R0);
+          const double a1 = -2.0 * LB_PI * (double)(k * (2 * q + 1)) / (32.0 * R0);
+          tab[(size_t)q * R0 + k] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
+        }
+      if ((rc = upload(plan, (void**)&plan->d_tab1_any, tab.data(), sizeof(float4) * tab.size()))) return fail(rc);
+    }
+  }
+
   // ---- mix1 (buf.c:1297-1300, prepare_mixer buf.c:55-111)
   if (cfg->mix1_n > 0) {
     if (cfg->mix1_n < 3 || cfg->mix1_n > (plan->nch == 2 ? 12 : 13) || cfg->mix1_n > cfg->fft1_n) return fail(LB200_ERR_UNSUPPORTED);
@@ -262,6 +281,7 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
   }
   // the plan keeps its own copies; never dereference the caller's table pointers again
   plan->cfg.fft1_window = nullptr; plan->cfg.fft1_filtercorr = nullptr; plan->cfg.fft1_foldcorr = nullptr;
+  plan->cfg.fft1_inverted_window = nullptr;
   plan->cfg.mix1_fqwin = nullptr; plan->cfg.mix1_window = nullptr; plan->cfg.mix1_cos2win = nullptr; plan->cfg.mix1_sin2win = nullptr;
   *out = plan;
   return LB200_OK;
@@ -282,7 +302,8 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   void* ptrs[] = {plan->d_foldcorr, plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
                   plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wn1, plan->d_Wn2,
                   plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2, plan->d_zbuf, plan->d_Wre, plan->d_powtmp,
-                  plan->d_wT, plan->d_pipe_y, plan->d_pipe_sync};
+                  plan->d_wT, plan->d_pipe_y, plan->d_pipe_sync, plan->d_invwin, plan->d_timf2_tmp,
+                  (plan->d_tab1_any != plan->d_tab1) ? (void*)plan->d_tab1_any : nullptr};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < lb200_plan::kJobSlots; i++) {
     if (plan->d_mixjobs[i]) cudaFree(plan->d_mixjobs[i]);
@@ -293,6 +314,7 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   free_mirror(plan->m_timf3); free_mirror(plan->m_power); free_mirror(plan->m_corrsum); free_mirror(plan->m_corr); free_mirror(plan->m_xy);
   free_mirror(plan->m_wg_sumsq); free_mirror(plan->m_wg_slowsum); free_mirror(plan->m_wg_wsum); free_mirror(plan->m_wg_yfac);
   free_mirror(plan->m_wg_waterf); free_mirror(plan->m_codec_in); free_mirror(plan->m_codec_out);
+  free_mirror(plan->m_t2_fft1); free_mirror(plan->m_t2_ring); free_mirror(plan->m_t2_pwr); free_mirror(plan->m_t2_lim);
   for (cudaEvent_t e : plan->events) cudaEventDestroy(e);
   if (plan->s_in) cudaStreamDestroy(plan->s_in);
   if (plan->s_out) cudaStreamDestroy(plan->s_out);

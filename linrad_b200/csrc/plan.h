@@ -75,6 +75,12 @@ struct lb200_plan {
   const void* map_out_base = nullptr;
   size_t map_out_planes = 0;
   bool pipe_checked = false;   // the error flag of the last launch has been read back
+  // make_timf2 (timf2.cuh)
+  float* d_invwin = nullptr;        // fft1_inverted_window (windows other than none / sin^2)
+  float4* d_tab1_any = nullptr;     // pass-1 twiddles of the 32-points-per-thread plan (any input kind)
+  float2* d_timf2_tmp = nullptr;    // timf2_tmp of a whole call
+  size_t timf2_tmp_elems = 0;
+  HostMirror m_t2_fft1, m_t2_ring, m_t2_pwr, m_t2_lim;
   // mix1 per-call staging: a small ring of pinned/device job tables so that consecutive
   // calls never wait for each other on the host
   static constexpr int kJobSlots = 4;

@@ -541,3 +541,70 @@ static double afc_track(int ss, long tno)
 
 /* timing leg for bench.py --impl reference / cpu_baseline: same loop, no copies */
 int ref_process_timed(const void *data, int nblocks) { return ref_process(data, nblocks, NULL, NULL, NULL); }
+
+/* ---------------------------------------------------------------------------------------------
+ * Second-FFT front end: the reference's own make_timf2 (timf2.c:31-208: strong/weak split by
+ * liminfo, fft1back_one/two, fft1back_fp_finish) run on the fft1_float blocks the harness holds.
+ * Sizes and tables as buf.c does them for the float path (swfloat): buf.c:396-401 (timf2 ring),
+ * 962-1036 (buffers), 1313-1325 (inverted window, back scramble, back table), 1499-1508 (initial
+ * contents).  genparm[SECOND_FFT_ENABLE] stays 0: the harness calls make_timf2 itself. */
+void make_timf2(void);
+static int timf2_ready;
+int ref_timf2_setup(int att_n, int pow_size)
+{
+  int i;
+  genparm[FIRST_BCKFFT_VERNR] = 0;                       /* fft_cntrl rows 10 / 13: the C back transforms */
+  genparm[FIRST_BCKFFT_ATT_N] = att_n;
+  swfloat = 1;
+  swmmx_fft2 = 0;
+  ampinfo_flag = 0;
+  yieldflag_timf2_fft1 = 0;
+  fft1_split_float = zalloc(sizeof(float) * 4 * ui.rx_rf_channels * fft1_size + 64);
+  liminfo = zalloc(sizeof(float) * 2 * fft1_size + 64);
+  fft1_back_scramble = zalloc(sizeof(short int) * fft1_size + 64);
+  make_permute(fft_cntrl[FFT1_BCKCURMODE].permute, fft1_n, fft1_size, fft1_back_scramble);
+  if (fft_cntrl[FFT1_CURMODE].permute == 2 || fft_cntrl[FFT1_CURMODE].real2complex == 1) {
+    fft1_backtab = zalloc(sizeof(COSIN_TABLE) * fft1_size / 2 + 64);
+    make_sincos(0, fft1_size, fft1_backtab);
+  } else {
+    fft1_backtab = fft1tab;
+  }
+  if (genparm[FIRST_FFT_SINPOW] != 0 && genparm[FIRST_FFT_SINPOW] != 2) {
+    fft1_inverted_window = zalloc(sizeof(float) * (16 + fft1_size / 2) + 64);
+    make_window(3, fft1_size, genparm[FIRST_FFT_SINPOW], fft1_inverted_window);
+  }
+  timf2pow_size = pow_size;
+  timf2pow_mask = timf2pow_size - 1;
+  timf2_size = 4 * ui.rx_rf_channels * timf2pow_size;
+  timf2_mask = timf2_size - 1;
+  timf2_float = zalloc(sizeof(float) * timf2_size + 64);
+  timf2_pwr_float = zalloc(sizeof(float) * timf2pow_size + 64);
+  for (i = 0; i < timf2pow_size; i++) timf2_pwr_float[i] = 0.5F;
+  timf2_input_block = (fft1_size - fft1_interleave_points) * 4 * ui.rx_rf_channels;
+  timf2_pa = 0;
+  fft1_lowlevel_fraction = .75F;
+  /* timf2_tmp needs 4*channels*fft1_size floats; the fft1 scratch behind fftw_tmp is too small for it */
+  timf2_tmp = zalloc(sizeof(float) * 4 * ui.rx_rf_channels * fft1_size + 256);
+  timf2_ready = 1;
+  return 0;
+}
+void ref_set_liminfo(const float *v) { memcpy(liminfo, v, sizeof(float) * fft1_size); }
+/* make_timf2 on `nblocks` consecutive blocks of fft1_float starting at float index px */
+int ref_make_timf2(int px, int nblocks)
+{
+  int b;
+  if (!timf2_ready) return -1;
+  fft1_px = px & fft1_mask;
+  for (b = 0; b < nblocks; b++) make_timf2();
+  return ref_last_lirerr;
+}
+float *ref_timf2_float(void) { return timf2_float; }
+float *ref_timf2_pwr_float(void) { return timf2_pwr_float; }
+int ref_timf2_size(void) { return timf2_size; }
+int ref_timf2_pa(void) { return timf2_pa; }
+int ref_timf2_input_block(void) { return timf2_input_block; }
+float ref_lowlevel_fraction(void) { return fft1_lowlevel_fraction; }
+int ref_lowlevel_points(void) { return fft1_lowlevel_points; }
+float *ref_inverted_window(void) { return fft1_inverted_window; }
+void ref_set_fft1_block(int block_index, const float *v) { memcpy(&fft1_float[(size_t)block_index * fft1_block], v, sizeof(float) * fft1_block); }
+

@@ -76,3 +76,7 @@ void new_fft1_averages(int ptr, int ia, int ib)
     }
   }
 }
+/* timf2.c: the short-int / MMX halves of the split and the back transform are never taken (swfloat = 1) */
+void split_one(void) { lirerr(99001); }
+void split_two(void) { lirerr(99002); }
+

@@ -137,6 +137,37 @@ class RefOracle:
             raise RuntimeError(f"reference raised lirerr({rc})")
         return dict(fft1=fft1, raw=rawout, timf3=t3)
 
+    # ---- second FFT front end: the reference's own make_timf2 on the blocks held in fft1_float
+    def timf2_setup(self, att_n=0, pow_size=1 << 16):
+        self.lib.ref_timf2_float.restype = C.POINTER(C.c_float)
+        self.lib.ref_timf2_pwr_float.restype = C.POINTER(C.c_float)
+        self.lib.ref_inverted_window.restype = C.POINTER(C.c_float)
+        self.lib.ref_lowlevel_fraction.restype = C.c_float
+        self.lib.ref_timf2_setup(att_n, pow_size)
+        self.timf2_pow_size = pow_size
+
+    def set_fft1_block(self, index, values):
+        v = np.ascontiguousarray(values, np.float32)
+        self.lib.ref_set_fft1_block(index, v.ctypes.data_as(C.c_void_p))
+
+    def make_timf2(self, liminfo, px, nblocks):
+        lim = np.ascontiguousarray(liminfo, np.float32)
+        self.lib.ref_set_liminfo(lim.ctypes.data_as(C.c_void_p))
+        rc = self.lib.ref_make_timf2(px, nblocks)
+        if rc != 0:
+            raise RuntimeError(f"reference raised lirerr({rc})")
+        n = self.lib.ref_timf2_size()
+        t2 = np.ctypeslib.as_array(self.lib.ref_timf2_float(), shape=(n,)).copy()
+        pw = np.ctypeslib.as_array(self.lib.ref_timf2_pwr_float(), shape=(self.timf2_pow_size,)).copy()
+        return dict(timf2=t2, pwr=pw, timf2_pa=self.lib.ref_timf2_pa(), input_block=self.lib.ref_timf2_input_block(),
+                    lowlevel_points=self.lib.ref_lowlevel_points(), lowlevel_fraction=float(self.lib.ref_lowlevel_fraction()))
+
+    def inverted_window(self):
+        p = self.lib.ref_inverted_window()
+        if not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(self.fft1_size // 2 + 1,)).copy()
+
     def process_timed(self, raw, nblocks):
         return self.lib.ref_process_timed(raw.ctypes.data, nblocks)
 
