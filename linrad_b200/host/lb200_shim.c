@@ -12,6 +12,7 @@
  *   lb200_shim_fft1_b()        in place of fft1_b()           (wcw.c:1036, do_fft1b wcw.c:500)
  *   lb200_shim_fft1_c()        in place of fft1_c()           (wcw.c:338,366,423,1069,1098)
  *   lb200_shim_mix1_fixed()    in place of fft1_mix1_fixed()  (wcw.c:1700,1712)
+ *   lb200_shim_make_timf2()    in place of make_timf2()       (timf2.c:31; second FFT enabled, float path)
  *
  * fft1_b and fft1_c stay two calls on two threads, as in Linrad, but the arithmetic of both
  * runs in ONE kernel: lb200_shim_fft1_b asks the library for the filter-corrected spectrum and
@@ -111,6 +112,9 @@ c.mix1_highest_fq=mix1_highest_fq;
 c.max_batch=1;
 c.pg_ch2_c1=pg_ch2_c1;
 c.pg_ch2_c2=pg_ch2_c2;
+/* second FFT (float path): the inverted window of fft1back_fp_finish, buf.c:1005,1313 */
+c.fft1_inverted_window=NULL;
+if(genparm[FIRST_FFT_SINPOW] != 0 && genparm[FIRST_FFT_SINPOW] != 2)c.fft1_inverted_window=fft1_inverted_window;
 shim_power=malloc((size_t)(fft1n_mask+1)*(size_t)fft1_size*sizeof(float));
 if(shim_power == NULL){shim_fail(LB200_ERR_BAD_CONFIG); return -1;}
 shim_xy=NULL;
@@ -345,3 +349,34 @@ timf3_pa=(timf3_pa+timf3_block)&timf3_mask;         /* mix1.c:1093-1095 */
 fft1_nx=(fft1_nx+1)&fft1n_mask;
 fft1_px=(fft1_px+fft1_block)&fft1_mask;
 }
+
+/* make_timf2 (timf2.c:31-208), float path: strong/weak split by liminfo, back transform and */
+/* fft1back_fp_finish on the GPU; the index bookkeeping of timf2.c:117-118, 205-207 stays here. */
+void lb200_shim_make_timf2(void)
+{
+lb200_timf2_args a;
+int rc;
+if(!swfloat){shim_fail(LB200_ERR_UNSUPPORTED); return;}   /* the short-int / MMX back transform is not reproduced */
+memset(&a,0,sizeof(a));
+a.fft1_float.base=fft1_float;
+a.fft1_float.size=(size_t)fft1_mask+1;
+a.fft1_px=(uint32_t)fft1_px;
+a.nblocks=1;
+a.liminfo=liminfo;
+a.timf2_float.base=timf2_float;
+a.timf2_float.size=(size_t)timf2_mask+1;
+a.timf2_pwr_float=timf2_pwr_float;
+a.timf2_pa=(uint32_t)timf2_pa;
+a.first_bckfft_att_n=genparm[FIRST_BCKFFT_ATT_N];
+a.fft1_lowlevel_points=&fft1_lowlevel_points;
+pthread_mutex_lock(&shim_lock[0]);
+rc=lb200_make_timf2(shim_plan[0],&a);
+pthread_mutex_unlock(&shim_lock[0]);
+if(rc != LB200_OK){shim_fail(rc); return;}
+fft1_px=(fft1_px+fft1_block)&fft1_mask;
+fft1_nx=(fft1_nx+1)&fft1n_mask;
+fft1_lowlevel_fraction=0.02*(49*fft1_lowlevel_fraction+fft1_lowlevel_points/
+             ((float)(fft1_last_point-fft1_first_point)));
+timf2_pa=(timf2_pa+timf2_input_block)&timf2_mask;
+}
+

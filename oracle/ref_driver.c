@@ -75,7 +75,10 @@ extern void (*lb200_shim_afc_tables)(int ss);
 #define HOT_FFT1_B lb200_shim_fft1_b
 #define HOT_FFT1_C lb200_shim_fft1_c
 #define HOT_MIX1_FIXED lb200_shim_mix1_fixed
+void lb200_shim_make_timf2(void);
+#define HOT_MAKE_TIMF2 lb200_shim_make_timf2
 #else
+#define HOT_MAKE_TIMF2 make_timf2
 #define HOT_FFT1_B fft1_b
 #define HOT_FFT1_C fft1_c
 #define HOT_MIX1_FIXED fft1_mix1_fixed
@@ -586,6 +589,11 @@ int ref_timf2_setup(int att_n, int pow_size)
   /* timf2_tmp needs 4*channels*fft1_size floats; the fft1 scratch behind fftw_tmp is too small for it */
   timf2_tmp = zalloc(sizeof(float) * 4 * ui.rx_rf_channels * fft1_size + 256);
   timf2_ready = 1;
+#ifdef LB200_USE_SHIM
+  /* the plan is created from Linrad's tables: fft1_inverted_window exists only now */
+  lb200_shim_close();
+  if (lb200_shim_open(1) != 0) return ref_last_lirerr ? ref_last_lirerr : -1;
+#endif
   return 0;
 }
 void ref_set_liminfo(const float *v) { memcpy(liminfo, v, sizeof(float) * fft1_size); }
@@ -595,7 +603,7 @@ int ref_make_timf2(int px, int nblocks)
   int b;
   if (!timf2_ready) return -1;
   fft1_px = px & fft1_mask;
-  for (b = 0; b < nblocks; b++) make_timf2();
+  for (b = 0; b < nblocks; b++) HOT_MAKE_TIMF2();
   return ref_last_lirerr;
 }
 float *ref_timf2_float(void) { return timf2_float; }

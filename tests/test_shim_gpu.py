@@ -128,3 +128,34 @@ def test_shim_mix1_afc(mode, ch, ver, sinpow):
                   fft1_rel_rms=rel_rms(got["fft1"], ref["fft1"]))
     assert e3_rest <= 1e-4
     assert got["timf3_pa"] == ref["timf3_pa"]
+
+
+@pytest.mark.parametrize("sinpow,ch,mode,ver", [(2, 1, IQ_DATA, 6), (3, 1, IQ_DATA, 6), (2, 2, IQ_DATA | TWO_CHANNELS, 7)])
+def test_shim_make_timf2(sinpow, ch, mode, ver):
+    """make_timf2 inside the compiled reference through lb200_shim_make_timf2: timf2_float, timf2_pwr_float,
+    timf2_pa, fft1_lowlevel_points and fft1_lowlevel_fraction against the reference's own timf2.c"""
+    from oracle.refwrap import RefOracle
+    n, nblocks = 10, 6
+    N = 1 << n
+    kw = dict(input_mode=mode, rf_channels=ch, ad_speed=96000, fft1_n=n, mix1_red_n=3, sinpow=sinpow)
+    rng = np.random.default_rng(5)
+    liminfo = np.zeros(N, np.float32)
+    for _ in range(5):
+        a = int(rng.integers(0, N - 30))
+        liminfo[a: a + int(rng.integers(1, 30))] = float(rng.uniform(0.01, 1.0))
+    res = []
+    for shim in (False, True):
+        r = RefOracle(fft1_version=ver, n_sel=0, max_fft1n=8, through_shim=shim, **kw)
+        P = r.lib.ref_new_points()
+        raw = make_timf1(mode, ch, N, nblocks, P, seed=7)
+        rawb = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)[: nblocks * r.timf1_blockbytes]
+        r.process(rawb)
+        r.timf2_setup(1, 1 << 14)
+        res.append(r.make_timf2(liminfo, 0, nblocks))
+    ref, got = res
+    assert got["timf2_pa"] == ref["timf2_pa"] and got["lowlevel_points"] == ref["lowlevel_points"]
+    assert got["lowlevel_fraction"] == ref["lowlevel_fraction"]
+    assert rel_rms(got["timf2"], ref["timf2"]) <= 1e-5
+    assert np.abs(got["pwr"].astype(np.float64) - ref["pwr"]).max() <= 2e-5 * np.abs(ref["pwr"]).max()
+    assert np.array_equal(got["timf2"] == 0, ref["timf2"] == 0)
+
