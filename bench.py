@@ -289,6 +289,43 @@ def cpu_baseline_quick(workload, seconds=12.0):
         return {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
 
+def cufft_reference_path(workload, seconds=6.0, batch_n=4):
+    """Informational: the reference's OWN GPU support (fft_cntrl row 19 "CUDA", fft1.c:3531-3553: window on the
+    CPU, pageable cudaMemcpy in, cufftExecC2C of 2^gpu.fft1_batch_n transforms, cudaMemcpy out, CPU post-processing,
+    fft1_c and mix1 on the CPU), compiled from the reference's files with -DHAVE_CUFFT=1 and run on this GPU, one
+    thread.  Only 1-channel IQ set-ups have that row (fft1var.c:78); other workloads report the 1-channel case."""
+    try:
+        from oracle import refwrap
+        if not (refwrap.available() and refwrap.cufft_available()):
+            return None
+        kw, _, selbins, _ = WORKLOADS["cfg4" if workload == "cfg5" else workload]
+        note = ""
+        if kw["input_mode"] != sizing.IQ_DATA or kw["rf_channels"] != 1:
+            kw, _, selbins, _ = WORKLOADS["cfg1"]
+            note = "; this workload's input format has no CUDA row in the reference: configs[0] timed instead"
+        s = sizing.PathSetup(**kw)
+        r = refwrap.RefOracle(fft1_version=19, n_sel=len(selbins), cufft=True, gpu_batch_n=batch_n, **kw)
+        for i, fb in enumerate(selbins):
+            r.set_selfreq(i, s.selfreq_for_bin(fb))
+        calls = 2
+        blocks = calls << batch_n
+        raw = make_timf1(s.input_mode, s.rf_channels, s.fft1_size, blocks, s.fft1_new_points, seed=9)
+        r.process_timed(raw, calls)
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < seconds:
+            r.process_timed(raw, calls)
+            n += blocks
+        dt = time.perf_counter() - t0
+        v = n * samples_per_transform(s) / dt / 1e6
+        return {"value": v, "unit": "Msamples/s", "cores": 1, "kind": "reference, built with its own -DHAVE_CUFFT=1",
+                "fft1_size": s.fft1_size, "mix1_selections": len(selbins), "batch": 1 << batch_n,
+                "sample": f"{n} transforms in {dt:.1f} s: fft1_b row 19 (fft1win_gpu + cudaMemcpy + cufftExecC2C x{1 << batch_n} + "
+                          f"cudaMemcpy + swap) + fft1_c + fft1_waterfall + fft1_mix1_fixed, one host thread" + note}
+    except Exception as e:
+        return {"value": None, "unit": "Msamples/s", "sample": f"unavailable: {e}"}
+
+
 # ------------------------------------------------------------------------------------------
 class GpuWorkload:
     """device-resident rings of S receiver streams on one GPU and one pass of the hot path over them"""
@@ -733,8 +770,10 @@ def main():
             torch.cuda.empty_cache()
 
     cpu = None
+    ref_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_quick(args.workload)
+        ref_gpu = cufft_reference_path(args.workload)
 
     if rank == 0:
         kw, _, selbins, default_batch = WORKLOADS[args.workload]
@@ -750,7 +789,7 @@ def main():
                        "step": "fft1 (+fft1_c power) -> slowsum + waterfall -> mix1 per stream, then the sum of the streams' spectra",
                        "l2": f"working set per pass {(S * B * (s.timf1_blockbytes + 4 * s.fft1_block)) >> 20} MiB > 126 MiB L2, no flush needed",
                        "spectrum_reduction": reduce_kind},
-            "roofline": m["roofline"], "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": m["launches"],
+            "roofline": m["roofline"], "cpu_baseline": cpu, "cufft_reference_path": ref_gpu, "e2e": e2e, "gpu_launches": m["launches"],
             "clocks": m["clocks"], "per_config": per_config,
         }
         sys.stdout.flush()

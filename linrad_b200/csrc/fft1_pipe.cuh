@@ -27,7 +27,14 @@
 //   * the new timf1 bytes of a later transform are pulled into L2 by cp.async.bulk.prefetch.L2.
 #pragma once
 #include <cuda.h>
+#ifdef LB_PIPE_STATS
+#include <cstdio>
+#endif
 #include "fft1_fused.cuh"
+
+#ifndef LB_PIPE_THREADS
+#define LB_PIPE_THREADS 256     // threads per CTA = 32-point slices per item
+#endif
 
 namespace lb {
 
@@ -127,7 +134,8 @@ struct PipeCfg {
   static constexpr int N1 = 1 << LN1, N2 = 1 << LN2, N = N1 * N2;
   static constexpr int FRAME = FmtInfo<FMT>::FRAME, NCH = FmtInfo<FMT>::NCH;
   static constexpr bool REAL = FmtInfo<FMT>::REAL;
-  static constexpr int NTHREADS = 256, NWARPS = 8;
+  static constexpr int NTHREADS = LB_PIPE_THREADS, NWARPS = NTHREADS / 32;
+  static constexpr int TILE_BYTES = 32 * NTHREADS * 8;      // one item: 32 points per thread
   // role A: T1 lanes per column, CW columns per warp, TA columns per item
   static constexpr int T1 = N1 / 32, LT1 = LN1 - 5, CW = 32 / T1, TA = NWARPS * CW, TILES_A = N2 / TA;
   static constexpr int Q1 = 32 / T1;                       // pass 0 does Q1 radix-T1 butterflies per lane
@@ -138,17 +146,17 @@ struct PipeCfg {
   // role B: T2 threads per row, TB rows per item
   static constexpr int T2 = N2 / 32, LT2 = LN2 - 5, TB = NTHREADS / T2, TILES_B = N1 / TB;
   static constexpr int Q2 = 32 / T2;
-  static constexpr int ROUND_B = 8192 * 8 / Q2;            // one exchange round, all rows
-  static constexpr int STAGE_B = 32768;                    // half an output tile (TMA store rounds)
+  static constexpr int ROUND_B = TILE_BYTES / Q2;           // one exchange round, all rows
+  static constexpr int STAGE_B = TILE_BYTES / 2;                   // half an output tile (TMA store rounds)
   static constexpr int BOX_IN = N2 < 256 ? N2 : 256;       // rows per input box
   static constexpr int BOX_OUT = N2 / 2 < 256 ? N2 / 2 : 256;
   static constexpr int IA = TILES_A * NCH, IB = TILES_B * NCH;   // items per transform
   static constexpr int cmax(int a, int b) { return a > b ? a : b; }
-  static constexpr int IN_BYTES = (cmax(N1 * PITCH_A, 65536) + 127) & ~127;
+  static constexpr int IN_BYTES = (cmax(N1 * PITCH_A, TILE_BYTES) + 127) & ~127;
   static constexpr int WORK_BYTES = (cmax(cmax(NWARPS * AREA_A, ROUND_B), STAGE_B) + 127) & ~127;
   static constexpr int TAB_BYTES = (T1 + T2) * 5 * 8;
   static constexpr int SMEM = IN_BYTES + WORK_BYTES + TAB_BYTES;
-  static constexpr int MINB = SMEM + 1024 <= 113 * 1024 ? 2 : 1;
+  static constexpr int MINB = cmax(1, (65536 / (128 * NTHREADS)) < (227 * 1024 / (SMEM + 1024)) ? (65536 / (128 * NTHREADS)) : (227 * 1024 / (SMEM + 1024)));
 };
 
 struct PipeItem {
@@ -233,7 +241,7 @@ LB_D float2 cvt_raw(const unsigned char* p, int c)
 }
 
 template <int LN1, int LN2, int FMT>
-__global__ void __launch_bounds__(256, PipeCfg<LN1, LN2, FMT>::MINB)
+__global__ void __launch_bounds__(PipeCfg<LN1, LN2, FMT>::NTHREADS, PipeCfg<LN1, LN2, FMT>::MINB)
 fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapOut)
 {
   using C = PipeCfg<LN1, LN2, FMT>;
@@ -257,11 +265,11 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   const int total = nb * (C::IA + C::IB);
 
   // last-pass twiddles: the five exact binary powers of w = exp(-2 pi i t / M) per lane position
-  for (int i = tid; i < T1 * 5; i += 256) wbt[i] = q.Wn1[(i / 5) << (i % 5)];
-  for (int i = tid; i < T2 * 5; i += 256) wbt[T1 * 5 + i] = q.Wn2[(i / 5) << (i % 5)];
+  for (int i = tid; i < T1 * 5; i += C::NTHREADS) wbt[i] = q.Wn1[(i / 5) << (i % 5)];
+  for (int i = tid; i < T2 * 5; i += C::NTHREADS) wbt[T1 * 5 + i] = q.Wn2[(i / 5) << (i % 5)];
   if (tid == 0) {
     a_arrived = 0;
-    mbar_init(&bar_in, 256);
+    mbar_init(&bar_in, C::NTHREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
@@ -281,7 +289,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       const uint32_t start = p.ref0 + (uint32_t)it.b * p.blockbytes - p.pre_bytes;
       const uint32_t base = start + (uint32_t)(tile * TA) * FRAME;
 #pragma unroll 4
-      for (int ch = tid; ch < N1 * C::CPR_A; ch += 256) {
+      for (int ch = tid; ch < N1 * C::CPR_A; ch += C::NTHREADS) {
         const int row = ch / C::CPR_A, cc = ch - row * C::CPR_A;
         const uint32_t off = (base + (uint32_t)row * (uint32_t)(N2 * FRAME) + (uint32_t)cc * 16u) & p.ring_mask;
         cp_async16(in + row * C::PITCH_A + cc * 16, p.timf1 + off);
@@ -303,7 +311,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           // Y was written through the generic proxy (other SMs, observed by an acquire): order it
           // before the TMA unit's reads
           asm volatile("fence.proxy.async;" ::: "memory");
-          mbar_expect_tx(&bar_in, 65536u);
+          mbar_expect_tx(&bar_in, (uint32_t)C::TILE_BYTES);
 #pragma unroll
           for (int bx = 0; bx < N2 / C::BOX_IN; bx++)
             tma_load_3d(in + bx * (C::BOX_IN * TB * 8), &mapY, 2 * tile * TB, bx * C::BOX_IN, plane, &bar_in);
@@ -314,7 +322,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
         constexpr int CPR = TB * 8 / 16;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(q.Y + (size_t)plane * N + (size_t)tile * TB);
 #pragma unroll 4
-        for (int ch = tid; ch < N2 * CPR; ch += 256) {
+        for (int ch = tid; ch < N2 * CPR; ch += C::NTHREADS) {
           const int row = ch / CPR, cc = ch - row * CPR;
           cp_async16(in + row * (TB * 8) + cc * 16, src + (size_t)row * (N1 * 8) + cc * 16);
         }
@@ -334,12 +342,24 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     __syncthreads();
     issue_load(cur);
   }
+#ifdef LB_PIPE_STATS
+  long long st_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // thread 0: cycles in [A wait, A rest, B wait, B rest, deferred, claim, slot wait] + counts
+  long long st_t = clock64();
+  const long long st_begin = st_t;
+#define LB_ST(i) do { if (tid == 0) { const long long n_ = clock64(); st_[i] += n_ - st_t; st_t = n_; } } while (0)
+#define LB_CNT(i) do { if (tid == 0) st_[i] += 1; } while (0)
+#else
+#define LB_ST(i) do { } while (0)
+#define LB_CNT(i) do { } while (0)
+#endif
   uint32_t par = 0;
   int s = 0;
   bool stores_pending = false;                   // thread 0: TMA stores may still be reading `work`
 
   while (cur.role >= 0) {
+    LB_ST(9);
     if (tid == 0) claim(items[s ^ 1]);
+    LB_ST(5);
     const int tile = cur.j / NCH;
     const int c = cur.j - tile * NCH;
     float2 v[32];
@@ -363,7 +383,10 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
 #pragma unroll
         for (int e = 0; e < 32; e++) wv[e] = __ldg(wp + e * T1);
       }
+      LB_ST(1);
       pipe_mbar_wait(&bar_in, par, err);
+      LB_ST(0);
+      LB_CNT(7);
       par ^= 1;
       {
         const unsigned char* rp = in + t * C::PITCH_A + col * FRAME;
@@ -410,10 +433,12 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
       apply_power_twiddles<32>(v, tw_base, tw_sb);
       // ---- the slot must have been read by the rows of transform b - nslots
+      LB_ST(1);
       if (cur.b >= q.nslots) {
         if (lane == 0) pipe_wait(doneB + (cur.b - q.nslots), C::IB, err);
         __syncwarp();
       }
+      LB_ST(6);
       {
         float2* Yp = q.Y + (size_t)(slot_of(cur.b) * NCH + c) * N + (size_t)n2 * N1 + t;
 #pragma unroll
@@ -430,16 +455,21 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           atomicAdd(doneA + cur.b, C::NWARPS);
         }
       }
+      LB_ST(1);
       if (nxt.role >= 0 && !nxt.ready) {
         if (nxt.role == 1 && tid == 0) pipe_wait(doneA + nxt.b, C::IA * C::NWARPS, err);
         __syncthreads();
         issue_load(nxt);
       }
+      LB_ST(4);
       cur = nxt;
     } else {
       // =============================== role B: TB rows of transform cur.b ======================
       const int r = tid & (TB - 1), t = tid / TB;
+      LB_ST(3);
       pipe_mbar_wait(&bar_in, par, err);
+      LB_ST(2);
+      LB_CNT(8);
       par ^= 1;
       {
         const float2* ip = reinterpret_cast<const float2*>(in) + t * TB + r;
@@ -575,16 +605,23 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
           }
         }
       }
+      LB_ST(3);
       if (nxt.role >= 0 && !nxt.ready) {
         if (nxt.role == 1 && tid == 0) pipe_wait(doneA + nxt.b, C::IA * C::NWARPS, err);
         __syncthreads();
         issue_load(nxt);
       }
+      LB_ST(4);
       cur = nxt;
     }
     s ^= 1;
   }
   if (tid == 0) bulk_wait_all();                  // shared memory must outlive the last TMA store
+#ifdef LB_PIPE_STATS
+  if (tid == 0 && (blockIdx.x % 37) == 0 && nb >= 60)
+    printf("PIPESTAT cta %d total %lld Await %lld Arest %lld Bwait %lld Brest %lld deferred %lld claim %lld slotwait %lld other %lld nA %lld nB %lld\n", (int)blockIdx.x,
+           clock64() - st_begin, st_[0], st_[1], st_[2], st_[3], st_[4], st_[5], st_[6], st_[9], st_[7], st_[8]);
+#endif
 }
 #endif  // __CUDACC__
 

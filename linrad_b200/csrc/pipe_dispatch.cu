@@ -96,7 +96,7 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   const int ln = plan->cfg.fft1_n;
   pipe_fn_t fn = pipe_fn(plan->fmt);
   if (!fn) return cudaErrorNotSupported;
-  int geo[7];
+  int geo[8];
   cudaError_t e = fn(ln, geo, nullptr, nullptr, nullptr, 0, nullptr, plan->stream);
   if (e != cudaSuccess) return e;
   const int IA = geo[0], IB = geo[1], TB = geo[2], box_in = geo[3], box_out = geo[4], ln1 = geo[5], ln2 = geo[6];
@@ -106,7 +106,7 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
 
   // ---- queue lag and ring depth: a dependency should be long satisfied when its consumer is claimed.
   // About 2 items per resident CTA are in flight (the one computed and the one prefetched).
-  const int resident = plan->sm_count * 2;
+  const int resident = plan->sm_count * (512 / geo[7]);       // sixteen warps per SM (128 registers per thread)
   const int per_phase = IA + IB;
   int lag = env_i("LB200_PIPE_LAG", (3 * resident / 2 + per_phase - 1) / per_phase + 1);
   if (lag < 1) lag = 1;
@@ -201,8 +201,8 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   CUtensorMap my, mo;
   memcpy(&my, plan->map_y, sizeof(my));
   memcpy(&mo, plan->map_out, sizeof(mo));
-  int grid = 0;
-  e = fn(ln, nullptr, &q, &my, &mo, plan->sm_count, &grid, plan->stream);
+  int grid[2] = {0, 0};
+  e = fn(ln, nullptr, &q, &my, &mo, plan->sm_count, grid, plan->stream);
   if (e != cudaSuccess) return e;
   plan->launches += 1;
   return cudaSuccess;

@@ -15,6 +15,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <signal.h>
+#include <execinfo.h>
+#include <unistd.h>
 #include "osnum.h"
 #include "globdef.h"
 #include "uidef.h"
@@ -107,6 +110,43 @@ static void afc_tables_via_reference(int ss)
 }
 #endif
 
+#if HAVE_CUFFT == 1
+/* The reference's own GPU path (fft_cntrl row 19, fft1.c:3531-3553): the handles and device
+ * buffers live in wcw.c:72-76, which is the thread body and is not compiled here, so the harness
+ * owns them and creates them the way wcw.c:553-576 does.  Built only into _ref/libref_cufft.so. */
+#include <cufft.h>
+#include <cuda_runtime.h>
+cufftHandle cufft_handle_fft1b[MAX_FFT1_THREADS];
+cuFloatComplex *cuda_in[MAX_FFT1_THREADS];
+cuFloatComplex *cuda_out[MAX_FFT1_THREADS];
+static int cufft_ready = 0;
+static void cufft_close(void)
+{
+  if (!cufft_ready) return;
+  cufftDestroy(cufft_handle_fft1b[0]);
+  cudaFree(cuda_in[0]); cudaFree(cuda_out[0]);
+  cuda_in[0] = cuda_out[0] = NULL;
+  cufft_ready = 0;
+}
+#endif
+static int gpu_batch_n = 4;            /* gpu.fft1_batch_n (buf.c:251): 16 transforms per cuFFT call */
+void ref_set_gpu_batch_n(int n) { gpu_batch_n = n; }
+int ref_has_cufft(void)
+{
+#if HAVE_CUFFT == 1
+  return 1;
+#else
+  return 0;
+#endif
+}
+/* debugging aid: LB200_REF_BACKTRACE=1 prints the C frames when the compiled reference crashes */
+static void segv_backtrace(int sig)
+{
+  void *frames[48];
+  int n = backtrace(frames, 48);
+  backtrace_symbols_fd(frames, n, 2);
+  _exit(139);
+}
 static ref_cfg C;
 static sel_state SEL[REF_MAX_SEL];
 static float *timf3_all;        /* n_sel regions of 2*timf3_size floats */
@@ -121,6 +161,7 @@ static void *zalloc(size_t n) { void *p = calloc(n + 64, 1); if (!p) { fprintf(s
 
 int ref_fft1_size(void) { return fft1_size; }
 int ref_fft1_block(void) { return fft1_block; }
+int ref_fft1_muln(void) { return fft1_muln; }
 int ref_interleave_points(void) { return fft1_interleave_points; }
 int ref_new_points(void) { return fft1_new_points; }
 int ref_timf1_blockbytes(void) { return timf1_blockbytes; }
@@ -226,6 +267,7 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   if (inited) lb200_shim_close();
 #endif
   if (inited) free_all();
+  if (getenv("LB200_REF_BACKTRACE")) signal(SIGSEGV, segv_backtrace);
   C = *cfg;
   ref_last_lirerr = 0;
   memset(&ui, 0, sizeof(ui));
@@ -264,11 +306,21 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   fft1_block = twice_rxchan * fft1_size;
   fft1_use_gpu = 0;
   fft1_muln = (fft_cntrl[FFT1_CURMODE].real2complex + 1) * fft_cntrl[FFT1_CURMODE].parall_fft;
+  if (fft_cntrl[FFT1_CURMODE].gpu == GPU_CUDA) {          /* buf.c:238-258 */
+#if HAVE_CUFFT == 1
+    fft1_use_gpu = GPU_CUDA;
+    gpu_fft1_batch_size = 1 << gpu_batch_n;
+    fft1_muln = gpu_fft1_batch_size;
+#else
+    fprintf(stderr, "[ref oracle] fft_cntrl row %d needs the cuFFT build (_ref/libref_cufft.so)\n", C.fft1_version);
+    return -3;
+#endif
+  } else if (fft_cntrl[FFT1_CURMODE].gpu != 0) return -3;
   fft1_mulblock = fft1_block * fft1_muln;
   j = fft1_size * (fft_cntrl[FFT1_CURMODE].real2complex + 1);
   fft1_permute_size = j; fft1_window_size = j; fft1_costab_size = j / 2;
   if (fft_cntrl[FFT1_CURMODE].permute == 2) { fft1_costab_size *= 2; fft1_permute_size *= 2; fft1_window_size += 16; }
-  if (fft_cntrl[FFT1_CURMODE].doub == 0 && fft1_permute_size > 0x10000) { fprintf(stderr, "[ref oracle] N too big for float path\n"); return -2; }
+  if (!fft1_use_gpu && fft_cntrl[FFT1_CURMODE].doub == 0 && fft1_permute_size > 0x10000) { fprintf(stderr, "[ref oracle] N too big for float path\n"); return -2; }
   fft1_blockbytes = fft1_block * (int)sizeof(float);
   frame_bytes = 2 * ui.rx_ad_channels;
   if (ui.rx_input_mode & DWORD_INPUT) frame_bytes *= 2;
@@ -320,6 +372,7 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   fft1_pa = fft1_pb = fft1_px = 0; fft1_na = fft1_nb = fft1_nx = fft1_nm = 0;
   fft1_tmp_bytes = fft1_blockbytes * (fft_cntrl[FFT1_CURMODE].real2complex + 1) * fft_cntrl[FFT1_CURMODE].parall_fft;
   if (fft_cntrl[FFT1_CURMODE].doub) fft1_tmp_bytes *= 2;
+  if (fft1_use_gpu) fft1_tmp_bytes = fft1_blockbytes * gpu_fft1_batch_size;      /* buf.c:794-797 */
   /* buf.c:901-908 lays timf2_tmp (2*fft1_tmp_bytes of scratch) directly behind fftw_tmp.  That
    * matters: when log2(2*fft1_size) is even, fft_real_to_hermitian's stray length-2 butterfly
    * after its first loop (fft0.c:63-65) lands at z[2*size-2], i.e. outside fftw_tmp and inside
@@ -365,8 +418,22 @@ int ref_init(const ref_cfg *cfg, int timf1_bytes_req, int max_fft1n_req)
   fft1_bigpermute = zalloc(sizeof(unsigned int) * (fft1_permute_size + 16));
   fft1_window = zalloc(sizeof(float) * (fft1_window_size + 32));
   d_fft1_window = zalloc(sizeof(double) * (fft1_window_size + 32));
-  make_sincos(i, k, fft1tab);
-  if (fft_cntrl[FFT1_CURMODE].doub) {
+  if (!fft1_use_gpu) make_sincos(i, k, fft1tab);        /* buf.c:1408, 1434: no CPU tables for the GPU rows */
+  if (fft1_use_gpu) {
+#if HAVE_CUFFT == 1
+    /* wcw.c:553-576 */
+    int ncu[1];
+    ncu[0] = fft1_size;
+    cufft_close();
+    if (cufftPlanMany(&cufft_handle_fft1b[0], 1, ncu, NULL, 1, fft1_size, NULL, 1, fft1_size, CUFFT_C2C, gpu_fft1_batch_size) != CUFFT_SUCCESS) {
+      fprintf(stderr, "[ref oracle] cufftPlanMany failed (lirerr 1461)\n");
+      return 1461;
+    }
+    if (cudaMalloc((void **)&cuda_in[0], (size_t)gpu_fft1_batch_size * fft1_size * sizeof(cuFloatComplex)) != cudaSuccess ||
+        cudaMalloc((void **)&cuda_out[0], (size_t)gpu_fft1_batch_size * fft1_size * sizeof(cuFloatComplex)) != cudaSuccess) return 1461;
+    cufft_ready = 1;
+#endif
+  } else if (fft_cntrl[FFT1_CURMODE].doub) {
     make_d_sincos(i, k, d_fft1tab);
     make_bigpermute(fft_cntrl[FFT1_CURMODE].permute, fft_cntrl[FFT1_CURMODE].real2complex ? fft1_n + 1 : fft1_n, k, fft1_bigpermute);
     make_d_window(fft_cntrl[FFT1_CURMODE].window, k, C.sinpow, d_fft1_window);
@@ -482,7 +549,12 @@ int ref_process(const void *data, int nblocks, float *fft1_out, float *raw_out, 
   int b, ss, i, sub;
   const char *src = (const char *)data;
   for (b = 0; b < nblocks; b++) {
-    for (i = 0; i < timf1_blockbytes; i++) timf1_char[(timf1p_pa + i) & timf1_bytemask] = src[(size_t)b * timf1_blockbytes + i];
+    {                                              /* the block goes into the ring in at most two pieces */
+      size_t first = (size_t)(timf1_bytemask + 1 - timf1p_pa);
+      if (first > (size_t)timf1_blockbytes) first = timf1_blockbytes;
+      memcpy(timf1_char + timf1p_pa, src + (size_t)b * timf1_blockbytes, first);
+      memcpy(timf1_char, src + (size_t)b * timf1_blockbytes + first, (size_t)timf1_blockbytes - first);
+    }
     timf1p_pa = (timf1p_pa + timf1_blockbytes) & timf1_bytemask;
     timf1p_pb = timf1p_pa;
     /* wcw.c:1036-1047 */

@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libref_oracle.so")
 SHIM_SO = os.path.join(_HERE, "_ref", "libref_shim.so")     # same harness, hot path through lb200_shim.c (GPU)
+CUFFT_SO = os.path.join(_HERE, "_ref", "libref_cufft.so")   # same harness, reference built with -DHAVE_CUFFT=1 (fft_cntrl row 19; GPU)
 
 DWORD_INPUT, TWO_CHANNELS, IQ_DATA = 1, 2, 4
 
@@ -32,6 +33,10 @@ def shim_available():
     return os.path.exists(SHIM_SO)
 
 
+def cufft_available():
+    return os.path.exists(CUFFT_SO)
+
+
 class RefOracle:
     """One instance at a time (the reference keeps its state in globals)."""
 
@@ -39,11 +44,12 @@ class RefOracle:
                  fft1_gain=2000, mix1_red_n=4, avg1num=5, avg2num=4, waterfall_avgnum=10,
                  direction=1, n_sel=0, first_xpoint=0, xpoints=None, xpoints_per_pixel=1,
                  pixels_per_xpoint=1, wf_lines=8, sample_shift=0, timf1_bytes=None, max_fft1n=8, through_shim=False,
-                 correlation=0, afc=0, afc_mix=0):
-        self.lib = C.CDLL(SHIM_SO if through_shim else REF_SO)
+                 correlation=0, afc=0, afc_mix=0, cufft=False, gpu_batch_n=4):
+        self.lib = C.CDLL(CUFFT_SO if cufft else SHIM_SO if through_shim else REF_SO)
         L = self.lib
         L.ref_init.argtypes = [C.POINTER(RefCfg), C.c_int, C.c_int]
         L.ref_process.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_process_timed.argtypes = [C.c_void_p, C.c_int]      # without it the pointer travels as a C int
         L.ref_set_selfreq.argtypes = [C.c_int, C.c_double]
         L.ref_set_foldcorr.argtypes = [C.c_void_p]
         L.ref_set_ch2_phasing.argtypes = [C.c_float, C.c_float]
@@ -73,6 +79,12 @@ class RefOracle:
             timf1_bytes = 1
             while timf1_bytes < 8 * n * frame:
                 timf1_bytes *= 2
+        if cufft:
+            # the reference's GPU row transforms 2^gpu.fft1_batch_n blocks per fft1_b call (buf.c:248-258)
+            L.ref_set_gpu_batch_n(gpu_batch_n)
+            timf1_bytes *= 1 << gpu_batch_n
+            while max_fft1n < 2 << gpu_batch_n:
+                max_fft1n *= 2
         rc = L.ref_init(C.byref(self.cfg), timf1_bytes, max_fft1n)
         if rc != 0:
             raise RuntimeError(f"ref_init failed rc={rc}")
@@ -93,7 +105,7 @@ class RefOracle:
         self.points_per_hz = L.ref_points_per_hz()
         self.first_point = L.ref_first_point()
         self.last_point = L.ref_last_point()
-        self.muln = 1
+        self.muln = L.ref_fft1_muln()              # transforms per fft1_b call (timf1_blockbytes covers all of them)
 
     def _arr(self, fn, count, dtype=np.float32):
         ptr = getattr(self.lib, fn)()
@@ -127,9 +139,10 @@ class RefOracle:
         nbytes = raw.nbytes
         assert nbytes % self.timf1_blockbytes == 0, (nbytes, self.timf1_blockbytes)
         nb = nbytes // self.timf1_blockbytes
-        fft1 = np.zeros((nb, self.fft1_block), np.float32)
-        rawout = np.zeros((nb, self.fft1_block), np.float32) if want_raw else None
-        t3 = np.zeros((nb, max(self.n_sel, 1), self.timf3_block), np.float32) if self.n_sel else None
+        nt = nb * self.muln
+        fft1 = np.zeros((nt, self.fft1_block), np.float32)
+        rawout = np.zeros((nt, self.fft1_block), np.float32) if want_raw else None
+        t3 = np.zeros((nt, max(self.n_sel, 1), self.timf3_block), np.float32) if self.n_sel else None
         rc = self.lib.ref_process(raw.ctypes.data, nb, fft1.ctypes.data,
                                   rawout.ctypes.data if want_raw else None,
                                   t3.ctypes.data if t3 is not None else None)
