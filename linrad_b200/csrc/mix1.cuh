@@ -57,6 +57,16 @@ LB_D void mix1_sincos(float x, float* s, float* c)
   *c = __cosf(r);
 }
 
+// [start, start+bytes) of fft1_float -> L2 (16-byte granules; a transform's block does not wrap)
+LB_D void mix1_l2_prefetch(const unsigned char* base, uint32_t start, uint32_t bytes)
+{
+#if defined(__CUDA_ARCH__)
+  const uint32_t a = start & ~15u;
+  const uint32_t len = (bytes + (start & 15u) + 15u) & ~15u;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + a), "r"(len) : "memory");
+#endif
+}
+
 // taper index of do_mix1 (mix1.c:113-135 / 455-491, including the doubled factors of the
 // two-channel loop at i==M-1 and i==M/2)
 template <int NCH>
@@ -118,6 +128,20 @@ mix1_kernel(const Mix1K p)
     float* t3 = p.timf3 + (size_t)ss * p.sel_stride;
     // ystart = bfirst-1 rebuilds the predecessor's tail when this run does not start the call
     const int ystart = (bfirst > 0 && carry_len > 0) ? bfirst - 1 : bfirst;
+    // the spectra this run will gather (fft1_float has long left L2 when the batch is large): one thread
+    // per transform asks for its M bins now, so that only the first gather of the run waits for DRAM
+    if (tid < blast - ystart && tid < 32) {
+      const Mix1Job pj = jobs[ystart + tid];
+      if (pj.point >= 0) {
+        int lo = pj.point - M / 2, hi = pj.point + M / 2;
+        if (lo < p.first_point) lo = p.first_point;
+        if (hi > p.last_point) hi = p.last_point;
+        if (hi > lo) {
+          const uint32_t start = ((pj.src & p.fft1_mask) + (uint32_t)lo * MM) * 4u;
+          mix1_l2_prefetch(reinterpret_cast<const unsigned char*>(p.fft1), start, (uint32_t)(hi - lo) * MM * 4u);
+        }
+      }
+    }
     for (int y0 = ystart; y0 < blast; y0 += PAR) {
       const int b = y0 + lane;                 // this lane's transform
       const bool active = b < blast;

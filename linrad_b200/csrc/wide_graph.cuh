@@ -59,23 +59,41 @@ __global__ void __launch_bounds__(256) slowsum_kernel(const WgK p)
   float s = p.slowsum[i];
   int recalc = p.recalc0;
   bool change = p.change_flag0 != 0;
-  for (int r = 0; r < p.nrows; r++) {
-    const uint32_t pa = (p.pa0 + (uint32_t)r * (uint32_t)p.N) & p.sumsq_mask;
-    if (change) {                                     // fft1.c:4541-4546
-      change = false;
-      if (i >= p.wg_first_point && i <= p.wg_last_point) s = wg_fresh(p, pa, i);
-      continue;
+  // rows are taken twelve at a time: the loads of a group are in flight together, the arithmetic
+  // stays in row order
+  constexpr int G = 12;
+  for (int r0 = 0; r0 < p.nrows; r0 += G) {
+    float add[G], sub[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      add[g] = 0.f;
+      sub[g] = 0.f;
+      if (r0 + g < p.nrows) {
+        const uint32_t pa = (p.pa0 + (uint32_t)(r0 + g) * (uint32_t)p.N) & p.sumsq_mask;
+        const uint32_t pb = (pa - (uint32_t)p.avg2num * (uint32_t)p.N) & p.sumsq_mask;   // fft1.c:4568
+        add[g] = __ldg(p.sumsq + pa + i);
+        sub[g] = __ldg(p.sumsq + pb + i);
+      }
     }
-    const uint32_t pb = (pa - (uint32_t)p.avg2num * (uint32_t)p.N) & p.sumsq_mask;   // fft1.c:4568
-    if (recalc == p.last_point) recalc = p.first_point;
-    const int ia = recalc;
-    recalc += p.xpoints / p.fresh_recalc;
-    if (recalc > p.last_point) recalc = p.last_point;
-    if (i >= ia && i <= recalc) {
-      s = wg_fresh(p, pa, i);
-    } else if (i >= p.first_point && i <= p.last_point) {
-      s = __fadd_rn(s, __fsub_rn(p.sumsq[pa + i], p.sumsq[pb + i]));                 // fft1.c:4576,4581
-      if (s < LB_FFT1_SMALL) s = LB_FFT1_SMALL;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (r0 + g >= p.nrows) break;
+      const uint32_t pa = (p.pa0 + (uint32_t)(r0 + g) * (uint32_t)p.N) & p.sumsq_mask;
+      if (change) {                                     // fft1.c:4541-4546
+        change = false;
+        if (i >= p.wg_first_point && i <= p.wg_last_point) s = wg_fresh(p, pa, i);
+        continue;
+      }
+      if (recalc == p.last_point) recalc = p.first_point;
+      const int ia = recalc;
+      recalc += p.xpoints / p.fresh_recalc;
+      if (recalc > p.last_point) recalc = p.last_point;
+      if (i >= ia && i <= recalc) {
+        s = wg_fresh(p, pa, i);
+      } else if (i >= p.first_point && i <= p.last_point) {
+        s = __fadd_rn(s, __fsub_rn(add[g], sub[g]));                                   // fft1.c:4576,4581
+        if (s < LB_FFT1_SMALL) s = LB_FFT1_SMALL;
+      }
     }
   }
   p.slowsum[i] = s;
@@ -123,10 +141,31 @@ __global__ void __launch_bounds__(256) waterfall_kernel(const WgK p, int mode, i
   }
   uint32_t row = p.pwg0;
   int seg_start = 0;                // first row of the current (unfinished) line, mode 1
+  // modes 0 and 2: the rows' values are fetched twelve rows at a time (loads in flight together),
+  // the sums are formed in row order
+  constexpr int G = 12;
+  float pre[2][G];
   for (int r = 0; r < p.wrows; r++) {
     if (mode != 1) {
-      for (int k = 0; k < nb; k++)
-        if (in_wg(b0 + k)) acc[k] = __fadd_rn(acc[k], src(row, b0 + k));
+      const int g = r % G;
+      if (g == 0) {
+        uint32_t rw = row;
+#pragma unroll
+        for (int gg = 0; gg < G; gg++) {
+#pragma unroll
+          for (int k = 0; k < 2; k++) pre[k][gg] = (k < nb && r + gg < p.wrows && in_wg(b0 + k)) ? __ldg(&p.sumsq[rw + (uint32_t)(p.first_xpoint + (b0 + k - p.wg_first_point))]) : 0.f;
+          rw = (rw + p.N) & p.sumsq_mask;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        if (k < nb && in_wg(b0 + k)) {
+          float x = pre[k][0];
+#pragma unroll
+          for (int gg = 1; gg < G; gg++) x = g == gg ? pre[k][gg] : x;
+          acc[k] = __fadd_rn(acc[k], x);
+        }
+      }
     }
     row = (row + p.N) & p.sumsq_mask;
     counter += p.avg1num;
