@@ -154,6 +154,9 @@ struct PipeCfg {
   static constexpr int cmax(int a, int b) { return a > b ? a : b; }
   static constexpr int IN_BYTES = (cmax(N1 * PITCH_A, TILE_BYTES) + 127) & ~127;
   static constexpr int WORK_BYTES = (cmax(cmax(NWARPS * AREA_A, ROUND_B), STAGE_B) + 127) & ~127;
+  static constexpr int cmin(int a, int b) { return a < b ? a : b; }
+  static constexpr int ROUNDS_PER_BARRIER = cmin(Q2, cmax(1, WORK_BYTES / ROUND_B));
+  static_assert(Q2 % ROUNDS_PER_BARRIER == 0, "exchange rounds");
   static constexpr int TAB_BYTES = (T1 + T2) * 5 * 8;
   static constexpr int SMEM = IN_BYTES + WORK_BYTES + TAB_BYTES;
   static constexpr int MINB = cmax(1, (65536 / (128 * NTHREADS)) < (227 * 1024 / (SMEM + 1024)) ? (65536 / (128 * NTHREADS)) : (227 * 1024 / (SMEM + 1024)));
@@ -491,12 +494,16 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       {
         float2* buf = reinterpret_cast<float2*>(work);
         float2 u[32];
+        // a round moves T2 values per thread; as many rounds as fit into `work` share one pair of barriers
+        constexpr int RPB = C::ROUNDS_PER_BARRIER, RELEMS = C::ROUND_B / 8;
 #pragma unroll
-        for (int qq = 0; qq < Q2; qq++) {
-          if (qq > 0) __syncthreads();            // the previous round has been read
-          rowx_store<T2, TB>(v, buf, t, r, qq);
+        for (int q0 = 0; q0 < Q2; q0 += RPB) {
+          if (q0 > 0) __syncthreads();            // the previous rounds have been read
+#pragma unroll
+          for (int j = 0; j < RPB; j++) rowx_store<T2, TB>(v, buf + j * RELEMS, t, r, q0 + j);
           __syncthreads();
-          rowx_load<T2, TB>(u, buf, t, r, qq);
+#pragma unroll
+          for (int j = 0; j < RPB; j++) rowx_load<T2, TB>(u, buf + j * RELEMS, t, r, q0 + j);
         }
 #pragma unroll
         for (int e = 0; e < 32; e++) v[e] = u[e];

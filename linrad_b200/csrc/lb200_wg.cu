@@ -126,9 +126,41 @@ extern "C" int lb200_fft1_waterfall_dev(lb200_plan* plan, const lb200_wg_config*
   int nunits = 0;
   const int mode = wg_mode(k, &nunits);
   if (nunits > 0) {
-    waterfall_kernel<<<(nunits + 255) / 256, 256, 0, plan->stream>>>(k, mode, nunits);
-    LB_CUDA(cudaGetLastError());
-    plan->launches++;
+    // launch 1: the complete lines of the call; launch 2: the rows behind the last line -> wg_waterf_sum
+    const WgLines lg = wg_lines(k.counter0, k.avg1num, k.waterfall_avgnum, k.wrows);
+    const int gx = (nunits + 255) / 256;
+    bool fused = false;
+    const bool aligned = k.xpixels > 0 && k.waterf_size % k.xpixels == 0;
+    if (lg.nl > 0 && (mode == 2 || !aligned)) {
+      // interpolation: the tail of a line reaches into the first pixels of the line written before it
+      // (fft1.c:190-205); a ring that is not a whole number of lines: lines overlap partially.  Either way the
+      // lines have to land in time order: one launch each
+      for (int L = 0; L < lg.nl; L++) {
+        waterfall_kernel<<<gx, 256, 0, plan->stream>>>(k, mode, nunits, 0, L, 1);
+        LB_CUDA(cudaGetLastError());
+        plan->launches++;
+      }
+    } else if (lg.nl > 0) {
+      // lines that land on the same place of the waterfall ring: only the last one survives the sequential walk,
+      // the earlier ones are not computed
+      int first = 0;
+      const int ring_lines = k.waterf_size / k.xpixels;
+      if (lg.nl > ring_lines) first = lg.nl - ring_lines;
+      int gy = 262144 / nunits;                            // enough threads for the GPU, else one per unit
+      if (gy < 1) gy = 1;
+      if (gy > lg.nl - first) gy = lg.nl - first;
+      if (gy > 32768) gy = 32768;
+      const int lps = (lg.nl - first + gy - 1) / gy;
+      fused = mode == 0 && gy == 1;                        // one thread per bin: lines and hand-back in one walk
+      waterfall_kernel<<<dim3(gx, gy), 256, 0, plan->stream>>>(k, mode, nunits, fused ? 2 : 0, first, lps);
+      LB_CUDA(cudaGetLastError());
+      plan->launches++;
+    }
+    if (!fused) {
+      waterfall_kernel<<<gx, 256, 0, plan->stream>>>(k, mode, nunits, 1, 0, 0);
+      LB_CUDA(cudaGetLastError());
+      plan->launches++;
+    }
   }
   wg_advance_waterfall(k, a->state, nullptr);
   return LB200_OK;

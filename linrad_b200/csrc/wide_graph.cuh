@@ -56,43 +56,63 @@ __global__ void __launch_bounds__(256) slowsum_kernel(const WgK p)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.N) return;
-  float s = p.slowsum[i];
-  int recalc = p.recalc0;
-  bool change = p.change_flag0 != 0;
-  // rows are taken twelve at a time: the loads of a group are in flight together, the arithmetic
-  // stays in row order
-  constexpr int G = 12;
-  for (int r0 = 0; r0 < p.nrows; r0 += G) {
-    float add[G], sub[G];
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      add[g] = 0.f;
-      sub[g] = 0.f;
-      if (r0 + g < p.nrows) {
-        const uint32_t pa = (p.pa0 + (uint32_t)(r0 + g) * (uint32_t)p.N) & p.sumsq_mask;
-        const uint32_t pb = (pa - (uint32_t)p.avg2num * (uint32_t)p.N) & p.sumsq_mask;   // fft1.c:4568
-        add[g] = __ldg(p.sumsq + pa + i);
-        sub[g] = __ldg(p.sumsq + pb + i);
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      if (r0 + g >= p.nrows) break;
-      const uint32_t pa = (p.pa0 + (uint32_t)(r0 + g) * (uint32_t)p.N) & p.sumsq_mask;
-      if (change) {                                     // fft1.c:4541-4546
+  // A row in whose recalculation window the bin lies (fft1.c:4568-4574) or the change-flag row
+  // (fft1.c:4541-4546) REPLACES the sum by a fresh one that does not depend on its history.  First walk the
+  // window recurrence alone (integers, no memory) to find the last such row of this call for this bin, then do
+  // the arithmetic from there: the value is the reference's, the work no longer grows with the rows of a call.
+  const bool change0 = p.change_flag0 != 0;
+  int last = -1;
+  {
+    int recalc = p.recalc0;
+    bool change = change0;
+    const int step = p.xpoints / p.fresh_recalc;
+    for (int r = 0; r < p.nrows; r++) {
+      if (change) {
         change = false;
-        if (i >= p.wg_first_point && i <= p.wg_last_point) s = wg_fresh(p, pa, i);
+        if (i >= p.wg_first_point && i <= p.wg_last_point) last = r;
         continue;
       }
       if (recalc == p.last_point) recalc = p.first_point;
       const int ia = recalc;
-      recalc += p.xpoints / p.fresh_recalc;
+      recalc += step;
       if (recalc > p.last_point) recalc = p.last_point;
-      if (i >= ia && i <= recalc) {
-        s = wg_fresh(p, pa, i);
-      } else if (i >= p.first_point && i <= p.last_point) {
-        s = __fadd_rn(s, __fsub_rn(add[g], sub[g]));                                   // fft1.c:4576,4581
-        if (s < LB_FFT1_SMALL) s = LB_FFT1_SMALL;
+      if (i >= ia && i <= recalc) last = r;
+    }
+  }
+  const bool inband = i >= p.first_point && i <= p.last_point;
+  if (last < 0 && !inband) return;                       // untouched by this call
+  float s;
+  int r0;
+  if (last >= 0) {
+    s = wg_fresh(p, (p.pa0 + (uint32_t)last * (uint32_t)p.N) & p.sumsq_mask, i);
+    r0 = last + 1;
+  } else {
+    s = p.slowsum[i];
+    r0 = change0 ? 1 : 0;                                 // the change-flag row adds nothing outside the wide graph
+  }
+  if (inband) {
+    // the remaining rows: add the new row, subtract the one that leaves the window (fft1.c:4576,4581);
+    // their loads are issued twelve rows at a time, the arithmetic stays in row order
+    constexpr int G = 12;
+    for (int rb = r0; rb < p.nrows; rb += G) {
+      float add[G], sub[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        add[g] = 0.f;
+        sub[g] = 0.f;
+        if (rb + g < p.nrows) {
+          const uint32_t pa = (p.pa0 + (uint32_t)(rb + g) * (uint32_t)p.N) & p.sumsq_mask;
+          const uint32_t pb = (pa - (uint32_t)p.avg2num * (uint32_t)p.N) & p.sumsq_mask;   // fft1.c:4568
+          add[g] = __ldg(p.sumsq + pa + i);
+          sub[g] = __ldg(p.sumsq + pb + i);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        if (rb + g < p.nrows) {
+          s = __fadd_rn(s, __fsub_rn(add[g], sub[g]));
+          if (s < LB_FFT1_SMALL) s = LB_FFT1_SMALL;
+        }
       }
     }
   }
@@ -116,10 +136,36 @@ __device__ __forceinline__ short wg_clamp_interp(float y)   // fft1.c:169-171: l
   return (short)y;
 }
 
-// One thread per unit u.  mode 0 (1:1): unit = bin u.  mode 1 (xpoints_per_pixel > 1): unit =
+// Geometry of the waterfall lines of one call (update_wg_waterf, fft1.c:104-113): the counter grows by
+// avg1num per row and a line is written when it reaches waterfall_avgnum, after which the sums of the bins on
+// the wide graph start again from 0.00001.  So line L depends only on its own rows (line 0 also on the sums
+// carried in wg_waterf_sum): lines are independent work.
+struct WgLines {
+  int rf;       // rows until the first line of the call is complete
+  int rl;       // rows per further line
+  int nl;       // complete lines in this call
+};
+__host__ __device__ inline WgLines wg_lines(int counter0, int avg1num, int waterfall_avgnum, int wrows)
+{
+  WgLines g;
+  int need = waterfall_avgnum - counter0;
+  g.rf = need <= 0 ? 1 : (need + avg1num - 1) / avg1num;
+  if (g.rf < 1) g.rf = 1;
+  g.rl = (waterfall_avgnum + avg1num - 1) / avg1num;
+  if (g.rl < 1) g.rl = 1;
+  g.nl = wrows >= g.rf ? 1 + (wrows - g.rf) / g.rl : 0;
+  return g;
+}
+
+// One thread per unit u and segment.  mode 0 (1:1): unit = bin u.  mode 1 (xpoints_per_pixel > 1): unit =
 // pixel u = bins first_xpoint + u*xpp ...  mode 2 (interpolation, pixels_per_xpoint > 1): unit =
 // bin first_xpoint + u; it owns wsum of that bin and the ppx pixels that end on it.
-__global__ void __launch_bounds__(256) waterfall_kernel(const WgK p, int mode, int nunits)
+// Launch 1 (handback == 0): blockIdx.y owns the `lps` consecutive lines from line_first + blockIdx.y*lps on and
+// walks them in order from the start state of the first.  Launch 2 (handback == 1) = the rows after the last
+// complete line: hands the running sums back to wg_waterf_sum (a launch of its own because line 0 reads what
+// it overwrites).  The host chooses lps so that there are enough threads when a call brings hundreds of
+// rows for few bins, and one thread per unit when the bins alone fill the GPU.
+__global__ void __launch_bounds__(256) waterfall_kernel(const WgK p, int mode, int nunits, int handback, int line_first, int lps)
 {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= nunits) return;
@@ -127,33 +173,43 @@ __global__ void __launch_bounds__(256) waterfall_kernel(const WgK p, int mode, i
   if (mode == 0) { b0 = u; nb = 1; }
   else if (mode == 1) { b0 = p.first_xpoint + u * p.xpp; nb = p.xpp; }
   else { b0 = p.first_xpoint + u - 1; nb = 2; }     // [previous bin, own bin]
-  float acc[2];
-  float accmax = 0.f;
-  (void)accmax;
-  // mode 1 carries up to xpp sums; they live in global memory between rows only when xpp > 2,
-  // so keep it simple: recompute from the global wsum per line segment (see below)
-  int counter = p.counter0;
-  int ptr = p.waterf_ptr0;
+  const WgLines lg = wg_lines(p.counter0, p.avg1num, p.waterfall_avgnum, p.wrows);
   auto in_wg = [&](int b) { return b >= p.wg_first_point && b <= p.wg_last_point && b < p.N && b >= 0; };
   auto src = [&](uint32_t row, int b) { return p.sumsq[row + (uint32_t)(p.first_xpoint + (b - p.wg_first_point))]; };   // fft1.c:121-126
+  // lines [L0, L1) are completed by this walk (none in the hand-back launch)
+  // handback == 2: one walk does both (1:1 mapping with one thread per unit: it reads and writes only its own sum)
+  const int L0 = handback == 1 ? lg.nl : line_first + (int)blockIdx.y * lps;
+  int L1 = handback == 1 ? lg.nl : L0 + lps;
+  if (L1 > lg.nl) L1 = lg.nl;
+  if (!handback && L0 >= L1) return;
+  // rows [rs, re) and the state the sequential walk has on entering row rs
+  const int rs = L0 == 0 ? 0 : lg.rf + (L0 - 1) * lg.rl;
+  const int re = handback ? p.wrows : lg.rf + (L1 - 1) * lg.rl;
+  int counter = L0 == 0 ? p.counter0 : 0;
+  int ptr = p.waterf_ptr0 - (int)(((long long)L0 * p.xpixels) % p.waterf_size);
+  if (ptr < 0) ptr += p.waterf_size;
+  float acc[2];
   if (mode != 1) {
-    for (int k = 0; k < nb; k++) acc[k] = (b0 + k >= 0 && b0 + k < p.N) ? p.wsum[b0 + k] : 0.f;
+    for (int k = 0; k < nb; k++) {
+      const int b = b0 + k;
+      acc[k] = (b >= 0 && b < p.N) ? ((L0 == 0 || !in_wg(b)) ? p.wsum[b] : 0.00001f) : 0.f;
+    }
   }
-  uint32_t row = p.pwg0;
-  int seg_start = 0;                // first row of the current (unfinished) line, mode 1
+  uint32_t row = (p.pwg0 + (uint32_t)rs * (uint32_t)p.N) & p.sumsq_mask;
+  int seg_start = rs;               // first row of the current (unfinished) line, mode 1
   // modes 0 and 2: the rows' values are fetched twelve rows at a time (loads in flight together),
   // the sums are formed in row order
   constexpr int G = 12;
   float pre[2][G];
-  for (int r = 0; r < p.wrows; r++) {
+  for (int r = rs; r < re; r++) {
     if (mode != 1) {
-      const int g = r % G;
+      const int g = (r - rs) % G;
       if (g == 0) {
         uint32_t rw = row;
 #pragma unroll
         for (int gg = 0; gg < G; gg++) {
 #pragma unroll
-          for (int k = 0; k < 2; k++) pre[k][gg] = (k < nb && r + gg < p.wrows && in_wg(b0 + k)) ? __ldg(&p.sumsq[rw + (uint32_t)(p.first_xpoint + (b0 + k - p.wg_first_point))]) : 0.f;
+          for (int k = 0; k < 2; k++) pre[k][gg] = (k < nb && r + gg < re && in_wg(b0 + k)) ? __ldg(&p.sumsq[rw + (uint32_t)(p.first_xpoint + (b0 + k - p.wg_first_point))]) : 0.f;
           rw = (rw + p.N) & p.sumsq_mask;
         }
       }
@@ -181,7 +237,7 @@ __global__ void __launch_bounds__(256) waterfall_kernel(const WgK p, int mode, i
           if (b >= p.N) break;
           float v = p.wsum[b];
           if (in_wg(b)) {
-            if (seg_start > 0) v = 0.00001f;          // reset by the previous line of this call
+            if (seg_start > 0) v = 0.00001f;          // reset by the previous line
             uint32_t rr = (p.pwg0 + (uint32_t)seg_start * (uint32_t)p.N) & p.sumsq_mask;
             for (int q = seg_start; q <= r; q++) { v = __fadd_rn(v, src(rr, b)); rr = (rr + p.N) & p.sumsq_mask; }
           }
@@ -220,7 +276,8 @@ __global__ void __launch_bounds__(256) waterfall_kernel(const WgK p, int mode, i
       if (ptr < 0) ptr += p.waterf_size;
     }
   }
-  // hand the running sums back
+  if (!handback) return;
+  // ---- hand the running sums back (the rows after the last complete line)
   if (mode == 0) {
     if (in_wg(u)) p.wsum[u] = acc[0];
   } else if (mode == 2) {

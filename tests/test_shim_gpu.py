@@ -45,7 +45,9 @@ def test_shim_inside_the_reference(mode, ch, ver, n, sinpow):
     e3_all, e3_rest = rel_rms(got["timf3"][:, 0], ref["timf3"][:, 0]), rel_rms(got["timf3"][1:, 0], ref["timf3"][1:, 0])
     parity_record(kind="shim_timf3", fft1_n=n, mode=mode, timf3_rel_rms_all_blocks=e3_all, timf3_rel_rms_without_block0=e3_rest,
                   fft1_rel_rms=rel_rms(got["fft1"], ref["fft1"]))
-    assert e3_rest <= 1e-4
+    # all blocks, the first one included; measured 0.4e-5 ... 2.3e-5 (profiles/r2_parity_report.jsonl).  The reference's own CUDA
+    # row against its CPU row on the same input: 3.3e-5 (tests/test_reference_cufft_gpu.py)
+    assert e3_all <= 3e-5 and e3_rest <= 3e-5, (e3_all, e3_rest)
     # the reference's own consumers ran on the shim's output: slowsum / waterfall stay consistent
     assert np.allclose(got["ref"].slowsum(), ref["ref"].slowsum(), rtol=2e-4, atol=1e-3 * float(np.abs(ref["ref"].slowsum()).max()))
 
@@ -126,7 +128,9 @@ def test_shim_mix1_afc(mode, ch, ver, sinpow):
     e3_all, e3_rest = rel_rms(got["timf3"][:, 0], ref["timf3"][:, 0]), rel_rms(got["timf3"][1:, 0], ref["timf3"][1:, 0])
     parity_record(kind="shim_timf3", fft1_n=n, mode=mode, timf3_rel_rms_all_blocks=e3_all, timf3_rel_rms_without_block0=e3_rest,
                   fft1_rel_rms=rel_rms(got["fft1"], ref["fft1"]))
-    assert e3_rest <= 1e-4
+    # all blocks, the first one included; measured 0.4e-5 ... 2.3e-5 (profiles/r2_parity_report.jsonl).  The reference's own CUDA
+    # row against its CPU row on the same input: 3.3e-5 (tests/test_reference_cufft_gpu.py)
+    assert e3_all <= 3e-5 and e3_rest <= 3e-5, (e3_all, e3_rest)
     assert got["timf3_pa"] == ref["timf3_pa"]
 
 

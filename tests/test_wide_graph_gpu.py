@@ -102,6 +102,59 @@ def test_wide_graph_interpolated_full():
     _wg_case(0, 2, chunks=(9,))
 
 
+@pytest.mark.parametrize("xpp,ppx,first_xpoint,xpoints,change_flag,waterfall_avgnum,odd_ring", [
+    (1, 1, 0, None, 0, 10, 0), (1, 1, 100, 600, 1, 10, 0), (4, 0, 0, None, 0, 15, 0), (0, 3, 100, 300, 0, 10, 0),
+    (0, 2, 0, None, 1, 5, 0), (1, 1, 0, None, 0, 3, 0), (1, 1, 0, None, 0, 10, 37), (0, 3, 100, 300, 0, 5, 11)])
+def test_wide_graph_many_rows_in_one_call_equal_row_by_row(xpp, ppx, first_xpoint, xpoints, change_flag, waterfall_avgnum, odd_ring):
+    """A batch call hands over hundreds of rows at once (bench: 1184 at configs[0]): the kernels then skip to the
+    last from-scratch recalculation of a bin (slowsum) and write all waterfall lines of the call side by side.  That
+    has to be the sequential walk bit for bit: 57 rows in one call, in uneven chunks and one at a time, on a random
+    ring, for the three pixel mappings, with and without the change flag and with lines every 1, 2 and 3 rows."""
+    s = sizing.PathSetup(input_mode=IQ_DATA, rf_channels=1, ad_speed=96000, fft1_n=10, mix1_red_n=3,
+                         first_xpoint=first_xpoint, xpoints=xpoints if xpoints is not None else -1)
+    N = s.fft1_size
+    rows_total, ring_rows = 57, 64
+    rng = np.random.default_rng(3)
+    ring = (rng.random(ring_rows * N, dtype=np.float32) * 1e6 + 1.0).astype(np.float32)
+    wg_first = s.first_xpoint
+    wg_last = min(s.first_xpoint + s.xpoints, N - 1)
+    if xpp > 1:
+        xpix = s.xpoints // xpp
+    elif ppx > 1:
+        xpix = s.xpoints * ppx
+    else:
+        xpix = min(s.xpoints, N - s.first_xpoint)
+    wgc = api.WgConfig(s.avg2num, waterfall_avgnum, s.first_xpoint, s.xpoints, wg_first, wg_last, xpix, xpp, ppx, 100)
+    yfac = (rng.random(N, dtype=np.float32) * 1e-3 + 1e-4).astype(np.float32)
+    wsize = xpix * 5 + odd_ring                        # the line pointer wraps many times; odd: lines overlap partially
+    results = []
+    plan = api.Plan(s)
+    try:
+        for chunks in ((rows_total,), (1,), (7, 2, 13)):
+            state = api.WgState(0, s.fft1_first_point, change_flag, 0, 0, 0)
+            slowsum = np.zeros(N, np.float32)
+            wsum = np.full(N, 0.00001, np.float32)
+            waterf = np.full(wsize + xpix + 64, -32768, np.int16)
+            done = ci = 0
+            while done < rows_total:
+                n = min(chunks[ci % len(chunks)], rows_total - done)
+                ci += 1
+                api.wide_graph_host(plan, wgc, state, sumsq=ring, sumsq_pa=(done * N) % ring.size, nrows=n, slowsum=slowsum,
+                                    wsum=wsum, yfac=yfac, waterf=waterf, waterf_size=wsize)
+                done += n
+            results.append((slowsum, wsum, waterf, (state.fft1_sumsq_recalc, state.wg_waterf_ptr, state.wg_waterf_sum_counter,
+                                                    state.fft1_sumsq_pwg, state.latest_wg_spectrum, state.change_fft1_flag)))
+    finally:
+        plan.close()
+    ref = results[1]                                   # row by row
+    assert (ref[2] != -32768).sum() >= min(wsize, xpix)
+    for got in (results[0], results[2]):
+        assert got[3] == ref[3]
+        assert np.array_equal(got[0].view(np.uint32), ref[0].view(np.uint32))
+        assert np.array_equal(got[1].view(np.uint32), ref[1].view(np.uint32))
+        assert np.array_equal(got[2], ref[2])
+
+
 # ---------------------------------------------------------------------------------------------
 def test_expand_rawdat_bit_exact():
     s = sizing.PathSetup(input_mode=IQ_DATA, rf_channels=1, ad_speed=96000, fft1_n=10, mix1_red_n=3)
