@@ -587,6 +587,48 @@ def measure(wl, steps, warmup, dist, step_ms=STEP_MS, clocks_index=None):
             "clocks": sampler.summary() if sampler else None, "timed_region_s": ms * 1e-3}
 
 
+def measure_timf2(wl, reps=5):
+    """make_timf2 (strong/weak split, back transform, fft1back_fp_finish) over the spectra the
+    pass has just left in fft1_float, device resident, timed with events on the plan's stream."""
+    torch, api, s = wl.torch, wl.api, wl.s
+    if s.fft1_n > 14 or not (s.input_mode & sizing.IQ_DATA):
+        return None
+    N, C, B = s.fft1_size, s.rf_channels, wl.B
+    newp = s.fft1_new_points
+    sf = 4 * C
+    ring = pow2_at_least(sf * (B * newp + N))
+    st = wl.streams[0]
+    timf2 = torch.zeros(ring, dtype=torch.float32, device=wl.dev)
+    pwr = torch.zeros(ring // sf, dtype=torch.float32, device=wl.dev)
+    lim = np.zeros(N, np.float32)
+    rng = np.random.default_rng(1)
+    for _ in range(12):                                     # a dozen strong carriers, as fft1_update_liminfo leaves them
+        a = int(rng.integers(0, N - 40))
+        lim[a: a + int(rng.integers(1, 40))] = float(rng.uniform(0.01, 1.0))
+    liminfo = torch.from_numpy(lim).to(wl.dev)
+    wl.one_pass()
+    times = []
+    for i in range(reps + 2):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(wl.stream)
+        api.make_timf2_dev(wl.plan, fft1=st["fft1"].data_ptr(), fft1_floats=wl.fft1_floats, fft1_px=0, nblocks=B,
+                           liminfo=liminfo.data_ptr(), timf2=timf2.data_ptr(), timf2_floats=ring, timf2_pwr=pwr.data_ptr(), timf2_pa=0)
+        e1.record(wl.stream)
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    alg = B * (8 * C * N + 16 * C * newp + 4 * newp)       # spectra in, [weak, strong] samples and |weak|^2 out
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    out = {"what": "lb200_make_timf2_dev (timf2_back_kernel + timf2_finish_kernel), transforms of the pass, device resident",
+           "transforms": B, "ms": ms, "algorithmic_bytes": alg, "achieved_GBps": alg / (ms * 1e-3) / 1e9,
+           "frac": alg / (ms * 1e-3) / 1e9 / peak, "Msamples_per_s": B * samples_per_transform(s) / (ms * 1e-3) / 1e6}
+    del timf2, pwr
+    return out
+
+
 def run_e2e(wl, args, dist):
     """end to end through the host-buffer C ABI: the call a Linrad-side host makes"""
     torch, api, s = wl.torch, wl.api, wl.s
@@ -673,10 +715,14 @@ def run_e2e(wl, args, dist):
             dt = float(t.item())
         gbs = 4 * nbytes / dt / 1e9
         bytes_per_sample = (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / (Be * spt)
+        # the two directions run side by side: the busier one bounds the step
+        busier = max(e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"]) / (Be * spt)
         e2e["pcie_probe"] = {"concurrent_gpus": world, "GBps_per_gpu_each_direction": gbs, "GBps_all_gpus_both_directions": 2 * gbs * world,
-                             "e2e_bytes_per_sample": bytes_per_sample,
-                             "e2e_ceiling_Msamples_per_s": 2 * gbs * 1e9 * world / bytes_per_sample / 1e6,
-                             "what": "256 MiB pinned copies H2D and D2H at the same time on every GPU of the run, slowest rank"}
+                             "e2e_bytes_per_sample": bytes_per_sample, "e2e_bytes_per_sample_busier_direction": busier,
+                             "e2e_ceiling_Msamples_per_s": gbs * 1e9 * world / busier / 1e6,
+                             "e2e_GBps_busier_direction_per_gpu": e2e["value"] * 1e6 * busier / world / 1e9,
+                             "what": "256 MiB pinned copies H2D and D2H at the same time on every GPU of the run, slowest rank; "
+                                     "ceiling = that rate / bytes per sample of the busier direction (D2H: fft1_float comes back)"}
         del hp_in, hp_out, dv_in, dv_out
     except Exception as ex:
         e2e["pcie_probe"] = {"error": str(ex)}
@@ -765,6 +811,12 @@ def main():
                                 "frac": r["roofline"]["frac"], "kernel_ms": r["roofline"]["kernel_ms"],
                                 "kernel": r["roofline"]["kernel"], "achieved_GBps": r["roofline"]["achieved"],
                                 "traffic": r["roofline"]["traffic"], "whole_step_frac": r["roofline"]["whole_step_frac"]}
+            try:
+                t2 = measure_timf2(w2)
+                if t2:
+                    per_config[name]["make_timf2"] = t2
+            except Exception as ex:                        # a widened row must not take the headline down
+                per_config[name]["make_timf2"] = {"error": str(ex)}
             w2.close()
             del w2
             torch.cuda.empty_cache()

@@ -403,6 +403,23 @@ def make_timf2_host(plan, *, fft1, fft1_px, nblocks, liminfo, timf2, timf2_pwr, 
     return low.value
 
 
+def make_timf2_dev(plan, *, fft1, fft1_floats, fft1_px, nblocks, liminfo, timf2, timf2_floats, timf2_pwr, timf2_pa, att_n=0):
+    """make_timf2 on raw device addresses (liminfo on the device too)"""
+    a = Timf2Args()
+    a.fft1_float = Ring(fft1, fft1_floats)
+    a.fft1_px = fft1_px
+    a.nblocks = nblocks
+    a.liminfo = liminfo
+    a.timf2_float = Ring(timf2, timf2_floats)
+    a.timf2_pwr_float = timf2_pwr
+    a.timf2_pa = timf2_pa
+    a.first_bckfft_att_n = att_n
+    plan.lib.lb200_make_timf2_dev.argtypes = [C.c_void_p, C.POINTER(Timf2Args)]
+    rc = plan.lib.lb200_make_timf2_dev(plan.h, C.byref(a))
+    if rc:
+        raise Lb200Error(rc, "lb200_make_timf2_dev")
+
+
 def widen_8bit_host(plan, pcm8):
     """8-bit unsigned PCM -> int16 (rxin.c:1573-1583)"""
     pcm8 = np.ascontiguousarray(pcm8, np.uint8)
