@@ -36,6 +36,9 @@ extern "C" {
 #define LB200_DWORD_INPUT 1
 #define LB200_TWO_CHANNELS 2
 #define LB200_IQ_DATA 4
+#define LB200_FLOAT_INPUT 64      /* globdef.h:283 FLOAT_INPUT; with IQ_DATA|DWORD_INPUT: frames of floats [re, im] (x channels).
+                                      This is how the third FFT's transforms (make_fft3_all, fft3.c:215-470) run: a second
+                                      plan whose timf1 ring is Linrad's timf3_float and whose fft1_float ring is fft3 */
 
 /* error codes (new lirerr numbers; 3100-3119 are unused in errors.lir) */
 #define LB200_OK 0

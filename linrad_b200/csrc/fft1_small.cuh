@@ -22,7 +22,10 @@ namespace lb {
 // consecutive frames are packed as one complex point z[m] = x[2m] + i x[2m+1]; FRAME is then
 // the byte size of the PAIR of frames.
 enum InFmt { FMT_I16_1CH = 0, FMT_I16_2CH = 1, FMT_I32_1CH = 2, FMT_I32_2CH = 3,
-             FMT_R16_1CH = 4, FMT_R16_2CH = 5, FMT_R32_1CH = 6, FMT_R32_2CH = 7 };
+             FMT_R16_1CH = 4, FMT_R16_2CH = 5, FMT_R32_1CH = 6, FMT_R32_2CH = 7,
+             // float IQ frames [re, im] / [re1, im1, re2, im2]: the timf3 baseband ring as input of the
+             // third FFT (make_fft3_all, fft3.c:215-470) -- same frame geometry as the int32 formats
+             FMT_F32_1CH = 8, FMT_F32_2CH = 9 };
 template <int FMT> struct FmtInfo;
 template <> struct FmtInfo<FMT_I16_1CH> { static constexpr int FRAME = 4, NCH = 1; static constexpr bool REAL = false; };
 template <> struct FmtInfo<FMT_I16_2CH> { static constexpr int FRAME = 8, NCH = 2; static constexpr bool REAL = false; };
@@ -32,6 +35,8 @@ template <> struct FmtInfo<FMT_R16_1CH> { static constexpr int FRAME = 4, NCH = 
 template <> struct FmtInfo<FMT_R16_2CH> { static constexpr int FRAME = 8, NCH = 2; static constexpr bool REAL = true; };
 template <> struct FmtInfo<FMT_R32_1CH> { static constexpr int FRAME = 8, NCH = 1; static constexpr bool REAL = true; };
 template <> struct FmtInfo<FMT_R32_2CH> { static constexpr int FRAME = 16, NCH = 2; static constexpr bool REAL = true; };
+template <> struct FmtInfo<FMT_F32_1CH> { static constexpr int FRAME = 8, NCH = 1; static constexpr bool REAL = false; };
+template <> struct FmtInfo<FMT_F32_2CH> { static constexpr int FRAME = 16, NCH = 2; static constexpr bool REAL = false; };
 
 struct Fft1K {
   const uint8_t* timf1;     // device ring
@@ -81,6 +86,8 @@ LB_D float2 load_iq_skew(const uint8_t* ring, uint32_t mask, uint32_t off, int s
   const uint32_t oi = (off + (uint32_t)skew_i) & mask, oq = (off + (uint32_t)skew_q) & mask;
   if (FMT == FMT_I16_1CH)
     return make_float2((float)*reinterpret_cast<const short*>(ring + oi), (float)*reinterpret_cast<const short*>(ring + oq + 2));
+  if (FMT == FMT_F32_1CH)
+    return make_float2(*reinterpret_cast<const float*>(ring + oi), -*reinterpret_cast<const float*>(ring + oq + 4));
   return make_float2((float)*reinterpret_cast<const int*>(ring + oi), (float)*reinterpret_cast<const int*>(ring + oq + 4));
 }
 
@@ -99,6 +106,14 @@ LB_D float2 load_iq(const uint8_t* ring, uint32_t off, int c)
   } else if (FMT == FMT_I32_2CH) {
     const int2 w = *reinterpret_cast<const int2*>(ring + off + 8 * c);
     return make_float2((float)w.x, (float)w.y);
+  } else if (FMT == FMT_F32_1CH) {
+    // make_fft3_all transforms x, fft1_b transforms conj(x) (probed on the compiled reference: fft3 =
+    // sum x w exp(+2 pi i n (k - N/2)/N), fft1 the same sum over conj(x)): conjugate on the way in
+    const float2 z = *reinterpret_cast<const float2*>(ring + off);
+    return make_float2(z.x, -z.y);
+  } else if (FMT == FMT_F32_2CH) {
+    const float2 z = *reinterpret_cast<const float2*>(ring + off + 8 * c);
+    return make_float2(z.x, -z.y);
   } else if (FMT == FMT_R16_1CH) {                     // [x(2m), x(2m+1)]
     const uint32_t w = *reinterpret_cast<const uint32_t*>(ring + off);
     return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));

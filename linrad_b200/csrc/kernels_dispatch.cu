@@ -12,6 +12,8 @@ fft1_small_launch_t lb_get_fft1_small_fmt4(int, int, int*, size_t*);
 fft1_small_launch_t lb_get_fft1_small_fmt5(int, int, int*, size_t*);
 fft1_small_launch_t lb_get_fft1_small_fmt6(int, int, int*, size_t*);
 fft1_small_launch_t lb_get_fft1_small_fmt7(int, int, int*, size_t*);
+fft1_small_launch_t lb_get_fft1_small_fmt8(int, int, int*, size_t*);
+fft1_small_launch_t lb_get_fft1_small_fmt9(int, int, int*, size_t*);
 
 fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* threads, size_t* smem)
 {
@@ -24,6 +26,8 @@ fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* thre
     case 5: return lb_get_fft1_small_fmt5(log2n, variant, threads, smem);
     case 6: return lb_get_fft1_small_fmt6(log2n, variant, threads, smem);
     case 7: return lb_get_fft1_small_fmt7(log2n, variant, threads, smem);
+    case 8: return lb_get_fft1_small_fmt8(log2n, variant, threads, smem);
+    case 9: return lb_get_fft1_small_fmt9(log2n, variant, threads, smem);
   }
   return nullptr;
 }

@@ -104,6 +104,11 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
   if (((cfg->rx_input_mode & LB200_TWO_CHANNELS) != 0) != (plan->nch == 2)) return fail(LB200_ERR_BAD_CONFIG);
   plan->frame = (plan->iq ? 2 : 1) * plan->nch * (dword ? 4 : 2);
   plan->fmt = (plan->iq ? 0 : 4) + (dword ? 2 : 0) + (plan->nch == 2 ? 1 : 0);
+  if (cfg->rx_input_mode & LB200_FLOAT_INPUT) {
+    // float IQ frames: the timf3 ring as input of the third FFT (fft3.c:215-470); 2^7..2^14 points
+    if (!plan->iq || !dword || cfg->fft1_n > 14 || cfg->fft1_n < 7) return fail(LB200_ERR_UNSUPPORTED);
+    plan->fmt = FMT_F32_1CH + (plan->nch == 2 ? 1 : 0);
+  }
   plan->fft1_block = plan->mm * plan->N;
   if (cfg->fft1_interleave_points < 0 || cfg->fft1_interleave_points >= plan->N) return fail(LB200_ERR_BAD_CONFIG);
   plan->new_points = plan->N - cfg->fft1_interleave_points;
@@ -487,7 +492,7 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
     return 0;
   };
   const int group = k.power_rows ? 1 : k.avg1num;
-  if (plan->cfg.fft1_n >= 10 && !env_int("LB200_FFT1_LEGACY", 0)) {
+  if (plan->cfg.fft1_n >= 10 && plan->fmt < FMT_F32_1CH && !env_int("LB200_FFT1_LEGACY", 0)) {
     // fused 32-points-per-thread kernel
     const bool full = (k.first_point == 0 && k.last_point == plan->N - 1);
     int fc = FC_TABLE;

@@ -13,6 +13,7 @@
  *   lb200_shim_fft1_c()        in place of fft1_c()           (wcw.c:338,366,423,1069,1098)
  *   lb200_shim_mix1_fixed()    in place of fft1_mix1_fixed()  (wcw.c:1700,1712)
  *   lb200_shim_make_timf2()    in place of make_timf2()       (timf2.c:31; second FFT enabled, float path)
+ *   lb200_shim_fft3_transforms() in place of the transform half of make_fft3_all() (fft3.c:215-470)
  *
  * fft1_b and fft1_c stay two calls on two threads, as in Linrad, but the arithmetic of both
  * runs in ONE kernel: lb200_shim_fft1_b asks the library for the filter-corrected spectrum and
@@ -380,3 +381,71 @@ fft1_lowlevel_fraction=0.02*(49*fft1_lowlevel_fraction+fft1_lowlevel_points/
 timf2_pa=(timf2_pa+timf2_input_block)&timf2_mask;
 }
 
+
+
+/* ---- third FFT: the transforms of make_fft3_all (fft3.c:215-470) -------------------------------------
+ * A second plan whose input ring is timf3_float (float IQ frames, LB200_FLOAT_INPUT) and whose output ring
+ * is fft3.  Call lb200_shim_fft3_open() where baseb_graph.c:3679-3680 has just built fft3_tab / fft3_window
+ * (init_basebmem), lb200_shim_fft3_close() where it frees them.  make_fft3_all is split in two in Linrad:
+ *   void make_fft3_all(void){ if(fft1_use_gpu == GPU_LB200)lb200_shim_fft3_transforms(); else <the loop over ss>;
+ *                             <fft3.c:471 on: powers, slowsum, waterfall, index bookkeeping, unchanged> }
+ */
+static lb200_plan *shim_fft3_plan;
+static float *shim_fft3_window;
+void lb200_shim_fft3_close(void)
+{
+if(shim_fft3_plan)lb200_destroy(shim_fft3_plan);
+shim_fft3_plan=NULL;
+free(shim_fft3_window); shim_fft3_window=NULL;
+}
+int lb200_shim_fft3_open(void)
+{
+lb200_config c;
+int rc;
+lb200_shim_fft3_close();
+if(fft1_correlation_flag > 1){shim_fail(LB200_ERR_UNSUPPORTED); return -1;}   /* the double precision branch, fft3.c:281-421 */
+memset(&c,0,sizeof(c));
+c.abi_version=LB200_ABI_VERSION;
+c.device=0;
+c.rx_input_mode=IQ_DATA|DWORD_INPUT|LB200_FLOAT_INPUT;
+if(ui.rx_rf_channels == 2)c.rx_input_mode|=TWO_CHANNELS;
+c.rx_rf_channels=ui.rx_rf_channels;
+c.fft1_n=fft3_n;
+c.fft1_interleave_points=fft3_size-fft3_new_points;
+c.fft1_direction=1;
+c.fft1_first_point=0;
+c.fft1_last_point=fft3_size-1;
+shim_fft3_window=malloc((size_t)fft3_size*sizeof(float));
+if(shim_fft3_window == NULL){shim_fail(LB200_ERR_BAD_CONFIG); return -1;}
+lb200_window_to_natural(1, fft3_size, fft3_window, shim_fft3_window);      /* make_window(1,...), baseb_graph.c:3680 */
+c.fft1_window=shim_fft3_window;
+c.fft_avg1num=1;
+c.max_batch=1;
+c.pg_ch2_c1=1;
+rc=lb200_create(&c,&shim_fft3_plan);
+if(rc != LB200_OK){shim_fft3_plan=NULL; shim_fail(rc); return -1;}
+return 0;
+}
+void lb200_shim_fft3_transforms(void)
+{
+lb200_fft1_args a;
+int ss, rc, mm;
+mm=twice_rxchan;
+for(ss=0; ss<genparm[MIX1_NO_OF_CHANNELS]; ss++)
+  {
+  if(mix1_selfreq[ss] < 0)continue;
+  memset(&a,0,sizeof(a));
+  a.timf1.base=&timf3_float[ss*mm*timf3_size];                 /* poffs, fft3.c:232 */
+  a.timf1.size=((size_t)timf3_mask+1)*sizeof(float);
+  /* lb200_fft1 reads the fft3_size frames that begin fft1_interleave_points frames before the reference */
+  a.timf1p_ref=(uint32_t)(((size_t)timf3_px*sizeof(float)+
+                 (size_t)(fft3_size-fft3_new_points)*mm*sizeof(float))&(a.timf1.size-1));
+  a.nblocks=1;
+  a.fft1_float.base=fft3;
+  a.fft1_float.size=(size_t)fft3_mask+1;
+  a.fft1_pa=(uint32_t)((fft3_pa+ss*mm*fft3_size)&fft3_mask);   /* z, fft3.c:233 */
+  a.apply_filtercorr=0;
+  rc=lb200_fft1(shim_fft3_plan,&a);
+  if(rc != LB200_OK){shim_fail(rc); return;}
+  }
+}

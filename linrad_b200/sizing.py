@@ -18,6 +18,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 DWORD_INPUT, TWO_CHANNELS, IQ_DATA = 1, 2, 4      # globdef.h:277-279
+FLOAT_INPUT = 64                                  # globdef.h:283 (float frames: the timf3 ring as input of the third FFT)
 PI_L = 3.1415926535897932                          # globdef.h:93
 FFT1_WATERFALL_ZERO = 0.14                         # graphcal.h:12
 f32 = np.float32

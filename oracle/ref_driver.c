@@ -688,3 +688,67 @@ int ref_lowlevel_points(void) { return fft1_lowlevel_points; }
 float *ref_inverted_window(void) { return fft1_inverted_window; }
 void ref_set_fft1_block(int block_index, const float *v) { memcpy(&fft1_float[(size_t)block_index * fft1_block], v, sizeof(float) * fft1_block); }
 
+
+
+/* ---- third FFT, transform half of make_fft3_all (fft3.c:215-470) ------------------------------------
+ * Tables as baseb_graph.c:3679-3680 builds them (init_fft(1,..), make_window(1,..)), buffers as
+ * baseb_graph.c:3481-3487.  With THREAD_FFT3 not ACTIVE make_fft3_all returns right after the transforms
+ * (fft3.c:470-471), before the baseband-graph power / waterfall half and before it advances timf3_px and
+ * fft3_pa, so the harness steps the indices.  MAX_MIX1 == 1: one selection (ss = 0, poffs = 0). */
+#ifdef LB200_USE_SHIM
+int lb200_shim_fft3_open(void);
+void lb200_shim_fft3_transforms(void);
+#endif
+static float *fft3_test_ring;
+static int fft3_new_points_req;
+void ref_set_fft3_new_points(int n) { fft3_new_points_req = n; }
+int ref_fft3_setup(int n, int sinpow, int ring_floats)
+{
+  if (!inited) return -1;
+  fft3_n = n;
+  fft3_size = 1 << n;
+  fft3_block = fft3_size * 2 * ui.rx_rf_channels * MAX_MIX1;          /* baseb_graph.c:3409 */
+  fft3_totsiz = 4 * fft3_block * 4;
+  fft3_mask = fft3_totsiz - 1;
+  fft3 = zalloc(sizeof(float) * fft3_totsiz);
+  fft3_tmp = zalloc(4 * (size_t)fft3_size * ui.rx_rf_channels * sizeof(float) + 64);
+  fft3_tab = zalloc(fft3_size * sizeof(COSIN_TABLE) / 2 + 64);
+  fft3_permute = zalloc(fft3_size * sizeof(short int) + 64);
+  fft3_window = zalloc(fft3_size * sizeof(float) + 64);
+  genparm[THIRD_FFT_SINPOW] = sinpow;
+  init_fft(1, fft3_n, fft3_size, fft3_tab, fft3_permute);
+  make_window(1, fft3_size, sinpow, fft3_window);
+  fft3_new_points = fft3_new_points_req > 0 ? fft3_new_points_req : fft3_size / 2;
+  fft3_pa = 0;
+  yieldflag_ndsp_fft3 = 0;
+  thread_command_flag[THREAD_FFT3] = THRFLAG_IDLE;
+  genparm[MIX1_NO_OF_CHANNELS] = 1;
+  mix1_selfreq[0] = 1000.0;
+  old_mix1_selfreq = mix1_selfreq[0];
+  free(fft3_test_ring);
+  fft3_test_ring = zalloc(sizeof(float) * (size_t)ring_floats);
+  timf3_float = fft3_test_ring;
+  timf3_size = ring_floats;
+  timf3_mask = ring_floats - 1;
+#ifdef LB200_USE_SHIM
+  if (lb200_shim_fft3_open() != 0) return ref_last_lirerr ? ref_last_lirerr : -1;
+#endif
+  return 0;
+}
+/* one make_fft3_all on the given ring contents with timf3_px = px; out = twice_rxchan*fft3_size floats */
+int ref_make_fft3(const float *ring, int px, float *out)
+{
+  memcpy(fft3_test_ring, ring, sizeof(float) * (size_t)timf3_size);
+  timf3_float = fft3_test_ring;
+  timf3_px = px;
+  fft3_pa = 0;
+#ifdef LB200_USE_SHIM
+  /* Linrad with the library plugged in: the transform half of make_fft3_all through the shim */
+  lb200_shim_fft3_transforms();
+#else
+  make_fft3_all();
+#endif
+  memcpy(out, &fft3[fft3_pa], sizeof(float) * twice_rxchan * fft3_size);
+  return ref_last_lirerr;
+}
+float *ref_fft3_window(void) { return fft3_window; }

@@ -30,6 +30,11 @@ void lir_text(int x, int y, char *txt) { (void)x; (void)y; (void)txt; }
 void lir_pixwrite(int x, int y, char *s) { (void)x; (void)y; (void)s; }
 void settextcolor(unsigned char color) { (void)color; }
 void awake_screen(void) {}
+/* fft3.c (make_fft3_all): only its transform part is driven, these belong to the display half */
+void add_mix1_cursor(int n) { (void)n; }
+void clear_thread_times(int n) { (void)n; }
+void lir_await_event(int n) { (void)n; }
+void parabolic_fit(float *amp, float *pos, float yy1, float yy2, float yy3) { (void)yy1; (void)yy2; (void)yy3; *amp = 0; *pos = 0; }
 void eliminate_spurs(void) {}
 void spursearch_spectrum_cleanup(void) {}
 void expand_foldcorr(float *x, float *tmp) { (void)x; (void)tmp; }

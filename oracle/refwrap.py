@@ -181,6 +181,29 @@ class RefOracle:
             return None
         return np.ctypeslib.as_array(p, shape=(self.fft1_size // 2 + 1,)).copy()
 
+    # ---- third FFT: the transform half of the reference's own make_fft3_all (fft3.c:215-470)
+    def fft3_setup(self, n, sinpow, ring_floats, new_points=0):
+        self.lib.ref_set_fft3_new_points(new_points)
+        self.lib.ref_fft3_window.restype = C.POINTER(C.c_float)
+        self.lib.ref_make_fft3.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        rc = self.lib.ref_fft3_setup(n, sinpow, ring_floats)
+        if rc != 0:
+            raise RuntimeError(f"ref_fft3_setup failed rc={rc}")
+        self.fft3_size = 1 << n
+        self.fft3_ring_floats = ring_floats
+
+    def make_fft3(self, ring, px):
+        ring = np.ascontiguousarray(ring, np.float32)
+        assert ring.size == self.fft3_ring_floats
+        out = np.zeros(2 * self.cfg.rf_channels * self.fft3_size, np.float32)
+        rc = self.lib.ref_make_fft3(ring.ctypes.data, px, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"reference raised lirerr({rc})")
+        return out
+
+    def fft3_window(self):
+        return np.ctypeslib.as_array(self.lib.ref_fft3_window(), shape=(self.fft3_size,)).copy()
+
     def process_timed(self, raw, nblocks):
         return self.lib.ref_process_timed(raw.ctypes.data, nblocks)
 

@@ -163,3 +163,24 @@ def test_shim_make_timf2(sinpow, ch, mode, ver):
     assert np.abs(got["pwr"].astype(np.float64) - ref["pwr"]).max() <= 2e-5 * np.abs(ref["pwr"]).max()
     assert np.array_equal(got["timf2"] == 0, ref["timf2"] == 0)
 
+
+
+@pytest.mark.parametrize("n,ch,sinpow,new_points", [(10, 1, 2, 0), (12, 1, 3, 1536), (9, 2, 2, 0)])
+def test_shim_fft3_transforms(n, ch, sinpow, new_points):
+    """the transform half of make_fft3_all inside the compiled reference through lb200_shim_fft3_transforms (a second
+    plan on the timf3 ring, LB200_FLOAT_INPUT) against the reference's own make_fft3_all on the same ring"""
+    from oracle.refwrap import RefOracle
+    mode = IQ_DATA | (TWO_CHANNELS if ch == 2 else 0)
+    kw = dict(input_mode=mode, rf_channels=ch, ad_speed=96000, fft1_n=10, fft1_version=6 if ch == 1 else 7, n_sel=0)
+    N = 1 << n
+    ring_floats = 8 * N * 2 * ch
+    rng = np.random.default_rng(n)
+    ring = (rng.standard_normal(ring_floats) * 2000.0).astype(np.float32)
+    a = RefOracle(**kw)
+    a.fft3_setup(n, sinpow, ring_floats, new_points)
+    b = RefOracle(through_shim=True, **kw)
+    b.fft3_setup(n, sinpow, ring_floats, new_points)
+    for px in (0, 2 * ch * 100, ring_floats - 2 * ch * (N // 2)):          # the last one wraps
+        want = a.make_fft3(ring, px)
+        got = b.make_fft3(ring, px)
+        assert rel_rms(got, want) <= 1e-5
