@@ -629,6 +629,55 @@ def measure_timf2(wl, reps=5):
     return out
 
 
+def measure_fft3(wl, reps=5):
+    """the transforms of make_fft3_all over the baseband the pass has just left in timf3 (a second
+    plan with float IQ input on that ring): fft3_size = mix1.size, sin^2 window, 50 % overlap, every selection."""
+    torch, api, s = wl.torch, wl.api, wl.s
+    if not wl.nsel or not (s.input_mode & sizing.IQ_DATA) or s.mix1_n < 7 or s.mix1_n > 14:
+        return None
+    C, B = s.rf_channels, wl.B
+    two = sizing.TWO_CHANNELS if C == 2 else 0
+    s3 = sizing.PathSetup(input_mode=sizing.IQ_DATA | sizing.DWORD_INPUT | sizing.FLOAT_INPUT | two, rf_channels=C, ad_speed=96000,
+                          fft1_n=s.mix1_n, mix1_red_n=3, sinpow=2)
+    N3, newp = s3.fft1_size, s3.fft1_new_points
+    per_sel = (B * s.timf3_block // (2 * C) - N3) // newp + 1          # whole transforms inside what one pass wrote
+    if per_sel < 1:
+        return None
+    plan3 = api.Plan(s3, device=wl.dev.index)
+    st = wl.streams[0]
+    out_floats = pow2_at_least(per_sel * s3.fft1_block)
+    out = torch.empty(out_floats, dtype=torch.float32, device=wl.dev)
+    stream3 = torch.cuda.ExternalStream(plan3.stream, device=wl.dev)
+    wl.one_pass()
+    torch.cuda.synchronize()
+    times = []
+    for i in range(reps + 2):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream3)
+        for ss in range(wl.nsel):
+            base = st["timf3"].data_ptr() + ss * 2 * wl.timf3_size * 4
+            plan3.fft1_dev(timf1=base, timf1_bytes=wl.timf3_size * 4, ref=s3.fft1_interleave_points * s3.frame_bytes, nblocks=per_sel,
+                           fft1=out.data_ptr(), fft1_floats=out_floats, fft1_pa=0, apply_fc=False,
+                           sumsq=None, sumsq_floats=0, sumsq_pa=0, counter=0)
+        e1.record(stream3)
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    ntr = per_sel * wl.nsel
+    alg = ntr * (8 * C * newp + 8 * C * N3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    res = {"what": "transform half of make_fft3_all (lb200_fft1_dev on a float-input plan over timf3, fft1_small_kernel), "
+                   "every selection of the pass, device resident",
+           "fft3_size": N3, "transforms": ntr, "calls": wl.nsel, "ms": ms, "algorithmic_bytes": alg,
+           "achieved_GBps": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak}
+    plan3.close()
+    del out
+    return res
+
+
 def run_e2e(wl, args, dist):
     """end to end through the host-buffer C ABI: the call a Linrad-side host makes"""
     torch, api, s = wl.torch, wl.api, wl.s
@@ -817,6 +866,12 @@ def main():
                     per_config[name]["make_timf2"] = t2
             except Exception as ex:                        # a widened row must not take the headline down
                 per_config[name]["make_timf2"] = {"error": str(ex)}
+            try:
+                t3 = measure_fft3(w2)
+                if t3:
+                    per_config[name]["make_fft3"] = t3
+            except Exception as ex:
+                per_config[name]["make_fft3"] = {"error": str(ex)}
             w2.close()
             del w2
             torch.cuda.empty_cache()
