@@ -620,14 +620,31 @@ static int ensure_pipeline(lb200_plan* plan, size_t nevents)
 }
 
 // which blocks of the fft1_float mirror hold what this plan itself produced for the host ring
-static void mark_fft1_valid(lb200_plan* plan, const void* host, size_t ring_floats, size_t pa, int nblocks, bool valid)
+static void mark_fft1_valid(lb200_plan* plan, const void* host, size_t ring_floats, size_t pa, int nblocks, bool valid, int host_stale = -1)
 {
   const size_t nb = ring_floats / plan->fft1_block;
   if (plan->fft1_valid_host != host || plan->fft1_valid.size() != nb) {
     plan->fft1_valid.assign(nb, 0);
+    plan->fft1_host_stale.assign(nb, 0);
     plan->fft1_valid_host = host;
   }
-  for (int b = 0; b < nblocks; b++) plan->fft1_valid[((pa / plan->fft1_block) + b) % nb] = valid ? 1 : 0;
+  for (int b = 0; b < nblocks; b++) {
+    const size_t i = ((pa / plan->fft1_block) + b) % nb;
+    plan->fft1_valid[i] = valid ? 1 : 0;
+    if (host_stale >= 0) plan->fft1_host_stale[i] = (uint8_t)host_stale;
+  }
+}
+// a block that exists neither in the mirror nor in the host ring (it was kept on the device and the mirror copy
+// is not the final spectrum, or has been lapped)
+static bool fft1_block_lost(const lb200_plan* plan, const void* host, size_t ring_floats, size_t px, int nblocks)
+{
+  const size_t nb = ring_floats / plan->fft1_block;
+  if (plan->fft1_valid_host != host || plan->fft1_valid.size() != nb || px % plan->fft1_block) return false;
+  for (int b = 0; b < nblocks; b++) {
+    const size_t i = ((px / plan->fft1_block) + b) % nb;
+    if (!plan->fft1_valid[i] && plan->fft1_host_stale[i]) return true;
+  }
+  return false;
 }
 static bool fft1_mirror_valid(const lb200_plan* plan, const void* host, size_t ring_floats, size_t px, int nblocks)
 {
@@ -641,11 +658,27 @@ static bool fft1_mirror_valid(const lb200_plan* plan, const void* host, size_t r
 // Host rings.  The call is cut into sub-batches that flow through three streams -- input copy,
 // kernels, output copy -- so that the H2D of sub-batch i+1, the kernels of i and the D2H of i-1
 // overlap (PCIe is full duplex and fft1_float going back is twice the size of timf1 coming in).
+static int fft1_host_pipeline(lb200_plan* plan, const lb200_fft1_args* a);
 extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
 {
   if (!plan || !a || !a->timf1.base || !a->fft1_float.base) return LB200_ERR_BAD_ARG;
   if (a->nblocks <= 0) return LB200_OK;
   if (!is_pow2(a->timf1.size) || !is_pow2(a->fft1_float.size)) return LB200_ERR_BAD_ARG;
+  // ring positions travel as 32-bit masks
+  if (a->timf1.size > ((size_t)1 << 32) || a->fft1_float.size > ((size_t)1 << 32) || a->fft1_sumsq.size > ((size_t)1 << 32)) return LB200_ERR_BAD_ARG;
+  const int rc = fft1_host_pipeline(plan, a);
+  if (rc != LB200_OK) {
+    // copies into the caller's memory may still be in flight on the three streams: let them land before the
+    // caller sees the error (and possibly frees its buffers)
+    if (plan->s_in) cudaStreamSynchronize(plan->s_in);
+    if (plan->stream) cudaStreamSynchronize(plan->stream);
+    if (plan->s_out) cudaStreamSynchronize(plan->s_out);
+    cudaGetLastError();
+  }
+  return rc;
+}
+static int fft1_host_pipeline(lb200_plan* plan, const lb200_fft1_args* a)
+{
   cudaSetDevice(plan->device);
   int rc;
   const size_t pre = plan->pre_bytes;
@@ -776,7 +809,8 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
   }
   LB_CUDA(cudaStreamSynchronize(plan->s_out));
   LB_CUDA(cudaStreamSynchronize(plan->stream));
-  if (a->apply_filtercorr) mark_fft1_valid(plan, a->fft1_float.base, a->fft1_float.size, a->fft1_pa, a->nblocks, true);
+  const int stale = (a->flags & LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE) ? 1 : 0;
+  mark_fft1_valid(plan, a->fft1_float.base, a->fft1_float.size, a->fft1_pa, a->nblocks, a->apply_filtercorr != 0, stale);
   return LB200_OK;
 }
 
@@ -923,6 +957,7 @@ static int check_mix1_args(lb200_plan* plan, const lb200_mix1_args* a)
   if (plan->M == 0) return LB200_ERR_BAD_CONFIG;
   if (a->no_of_channels < 1 || a->no_of_channels > LB200_MAX_MIX1) return LB200_ERR_BAD_ARG;
   if (!is_pow2(a->fft1_float.size) || !is_pow2(a->timf3_float.size)) return LB200_ERR_BAD_ARG;
+  if (a->fft1_float.size > ((size_t)1 << 32) || a->timf3_float.size > ((size_t)1 << 31)) return LB200_ERR_BAD_ARG;   // 32-bit ring masks
   const int Mn = plan->M - plan->cfg.mix1_interleave_points;
   // the whole call (plus the parked tail) must fit the ring without lapping itself
   if ((size_t)plan->mm * ((size_t)Mn * a->nblocks + plan->M) > a->timf3_float.size) return LB200_ERR_BAD_ARG;
@@ -959,6 +994,9 @@ extern "C" int lb200_mix1(lb200_plan* plan, const lb200_mix1_args* a)
   if ((rc = ensure_mirror(plan, plan->m_timf3, a->timf3_float.base, (size_t)K * 2 * a->timf3_float.size * 4))) return rc;
   // spectra this plan's own lb200_fft1 produced (filter-corrected, i.e. final) are still in the
   // mirror; anything else is brought over from the host ring
+  // a block kept on the device (LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE) whose mirror copy is not usable is in neither
+  // place: fail instead of mixing whatever the host ring holds
+  if (fft1_block_lost(plan, a->fft1_float.base, a->fft1_float.size, a->fft1_px, a->nblocks)) return LB200_ERR_BAD_ARG;
   if (env_int("LB200_MIX1_ALWAYS_UPLOAD", 0) || !fft1_mirror_valid(plan, a->fft1_float.base, a->fft1_float.size, a->fft1_px, a->nblocks))
     if ((rc = ring_copy(plan, plan->m_fft1.d, a->fft1_float.base, a->fft1_float.size * 4, (size_t)a->fft1_px * 4,
                         (size_t)plan->fft1_block * a->nblocks * 4, true))) return rc;

@@ -97,6 +97,7 @@ struct lb200_plan {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> events;
   std::vector<uint8_t> fft1_valid;
+  std::vector<uint8_t> fft1_host_stale;   // block produced with LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE: the host ring does not have it
   const void* fft1_valid_host = nullptr;
   // counters
   uint64_t launches = 0, h2d = 0, d2h = 0;

@@ -62,3 +62,30 @@ def test_strerror_covers_the_codes():
     lib = api.load_library()
     for code in (0, 3100, 3101, 3102, 3103, 3104, 1211, 1212):
         assert len(lib.lb200_strerror(code)) > 1
+
+
+def test_mix1_refuses_a_spectrum_that_exists_nowhere():
+    """LB200_FFT1_SPECTRUM_STAYS_ON_DEVICE leaves the host ring unwritten.  If the mirror copy is not the final
+    spectrum either (raw fft1_b output: apply_filtercorr = 0), lb200_mix1 must not mix the stale host ring."""
+    s = _setup()
+    plan = api.Plan(s)
+    try:
+        N = s.fft1_size
+        timf1 = np.zeros(8 * N * 4, np.uint8)
+        fft1 = np.zeros(8 * s.fft1_block, np.float32)
+        sumsq = np.zeros(16 * N, np.float32)
+        timf3_size = 16 * s.mix1_size * 2
+        timf3 = np.zeros(2 * timf3_size, np.float32)
+        states = api.new_states([s.selfreq_for_bin(300.4)])
+        mix = dict(fft1=fft1, fft1_px=0, nblocks=2, states=states, timf3=timf3, timf3_floats=timf3_size, timf3_pa=0)
+        # kept on the device, filter-corrected: fine
+        plan.fft1_host(timf1=timf1, ref=0, nblocks=2, fft1=fft1, sumsq=sumsq, keep_on_device=True)
+        plan.mix1_host(**mix)
+        # kept on the device but raw: the blocks are in neither place
+        plan.fft1_host(timf1=timf1, ref=0, nblocks=2, fft1=fft1, apply_fc=False, keep_on_device=True)
+        assert _code(lambda: plan.mix1_host(**mix)) == BAD_ARG
+        # written to the host ring again: fine again
+        plan.fft1_host(timf1=timf1, ref=0, nblocks=2, fft1=fft1, sumsq=sumsq)
+        plan.mix1_host(**mix)
+    finally:
+        plan.close()
