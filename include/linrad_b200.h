@@ -138,6 +138,14 @@ typedef struct lb200_fft1_args {
                                    fft1_c stores in fft1_xypower when fft1afc_flag > 0
                                    (fft1.c:4349-4368); NULL to skip.  One channel: fft1_power is
                                    power_rows itself. */
+  /* Several input rings in one call (ABI 3; lb200_fft1_dev, plans with LB200_FLOAT_INPUT, apply_filtercorr = 0):
+   * ring r = 0..no_of_rings-1 is read at timf1.base + r*timf1_ring_stride (bytes, same size and same timf1p_ref)
+   * and written at fft1_pa + r*fft1_pa_stride (floats, same fft1_float ring).  This is the loop over ss of
+   * make_fft3_all: timf3_float selections 2*timf3_size floats apart, fft3 blocks mm*fft3_size apart
+   * (fft3.c:232-233).  0 or 1 = one ring. */
+  int no_of_rings;
+  size_t timf1_ring_stride;
+  uint32_t fft1_pa_stride;
 } lb200_fft1_args;
 /* lb200_fft1 (host rings) only: leave fft1_float in the plan's device mirror of the ring and do
  * not write the host ring.  For set-ups where nothing on the host reads the spectrum (second FFT

@@ -74,6 +74,7 @@ class Fft1Args(C.Structure):
         ("fft1_sumsq", Ring), ("fft1_sumsq_pa", C.c_uint32), ("fft1_sumsq_counter", C.c_int),
         ("power_rows", C.c_void_p), ("flags", C.c_int),
         ("fft1_corrsum", Ring), ("corr_rows", C.c_void_p), ("xypower_rows", C.c_void_p),
+        ("no_of_rings", C.c_int), ("timf1_ring_stride", C.c_size_t), ("fft1_pa_stride", C.c_uint32),
     ]
 
 
@@ -278,10 +279,11 @@ class Plan:
         return a
 
     def fft1_dev(self, *, timf1, timf1_bytes, ref, nblocks, fft1, fft1_floats, fft1_pa=0, apply_fc=True,
-                 sumsq=None, sumsq_floats=0, sumsq_pa=0, counter=0, power=None):
+                 sumsq=None, sumsq_floats=0, sumsq_pa=0, counter=0, power=None, rings=1, ring_stride=0, pa_stride=0):
         """All pointers are raw device addresses (ints)."""
         a = self._fft1_args(timf1, timf1_bytes, ref, nblocks, fft1, fft1_floats, fft1_pa, apply_fc,
                             sumsq, sumsq_floats, sumsq_pa, counter, power)
+        a.no_of_rings, a.timf1_ring_stride, a.fft1_pa_stride = rings, ring_stride, pa_stride
         rc = self.lib.lb200_fft1_dev(self.h, C.byref(a))
         if rc:
             raise Lb200Error(rc, "lb200_fft1_dev")

@@ -77,6 +77,11 @@ struct Fft1K {
   // and the frame the Q word of sample n are taken from, relative to frame n (both 0 = off)
   int skew_i, skew_q;
   int stage_raw;            // fft1_fused_kernel, int16 one-channel IQ: raw spans by TMA bulk load (16-byte aligned spans only)
+  // several rings in one launch (fft1_small_kernel, raw output only): ring r = blockIdx.y reads at timf1 + r*ring_stride
+  // (bytes) and writes at out_pa + r*out_pa_stride (floats, same output ring) -- the selections of the third FFT
+  int nrings;
+  size_t ring_stride;
+  uint32_t out_pa_stride;
 };
 
 // I from the frame at off + skew_i, Q from the frame at off + skew_q (one-channel IQ formats)
@@ -151,6 +156,7 @@ fft1_small_kernel(const Fft1K p)
   const int group_size = p.power_rows ? 1 : p.avg1num;
   const int c0 = p.power_rows ? 0 : p.counter0;
   const int ngroups = (c0 + p.nblocks + group_size - 1) / group_size;
+  const uint8_t* const timf1_r = p.timf1 + (size_t)blockIdx.y * p.ring_stride;
   for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
     int b0 = g * group_size - c0;
     int b1 = b0 + group_size;
@@ -158,7 +164,7 @@ fft1_small_kernel(const Fft1K p)
     if (b1 > p.nblocks) b1 = p.nblocks;
     for (int b = b0; b < b1; b++) {
       const uint32_t start = p.ref0 + (uint32_t)b * p.blockbytes - p.pre_bytes;
-      float* outb = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
+      float* outb = p.out + ((p.out_pa + (uint32_t)blockIdx.y * p.out_pa_stride + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
 #pragma unroll 1
       for (int c = 0; c < NCH; c++) {
         float2 v[E];
@@ -168,9 +174,9 @@ fft1_small_kernel(const Fft1K p)
           const uint32_t off = (start + (uint32_t)idx * FRAME) & p.ring_mask;
           float2 s;
           if ((FMT == FMT_I16_1CH || FMT == FMT_I32_1CH) && (p.skew_i | p.skew_q))
-            s = load_iq_skew<FMT>(p.timf1, p.ring_mask, off, p.skew_i, p.skew_q);
+            s = load_iq_skew<FMT>(timf1_r, p.ring_mask, off, p.skew_i, p.skew_q);
           else
-            s = load_iq<FMT>(p.timf1, off, c);
+            s = load_iq<FMT>(timf1_r, off, c);
           if (REAL) {
             const float2 w = p.window ? reinterpret_cast<const float2*>(p.window)[idx] : make_float2(1.0f, 1.0f);
             v[e] = make_float2(s.x * w.x, s.y * w.y);

@@ -396,6 +396,16 @@ extern "C" int lb200_fft1_dev(lb200_plan* plan, const lb200_fft1_args* a)
   k.first_point = plan->cfg.fft1_first_point;
   k.last_point = plan->cfg.fft1_last_point;
   k.direction = plan->cfg.fft1_direction;
+  if (a->no_of_rings > 1) {
+    // the selections of the third FFT side by side: float input, raw output, one launch
+    if (plan->fmt < FMT_F32_1CH || a->apply_filtercorr) return LB200_ERR_UNSUPPORTED;
+    if ((a->timf1_ring_stride & 15u) || a->timf1_ring_stride < a->timf1.size) return LB200_ERR_BAD_ARG;
+    if (a->fft1_pa_stride % plan->fft1_block || (size_t)a->fft1_pa_stride < (size_t)plan->fft1_block * a->nblocks) return LB200_ERR_BAD_ARG;
+    if ((size_t)a->fft1_pa_stride * a->no_of_rings > a->fft1_float.size) return LB200_ERR_BAD_ARG;
+    k.nrings = a->no_of_rings;
+    k.ring_stride = a->timf1_ring_stride;
+    k.out_pa_stride = a->fft1_pa_stride;
+  }
 
   k.skew_i = plan->shift_i * plan->frame;
   k.skew_q = plan->shift_q * plan->frame;
@@ -679,6 +689,7 @@ extern "C" int lb200_fft1(lb200_plan* plan, const lb200_fft1_args* a)
 }
 static int fft1_host_pipeline(lb200_plan* plan, const lb200_fft1_args* a)
 {
+  if (a->no_of_rings > 1) return LB200_ERR_UNSUPPORTED;          // device rings only (one host ring is mirrored per plan)
   cudaSetDevice(plan->device);
   int rc;
   const size_t pre = plan->pre_bytes;

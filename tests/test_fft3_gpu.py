@@ -73,3 +73,48 @@ def test_float_input_needs_iq_dword_and_a_single_cta_size():
     s = sizing.PathSetup(input_mode=IQ_DATA | DWORD_INPUT | sizing.FLOAT_INPUT, rf_channels=1, ad_speed=96000, fft1_n=15, mix1_red_n=5)
     with pytest.raises(api.Lb200Error):
         api.Plan(s)
+
+
+def test_fft3_all_selections_in_one_call():
+    """no_of_rings: the loop over ss of make_fft3_all as one launch (timf3 selections 2*timf3_size floats apart, their fft3
+    blocks side by side) gives the same bits as one call per selection"""
+    import torch
+    n, ch, nsel, nblocks = 10, 1, 5, 7
+    s = sizing.PathSetup(input_mode=IQ_DATA | DWORD_INPUT | sizing.FLOAT_INPUT, rf_channels=ch, ad_speed=96000, fft1_n=n,
+                         mix1_red_n=3, sinpow=2)
+    N = s.fft1_size
+    timf3_size = 16 * N * 2 * ch
+    rng = np.random.default_rng(4)
+    host = (rng.standard_normal(nsel * 2 * timf3_size) * 1000.0).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    timf3 = torch.from_numpy(host).to(dev)
+    stride_out = nblocks * s.fft1_block
+    out_floats = 1
+    while out_floats < nsel * stride_out:
+        out_floats *= 2
+    a = torch.zeros(out_floats, dtype=torch.float32, device=dev)
+    b = torch.zeros(out_floats, dtype=torch.float32, device=dev)
+    plan = api.Plan(s)
+    try:
+        ref = s.fft1_interleave_points * s.frame_bytes + 4 * 2 * ch * 37
+        plan.fft1_dev(timf1=timf3.data_ptr(), timf1_bytes=timf3_size * 4, ref=ref, nblocks=nblocks, fft1=a.data_ptr(),
+                      fft1_floats=out_floats, fft1_pa=0, apply_fc=False, rings=nsel, ring_stride=2 * timf3_size * 4,
+                      pa_stride=stride_out)
+        for ss in range(nsel):
+            plan.fft1_dev(timf1=timf3.data_ptr() + ss * 2 * timf3_size * 4, timf1_bytes=timf3_size * 4, ref=ref, nblocks=nblocks,
+                          fft1=b.data_ptr(), fft1_floats=out_floats, fft1_pa=ss * stride_out, apply_fc=False)
+        plan.synchronize()
+        got, want = a.cpu().numpy(), b.cpu().numpy()
+        assert np.abs(want[: nsel * stride_out]).max() > 0
+        assert np.array_equal(got, want)
+        # and a plan without float input refuses it
+    finally:
+        plan.close()
+    s2 = sizing.PathSetup(input_mode=IQ_DATA | DWORD_INPUT, rf_channels=1, ad_speed=96000, fft1_n=n, mix1_red_n=3)
+    plan2 = api.Plan(s2)
+    try:
+        with pytest.raises(api.Lb200Error):
+            plan2.fft1_dev(timf1=timf3.data_ptr(), timf1_bytes=timf3_size * 4, ref=0, nblocks=1, fft1=a.data_ptr(), fft1_floats=out_floats,
+                           fft1_pa=0, apply_fc=False, rings=2, ring_stride=2 * timf3_size * 4, pa_stride=stride_out)
+    finally:
+        plan2.close()
