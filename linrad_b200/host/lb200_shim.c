@@ -449,3 +449,16 @@ for(ss=0; ss<genparm[MIX1_NO_OF_CHANNELS]; ss++)
   if(rc != LB200_OK){shim_fail(rc); return;}
   }
 }
+
+/* layout guard for the harness: the argument structures this object was compiled against */
+int lb200_shim_sizeof_args(int which)
+{
+switch(which)
+  {
+  case 0: return (int)sizeof(lb200_config);
+  case 1: return (int)sizeof(lb200_fft1_args);
+  case 2: return (int)sizeof(lb200_mix1_args);
+  case 3: return (int)sizeof(lb200_timf2_args);
+  }
+return -1;
+}

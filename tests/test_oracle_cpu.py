@@ -206,6 +206,18 @@ int main(void){
     assert got[:5] == sizes and got[5:10] == wg and got[10:] == offs
 
 
+def test_prebuilt_shim_harness_was_compiled_against_the_current_header():
+    """oracle/_ref/libref_shim.so travels prebuilt to the GPU box (the reference's sources do not): a header change without
+    `make -C oracle` would leave its shim object with stale argument structures"""
+    from oracle import refwrap
+    if not refwrap.shim_available():
+        pytest.skip("oracle/_ref/libref_shim.so not built")
+    _, api = _lib()
+    shim = C.CDLL(refwrap.SHIM_SO)
+    want = [C.sizeof(api.Config), C.sizeof(api.Fft1Args), C.sizeof(api.Mix1Args), C.sizeof(api.Timf2Args)]
+    assert [shim.lb200_shim_sizeof_args(i) for i in range(4)] == want
+
+
 def test_create_fails_loudly_without_gpu():
     """no CPU fallback: without a CUDA device lb200_create returns LB200_ERR_NO_DEVICE"""
     import torch
