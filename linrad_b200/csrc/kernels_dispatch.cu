@@ -185,9 +185,13 @@ cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k)
   const int group = k.power_rows ? 1 : k.avg1num;
   const int c0 = k.power_rows ? 0 : k.counter0;
   const int ngroups = (c0 + k.nblocks + group - 1) / group;
+  // Z of a sub-batch.  With the persistent four-step kernel fewer, longer launches win over keeping Z in L2
+  // (configs[2], 740 transforms: 0.367 ms in 4 sub-batches of 48 MB, 0.337 in 2, 0.328 in one of 194 MB), so the
+  // default budget is 256 MB there; the two-kernel path keeps its L2-sized sub-batches.
+  const bool piped = large && lb_fft1_pipe_supported(plan, k);
   const char* env = getenv("LB200_SCRATCH_MB");
-  const size_t budget = (size_t)(env ? atoi(env) : 48) << 20;
-  const size_t per_group = (size_t)group * nch * N * sizeof(float2) * ((large && !lb_fft1_pipe_supported(plan, k)) ? 2 : 1);
+  const size_t budget = (size_t)(env ? atoi(env) : (piped ? 256 : 48)) << 20;
+  const size_t per_group = (size_t)group * nch * N * sizeof(float2) * ((large && !piped) ? 2 : 1);
   int gps = (int)(budget / per_group);
   if (gps < 1) gps = 1;
   const size_t need = (size_t)gps * group * nch * N;
