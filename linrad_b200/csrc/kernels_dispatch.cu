@@ -194,6 +194,7 @@ cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k)
   const size_t per_group = (size_t)group * nch * N * sizeof(float2) * ((large && !piped) ? 2 : 1);
   int gps = (int)(budget / per_group);
   if (gps < 1) gps = 1;
+  if (gps > ngroups) gps = ngroups;                    // no more than this call needs
   const size_t need = (size_t)gps * group * nch * N;
   cudaError_t e = ensure_buf(&plan->d_zbuf, &plan->zbuf_elems, need);
   if (e != cudaSuccess) return e;
