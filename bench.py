@@ -42,9 +42,12 @@ WORKLOADS = {
     "cfg1": (dict(input_mode=IQ, rf_channels=1, ad_speed=96000, fft1_n=13, mix1_red_n=4), 6, [3000.37], 5920),
     "cfg2": (dict(input_mode=IQ | DW | TWO, rf_channels=2, ad_speed=192000, fft1_n=14, mix1_red_n=4), 7, [6000.74], 2960),
     "cfg3": (dict(input_mode=0, rf_channels=1, ad_speed=2400000, fft1_n=15, mix1_red_n=5), 2, [], 740),
-    "cfg4": (dict(input_mode=IQ, rf_channels=1, ad_speed=20000000, fft1_n=18, mix1_red_n=6), 20, CFG4_SEL, 60),
+    # 240 transforms per call and stream = 1.6 s of a 20 MS/s stream.  The persistent four-step kernel fills and drains
+    # its queue over ~8 transforms at either end of a launch: measured 0.155 ms per 60 transforms at 60 per call, 0.130 at
+    # 120, 0.124 at 240 (--batch N to try others; round 1 and the first round-2 lines used 60)
+    "cfg4": (dict(input_mode=IQ, rf_channels=1, ad_speed=20000000, fft1_n=18, mix1_red_n=6), 20, CFG4_SEL, 240),
     # configs[4]: 64 independent cfg4 streams on 8 GPUs = 8 streams per GPU (any --gpus N runs 8 per GPU)
-    "cfg5": (dict(input_mode=IQ, rf_channels=1, ad_speed=20000000, fft1_n=18, mix1_red_n=6), 20, CFG4_SEL, 60),
+    "cfg5": (dict(input_mode=IQ, rf_channels=1, ad_speed=20000000, fft1_n=18, mix1_red_n=6), 20, CFG4_SEL, 240),
 }
 STREAMS_PER_GPU = {"cfg5": 8}
 WORKLOAD_TEXT = {
