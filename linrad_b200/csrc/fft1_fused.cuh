@@ -126,6 +126,26 @@ LB_D void bulk_load_span(void* dst, const uint8_t* ring, uint32_t mask, uint32_t
   if (n1 < bytes) bulk_load(reinterpret_cast<unsigned char*>(dst) + n1, ring, bytes - n1, bar);
 }
 LB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// ---- 2-CTA cluster helpers (two-channel output path)
+LB_D uint32_t cluster_ctarank()
+{
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cta address -> the same offset in CTA `rank` of the cluster (shared::cluster window)
+LB_D uint32_t cluster_map(const void* p, uint32_t rank)
+{
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(rank));
+  return r;
+}
+LB_D void st_cluster_f2(uint32_t addr, float2 v)
+{
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+LB_D void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+LB_D void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 LB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 LB_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -345,6 +365,7 @@ fft1_fused_kernel(const Fft1K p)
         exch2_load<LOG2N>(v, xch, t);
       }
       mbar_arrive(&bars[1]);                   // my reads of the exchange buffer are done
+      if (NCH == 2 && p.cluster2) cluster_arrive();   // ... which my sibling will write into (waited for before the staging)
       radix32_gen(v, wb);
       // ---- epilogue: bin k = t + T*e; v holds (im, re) of the output value.  |z|^2 goes
       // straight to the fft1_sumsq row in L2 (fft1.c:4507-4520 sums the transforms of a group in
@@ -391,9 +412,34 @@ fft1_fused_kernel(const Fft1K p)
         // clock, and with room for only N/2 staged bins the second round has to wait for the
         // first, so plain streaming stores are faster here (profiles/r1_v4_notes.txt).
         fused_epilogue<FC, NCH, T, 0, 32>(v, p, prow, plain, rows, t, c);
-        float* outb = out_block + (size_t)t * MM + 2 * c;
+        if (p.cluster2) {
+          // The two channel CTAs of the group are one cluster and walk the same transforms in step.  Bins
+          // [0, N/2) of BOTH channels are collected in rank 0's exchange buffer, bins [N/2, N) in rank 1's, in
+          // fft1_float's own slot layout [re1, im1, re2, im2]: each CTA writes half of its values into its own
+          // buffer and half into its sibling's (st.shared::cluster), and then hands 8N contiguous bytes to the TMA
+          // unit: every global sector is written whole, once, off the LSU path.
+          const uint32_t rank = cluster_ctarank();
+          cluster_wait();                      // both CTAs have read their last exchange (arrived below)
+          const uint32_t lo = cluster_map(xch, 0), hi = cluster_map(xch, 1);
 #pragma unroll
-        for (int e = 0; e < 32; e++) lb_store_stream(reinterpret_cast<float2*>(outb + (size_t)e * (T * MM)), make_float2(v[e].y, v[e].x));
+          for (int e = 0; e < 16; e++) st_cluster_f2(lo + (uint32_t)((2 * (t + T * e) + c) * 8), make_float2(v[e].y, v[e].x));
+#pragma unroll
+          for (int e = 16; e < 32; e++) st_cluster_f2(hi + (uint32_t)((2 * (t + T * (e - 16)) + c) * 8), make_float2(v[e].y, v[e].x));
+          cluster_arrive();                    // my slots, here and over there, are written
+          cluster_wait();                      // ... and so are my sibling's
+          if (t == 0) {
+            fence_async_smem();
+            float* dst = out_block + (size_t)rank * (N / 2) * MM;
+#pragma unroll
+            for (int q = 0; q < 4; q++) bulk_store(dst + q * (N / 2), xch + q * (N / 4), N * 2);
+            bulk_commit();
+          }
+          staged = true;
+        } else {
+          float* outb = out_block + (size_t)t * MM + 2 * c;
+#pragma unroll
+          for (int e = 0; e < 32; e++) lb_store_stream(reinterpret_cast<float2*>(outb + (size_t)e * (T * MM)), make_float2(v[e].y, v[e].x));
+        }
       }
     }
   }

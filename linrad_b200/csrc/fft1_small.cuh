@@ -82,6 +82,9 @@ struct Fft1K {
   int nrings;
   size_t ring_stride;
   uint32_t out_pa_stride;
+  // fft1_fused_kernel, two-channel formats: the two channel CTAs of a group are launched as one 2-CTA cluster and
+  // hand whole [re1,im1,re2,im2] slots to the TMA unit (see the kernel); 0 = independent CTAs with 8-byte stores
+  int cluster2;
 };
 
 // I from the frame at off + skew_i, Q from the frame at off + skew_q (one-channel IQ formats)
