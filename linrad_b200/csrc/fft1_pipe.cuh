@@ -31,7 +31,6 @@
 #include <cstdio>
 #endif
 #include "fft1_fused.cuh"
-#include "fft1_real.cuh"
 
 #ifndef LB_PIPE_THREADS
 #define LB_PIPE_THREADS 256     // threads per CTA = 32-point slices per item
@@ -54,11 +53,6 @@ struct Fft1PipeK {
   int prefetch_ahead;    // L2 prefetch distance in transforms (0 = off)
   uint32_t out_blk0;     // tma_out: index of the call's first output block in the tensor map's outermost dimension
   uint32_t out_nblk;     // ... and the extent of that dimension (ring wrap)
-  // real input: the untangle / output mapping / fft1_c step (fft1_re.c:100-130, fft1_real.cuh) as a third role C in
-  // the same queue, lagC transforms behind the rows, reading the packed spectrum Z out of a ring of nslotsZ
-  // transforms in L2.  sync then also holds doneZ[nb] (rows of b written to Z) and doneC[nb] (Z slot of b read).
-  float2* Z;             // [nslotsZ * NCH][N]; nullptr: role B writes k.zbuf and a separate kernel finishes
-  int nslotsZ, lagC;
 };
 
 // ---- small PTX wrappers -----------------------------------------------------------------------
@@ -157,7 +151,6 @@ struct PipeCfg {
   static constexpr int BOX_IN = N2 < 256 ? N2 : 256;       // rows per input box
   static constexpr int BOX_OUT = N2 / 2 < 256 ? N2 / 2 : 256;
   static constexpr int IA = TILES_A * NCH, IB = TILES_B * NCH;   // items per transform
-  static constexpr int IC = REAL ? N / (32 * NTHREADS) : 0;       // role C: 32 output bins per thread, both channels
   static constexpr int cmax(int a, int b) { return a > b ? a : b; }
   static constexpr int IN_BYTES = (cmax(N1 * PITCH_A, TILE_BYTES) + 127) & ~127;
   static constexpr int WORK_BYTES = (cmax(cmax(NWARPS * AREA_A, ROUND_B), STAGE_B) + 127) & ~127;
@@ -176,9 +169,8 @@ struct PipeItem {
   int ready;             // input may be fetched right away
 };
 
-// queue position -> item.  Phase ph holds A(ph), B(ph - lagB), C(ph - lagB - lagC) as far as they exist, in that
-// order (IC == 0: no role C; then this is `lag` phases of A only, A(p) + B(p - lag), B only).
-LB_HD PipeItem pipe_decode2(int i, int nb, int lag, int IA, int IB)
+// queue position -> item.  Phases: `lag` phases of A only, then A(p) + B(p-lag), then B only.
+LB_HD PipeItem pipe_decode(int i, int nb, int lag, int IA, int IB)
 {
   PipeItem it;
   it.ready = 0;
@@ -202,44 +194,6 @@ LB_HD PipeItem pipe_decode2(int i, int nb, int lag, int IA, int IB)
   }
   return it;
 }
-LB_HD PipeItem pipe_decode3(int i, int nb, int lagB, int lagC, int IA, int IB, int IC)
-{
-  if (IC == 0) return pipe_decode2(i, nb, lagB, IA, IB);      // closed form, no local array
-  PipeItem it;
-  it.ready = 0;
-  it.role = -1; it.b = 0; it.j = 0;
-  const int LB = nb < lagB ? nb : lagB;
-  const int LC = IC > 0 ? (nb < lagC ? nb : lagC) : 0;
-  // phases where the set of roles changes, ascending
-  int brk[6] = {0, LB, LB + LC, nb, nb + LB, nb + LB + LC};
-  for (int a = 1; a < 6; a++) {
-    const int v = brk[a];
-    int c = a - 1;
-    while (c >= 0 && brk[c] > v) { brk[c + 1] = brk[c]; c--; }
-    brk[c + 1] = v;
-  }
-  for (int sgm = 0; sgm < 5; sgm++) {
-    const int s0 = brk[sgm], s1 = brk[sgm + 1];
-    if (s1 <= s0) continue;
-    const int nA = s0 < nb ? IA : 0;
-    const int nB = (s0 >= LB && s0 < nb + LB) ? IB : 0;
-    const int nC = (IC > 0 && s0 >= LB + LC && s0 < nb + LB + LC) ? IC : 0;
-    const int per = nA + nB + nC;
-    if (per == 0) continue;
-    const int cnt = (s1 - s0) * per;
-    if (i < cnt) {
-      const int ph = s0 + i / per;
-      const int o = i % per;
-      if (o < nA) { it.role = 0; it.b = ph; it.j = o; }
-      else if (o < nA + nB) { it.role = 1; it.b = ph - LB; it.j = o - nA; }
-      else { it.role = 2; it.b = ph - LB - LC; it.j = o - nA - nB; }
-      return it;
-    }
-    i -= cnt;
-  }
-  return it;
-}
-LB_HD PipeItem pipe_decode(int i, int nb, int lag, int IA, int IB) { return pipe_decode2(i, nb, lag, IA, IB); }
 
 // ---- the two-pass transform of M = 32*T points held by T lanes (32 points each) -----------------
 // pass 0: Q = 32/T radix-T butterflies without twiddles (lane t, butterfly q: v[q + r*Q]);
@@ -310,12 +264,8 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   int* const err = q.sync + 1;
   int* const doneA = q.sync + 2;
   int* const doneB = q.sync + 2 + p.nblocks;
-  int* const doneZ = q.sync + 2 + 2 * p.nblocks;     // role C only
-  int* const doneC = q.sync + 2 + 3 * p.nblocks;
   const int nb = p.nblocks;
-  const bool post = C::REAL && q.Z != nullptr;       // role C in the queue
-  const int ICq = post ? C::IC : 0;
-  const int total = nb * (C::IA + C::IB + ICq);
+  const int total = nb * (C::IA + C::IB);
 
   // last-pass twiddles: the five exact binary powers of w = exp(-2 pi i t / M) per lane position
   for (int i = tid; i < T1 * 5; i += C::NTHREADS) wbt[i] = q.Wn1[(i / 5) << (i % 5)];
@@ -329,20 +279,15 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   // ---- helpers ---------------------------------------------------------------------------------
   auto claim = [&](PipeItem& dst) {               // thread 0 only
     const int i = atomicAdd(head, 1);
-    PipeItem it = pipe_decode3(i < total ? i : total, nb, q.lag, q.lagC, C::IA, C::IB, ICq);
+    PipeItem it = i < total ? pipe_decode(i, nb, q.lag, C::IA, C::IB) : pipe_decode(total, nb, q.lag, C::IA, C::IB);
     if (it.role == 0) it.ready = 1;
     else if (it.role == 1) it.ready = ld_relaxed(doneA + it.b) >= C::IA * C::NWARPS ? 1 : 0;
-    else if (C::REAL && it.role == 2) it.ready = ld_relaxed(doneZ + it.b) >= C::IB ? 1 : 0;
     dst = it;
   };
   auto slot_of = [&](int b) { return b % q.nslots; };
   // fetch the input of an item into `in`; called by all threads, the item's dependency is satisfied
   auto issue_load = [&](const PipeItem& it) {
     const int tile = it.j / NCH;
-    if (C::REAL && it.role == 2) {
-      mbar_arrive(&bar_in);                       // nothing to stage: Z is read straight from L2
-      return;
-    }
     if (it.role == 0) {
       const uint32_t start = p.ref0 + (uint32_t)it.b * p.blockbytes - p.pre_bytes;
       const uint32_t base = start + (uint32_t)(tile * TA) * FRAME;
@@ -389,11 +334,6 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
     }
   };
 
-  // thread 0: block until the producers of an item's input are done
-  auto wait_dep = [&](const PipeItem& it) {
-    if (it.role == 1) pipe_wait(doneA + it.b, C::IA * C::NWARPS, err);
-    else if (C::REAL && it.role == 2) pipe_wait(doneZ + it.b, C::IB, err);
-  };
   if (tid == 0) {
     claim(items[0]);
     items[0].ready = 0;                          // the first item goes through the deferred path below
@@ -401,7 +341,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
   __syncthreads();
   PipeItem cur = items[0];
   if (cur.role >= 0) {
-    if (tid == 0) wait_dep(cur);
+    if (cur.role == 1 && tid == 0) pipe_wait(doneA + cur.b, C::IA * C::NWARPS, err);
     __syncthreads();
     issue_load(cur);
   }
@@ -520,13 +460,13 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
       LB_ST(1);
       if (nxt.role >= 0 && !nxt.ready) {
-        if (tid == 0) wait_dep(nxt);
+        if (nxt.role == 1 && tid == 0) pipe_wait(doneA + nxt.b, C::IA * C::NWARPS, err);
         __syncthreads();
         issue_load(nxt);
       }
       LB_ST(4);
       cur = nxt;
-    } else if (cur.role == 1) {
+    } else {
       // =============================== role B: TB rows of transform cur.b ======================
       const int r = tid & (TB - 1), t = tid / TB;
       LB_ST(3);
@@ -578,28 +518,7 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       const int b = cur.b;
       const int k1 = tile * TB + r;
       const bool use_tma_out = q.tma_out != 0;
-      if (post) {
-        // real input: the plain packed spectrum Z into its ring slot; role C finishes it.  The slot must have been
-        // read by the C items of transform b - nslotsZ.
-        if (b >= q.nslotsZ) {
-          if (lane == 0) pipe_wait(doneC + (b - q.nslotsZ), C::IC, err);
-          __syncwarp();
-        }
-        float2* zp = q.Z + ((size_t)(b % q.nslotsZ) * NCH + c) * N + k1 + (size_t)t * N1;
-#pragma unroll
-        for (int e = 0; e < 32; e++) zp[(size_t)e * (T2 * N1)] = v[e];
-        __syncwarp();
-        if (lane == 0) {                           // the last warp to get here publishes the rows
-          __threadfence_block();
-          const int old = atomicAdd(&a_arrived, 1);
-          __threadfence_block();
-          if (old == C::NWARPS - 1) {
-            a_arrived = 0;
-            __threadfence();
-            atomicAdd(doneZ + b, 1);
-          }
-        }
-      } else if (p.zbuf) {
+      if (p.zbuf) {
         // real input: the plain packed spectrum Z, finished by fft1_real_post_kernel
         if (!use_tma_out) {
           float2* zp = p.zbuf + ((size_t)(b - p.zb_first) * NCH + c) * N + k1 + (size_t)t * N1;
@@ -695,69 +614,12 @@ fft1_large_pipe_kernel(const Fft1PipeK q, const __grid_constant__ CUtensorMap ma
       }
       LB_ST(3);
       if (nxt.role >= 0 && !nxt.ready) {
-        if (tid == 0) wait_dep(nxt);
+        if (nxt.role == 1 && tid == 0) pipe_wait(doneA + nxt.b, C::IA * C::NWARPS, err);
         __syncthreads();
         issue_load(nxt);
       }
       LB_ST(4);
       cur = nxt;
-    } else {
-      // =============================== role C: 32*NTHREADS output bins of transform cur.b (real input) =====
-      // fft1_re.c:100-130 + fft1_c: X_k from Z_k and conj Z_{N-k}, output mapping, filter correction, |z|^2.
-      // Consecutive threads own consecutive bins: Z_k ascending, Z_{N-k} descending, outputs ascending.
-      if constexpr (C::REAL) {
-      pipe_mbar_wait(&bar_in, par, err);           // (no data: keeps the barrier's phases in step)
-      par ^= 1;
-      __syncthreads();                            // items[s^1] is visible
-      const PipeItem nxt = items[s ^ 1];
-      if (nxt.role >= 0 && nxt.ready) issue_load(nxt);
-      {
-        const int b = cur.b;
-        const float2* Zs = q.Z + (size_t)(b % q.nslotsZ) * NCH * N;
-        const int group_size = p.power_rows ? 1 : p.avg1num;
-        const int c0 = p.power_rows ? 0 : p.counter0;
-        const int g = (b + c0) / group_size;
-        float* rowp = (p.sumsq && !p.power_rows && p.fc_mode != 0) ? p.sumsq + ((p.sumsq_pa + (uint32_t)g * (uint32_t)N) & p.sumsq_mask) : nullptr;
-        float* prow = (p.power_rows && p.fc_mode != 0) ? p.power_rows + (size_t)b * N : nullptr;
-        float* outb = p.out + ((p.out_pa + (uint32_t)b * (uint32_t)(MM * N)) & p.out_mask);
-        const int j0 = cur.j * (32 * C::NTHREADS) + tid;
-#pragma unroll 4
-        for (int e = 0; e < 32; e++) {
-          const int j = j0 + e * C::NTHREADS;
-          const int k = real_bin_source(p, j, N);
-          const bool inr = (j >= p.first_point) && (j <= p.last_point);
-          float pw = 0.0f;
-          if (k >= -1) {
-#pragma unroll
-            for (int c = 0; c < NCH; c++) {
-              const float2 o = real_bin_value(p, Zs + (size_t)c * N, j, k, N, c, MM, inr, pw);
-              __stcs(reinterpret_cast<float2*>(outb + (size_t)j * MM + 2 * c), o);
-            }
-          }
-          if (prow) prow[j] = inr ? pw : 0.0f;
-          else if (rowp && inr) red_add(rowp + j, pw);
-        }
-        // the slot may be overwritten once every warp has read its share
-        __syncwarp();
-        if (lane == 0) {
-          __threadfence_block();
-          const int old = atomicAdd(&a_arrived, 1);
-          __threadfence_block();
-          if (old == C::NWARPS - 1) {
-            a_arrived = 0;
-            atomicAdd(doneC + b, 1);
-          }
-        }
-      }
-      if (nxt.role >= 0 && !nxt.ready) {
-        if (tid == 0) wait_dep(nxt);
-        __syncthreads();
-        issue_load(nxt);
-      }
-      cur = nxt;
-      } else {
-        cur.role = -1;                             // (no such items without real input)
-      }
     }
     s ^= 1;
   }

@@ -180,17 +180,6 @@ cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k)
 {
   const int log2n = plan->cfg.fft1_n;
   const bool large = log2n > 14;
-  {
-    // N >= 2^15: everything in the persistent kernel -- columns, rows and (role C) the untangle / output mapping /
-    // fft1_c step, with the packed spectrum in an L2-resident ring between them.  LB200_PIPE_POST=0: transform
-    // into zbuf and the separate fft1_real_post_kernel below.
-    const char* pp = getenv("LB200_PIPE_POST");
-    if (large && lb_fft1_pipe_supported(plan, k) && !(pp && atoi(pp) == 0)) {
-      Fft1K kk = k;
-      kk.zbuf = nullptr;
-      return lb_launch_fft1_pipe(plan, kk);           // counts its own launch
-    }
-  }
   const size_t N = (size_t)1 << log2n;
   const int nch = plan->nch;
   const int group = k.power_rows ? 1 : k.avg1num;

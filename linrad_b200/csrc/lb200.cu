@@ -307,7 +307,7 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   void* ptrs[] = {plan->d_foldcorr, plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
                   plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wn1, plan->d_Wn2,
                   plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2, plan->d_zbuf, plan->d_Wre, plan->d_powtmp,
-                  plan->d_wT, plan->d_pipe_y, plan->d_pipe_z, plan->d_pipe_sync, plan->d_invwin, plan->d_timf2_tmp,
+                  plan->d_wT, plan->d_pipe_y, plan->d_pipe_sync, plan->d_invwin, plan->d_timf2_tmp,
                   (plan->d_tab1_any != plan->d_tab1) ? (void*)plan->d_tab1_any : nullptr};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < lb200_plan::kJobSlots; i++) {

@@ -96,7 +96,7 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   const int ln = plan->cfg.fft1_n;
   pipe_fn_t fn = pipe_fn(plan->fmt);
   if (!fn) return cudaErrorNotSupported;
-  int geo[9];
+  int geo[8];
   cudaError_t e = fn(ln, geo, nullptr, nullptr, nullptr, 0, nullptr, plan->stream);
   if (e != cudaSuccess) return e;
   const int IA = geo[0], IB = geo[1], TB = geo[2], box_in = geo[3], box_out = geo[4], ln1 = geo[5], ln2 = geo[6];
@@ -127,42 +127,7 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
     plan->pipe_slots = want;
     if (!encode_map(plan->map_y, plan->d_pipe_y, ln1, ln2, (size_t)want * nch, TB, box_in)) memset(plan->map_y, 0, sizeof(plan->map_y));
   }
-  // ---- real input: role C (untangle + fft1_c) in the same queue, Z in a ring (LB200_PIPE_POST=0: separate kernel)
-  const int IC = geo[8];
-  const bool post = IC > 0 && !k.zbuf && env_i("LB200_PIPE_POST", 1);
-  int lagC = 0, zslots = 0;
-  if (post) {
-    const int per3 = IA + IB + IC;
-    lag = env_i("LB200_PIPE_LAG", (3 * resident / 2 + per3 - 1) / per3 + 1);
-    if (lag < 1) lag = 1;
-    slots = env_i("LB200_PIPE_SLOTS", 2 * lag);
-    if (slots < lag + 1) slots = lag + 1;
-    if (slots > nb) slots = nb;
-    if (slots < 1) slots = 1;
-    if (plan->pipe_slots < slots) {                      // (the Y ring was sized for the two-role lag above)
-      if (plan->d_pipe_y) cudaFree(plan->d_pipe_y);
-      plan->d_pipe_y = nullptr;
-      e = cudaMalloc((void**)&plan->d_pipe_y, (size_t)slots * nch * N * sizeof(float2));
-      if (e != cudaSuccess) return e;
-      plan->pipe_slots = slots;
-      if (!encode_map(plan->map_y, plan->d_pipe_y, ln1, ln2, (size_t)slots * nch, TB, box_in)) memset(plan->map_y, 0, sizeof(plan->map_y));
-    }
-    lagC = env_i("LB200_PIPE_LAGC", lag);
-    if (lagC < 1) lagC = 1;
-    zslots = 2 * lagC;
-    if (zslots > nb) zslots = nb;
-    if (zslots < 1) zslots = 1;
-    if (plan->pipe_zslots < zslots || !plan->d_pipe_z) {
-      if (plan->d_pipe_z) cudaFree(plan->d_pipe_z);
-      plan->d_pipe_z = nullptr;
-      plan->pipe_zslots = 0;
-      const int want = 2 * lagC > zslots ? 2 * lagC : zslots;
-      e = cudaMalloc((void**)&plan->d_pipe_z, (size_t)want * nch * N * sizeof(float2));
-      if (e != cudaSuccess) return e;
-      plan->pipe_zslots = want;
-    }
-  }
-  const size_t need_ints = 2 + 4 * (size_t)nb;
+  const size_t need_ints = 2 + 2 * (size_t)nb;
   if (plan->pipe_sync_ints < need_ints) {
     if (plan->d_pipe_sync) {
       if (lb_fft1_pipe_status(plan)) fprintf(stderr, "[lb200] four-step pipeline: a dependency wait timed out in an earlier call\n");
@@ -179,7 +144,7 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   // head and counters start at zero; the error flag [1] is sticky until read back
   e = cudaMemsetAsync(plan->d_pipe_sync, 0, sizeof(int), plan->stream);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(plan->d_pipe_sync + 2, 0, 4 * (size_t)nb * sizeof(int), plan->stream);
+  e = cudaMemsetAsync(plan->d_pipe_sync + 2, 0, 2 * (size_t)nb * sizeof(int), plan->stream);
   if (e != cudaSuccess) return e;
   plan->pipe_checked = false;
 
@@ -194,16 +159,13 @@ cudaError_t lb_launch_fft1_pipe(lb200_plan* plan, const Fft1K& k)
   q.sync = plan->d_pipe_sync;
   q.nslots = slots;
   q.lag = lag;
-  q.Z = post ? plan->d_pipe_z : nullptr;
-  q.nslotsZ = zslots;
-  q.lagC = lagC;
   q.prefetch_ahead = env_i("LB200_PIPE_PREFETCH", 3);
   static const unsigned char zero_map[128] = {0};
   const bool have_map_y = memcmp(plan->map_y, zero_map, 128) != 0;
   q.tma_in = (have_map_y && env_i("LB200_PIPE_TMA_IN", 1)) ? 1 : 0;
   // ---- output by TMA tensor stores: planar targets only (one channel, or the packed spectrum of real input)
   q.tma_out = 0;
-  if (!post && env_i("LB200_PIPE_TMA_OUT", 0) && (k.zbuf || nch == 1)) {   // measured: streaming stores are faster (0.150 vs 0.167 ms at configs[3], profiles/r2_notes.txt)
+  if (env_i("LB200_PIPE_TMA_OUT", 0) && (k.zbuf || nch == 1)) {   // measured: streaming stores are faster (0.150 vs 0.167 ms at configs[3], profiles/r2_notes.txt)
     void* base = k.zbuf ? (void*)k.zbuf : (void*)k.out;
     const size_t planes = k.zbuf ? plan->zbuf_elems / N : ((size_t)k.out_mask + 1) / (2 * N);
     if (planes >= 1 && (k.zbuf || (k.out_pa % (2 * N)) == 0)) {

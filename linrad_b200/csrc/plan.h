@@ -80,8 +80,6 @@ struct lb200_plan {
   float4* d_tab1_any = nullptr;     // pass-1 twiddles of the 32-points-per-thread plan (any input kind)
   float2* d_timf2_tmp = nullptr;    // timf2_tmp of a whole call
   size_t timf2_tmp_elems = 0;
-  float2* d_pipe_z = nullptr;       // real input, persistent kernel: ring of packed spectra between roles B and C
-  int pipe_zslots = 0;
   HostMirror m_t2_fft1, m_t2_ring, m_t2_pwr, m_t2_lim;
   // mix1 per-call staging: a small ring of pinned/device job tables so that consecutive
   // calls never wait for each other on the host
