@@ -218,3 +218,55 @@ def test_pipe_batch_cfg4_one_call_equals_calls_of_seven():
     # periodic input -> periodic spectra (transform 0 sees the empty ring in its overlap half)
     assert np.array_equal(f_big[1: nblocks - period], f_big[1 + period:])
     assert np.isfinite(f_big).all() and np.abs(f_big).max() > 0
+
+
+def _random_pipe_case(seed):
+    rng = np.random.default_rng(7000 + seed)
+    mode, ch = FORMATS[int(rng.integers(0, len(FORMATS)))]
+    n = int(rng.choice([15, 15, 16, 16, 17, 18]))
+    kw = dict(input_mode=mode, rf_channels=ch, ad_speed=int(rng.choice([2400000, 20000000])), fft1_n=n,
+              mix1_red_n=max(5, n - 12), sinpow=int(rng.choice([1, 2, 2, 3, 4])), direction=int(rng.choice([1, 1, -1])),
+              avg1num=int(rng.integers(1, 8)))
+    N = 1 << n
+    if rng.random() < 0.4:
+        lo = int(rng.integers(1, N // 3))
+        hi = int(rng.integers(2 * N // 3, N - 1))
+        kw.update(first_xpoint=lo, xpoints=hi - lo + 1)
+    nblocks = int(rng.integers(3, 20 if n <= 16 else 10))
+    chunk = int(rng.integers(1, nblocks + 1))
+    first = int(rng.integers(0, 64)) * 4096
+    return kw, nblocks, chunk, first
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_pipe_equals_legacy_random(seed):
+    """seeded sweep over formats, sizes, windows, direction, display range, averaging, call chunking and ring position:
+    the persistent kernel against the two-kernel path (which the parity tests pin on the compiled reference)"""
+    kw, nblocks, chunk, first = _random_pipe_case(seed)
+    s = sizing.PathSetup(**kw)
+    rawb = _input(s, nblocks, seed=seed)
+    with _Env(LB200_LARGE_LEGACY=1):
+        f0, p0 = _run(s, rawb, nblocks, chunk=chunk, first=first)
+    with _Env():
+        f1, p1 = _run(s, rawb, nblocks, chunk=chunk, first=first)
+    e = rel_rms(f1, f0)
+    assert e <= 4e-6, (e, kw, nblocks, chunk)     # two float32 transforms of different structure; with direction < 0 and a limited range
+                                                  # the post kernel adds its own rounding steps (measured up to 2.3e-6)
+    assert np.isfinite(f1).all()
+    assert np.array_equal(p1 == 0, p0 == 0)
+    if p0.size:
+        # same allowance as test_pipe_equals_legacy_direction_and_range: a few ulps of the strongest line in every bin
+        N, lo, hi = s.fft1_size, s.fft1_first_point, s.fft1_last_point
+        C = s.rf_channels
+        amp = np.zeros((nblocks, N))
+        for c in range(C):
+            amp = np.maximum(amp, np.hypot(f0[:, 2 * c::2 * C], f0[:, 2 * c + 1::2 * C]).astype(np.float64))
+        gain = float(s.filtercorr[2 * C * (N // 2)])
+        amp[:, :lo] *= gain
+        amp[:, hi + 1:] *= gain
+        a_peak, a_rms = amp.max(), np.sqrt((amp ** 2).mean())
+        eps = max(8 * np.sqrt(np.log2(N)) * 2.0 ** -23 * a_rms, 4 * 2.0 ** -23 * a_peak)
+        k = s.avg1num * C
+        allow = 5e-5 * p0 + 2 * np.sqrt(k * p0.astype(np.float64)) * eps + k * eps ** 2
+        bad = (np.abs(p1.astype(np.float64) - p0) > allow) & (p0 > 0)
+        assert not bad.any(), (int(bad.sum()), kw, nblocks, chunk)
