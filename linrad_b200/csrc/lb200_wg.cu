@@ -121,6 +121,8 @@ extern "C" int lb200_fft1_waterfall_dev(lb200_plan* plan, const lb200_wg_config*
   int rc = wg_fill(plan, c, a, k);
   if (rc) return rc;
   if (!a->wg_waterf_sum || !a->wg_waterf_yfac || !a->wg_waterf || a->wg_waterf_size < c->wg_xpixels) return LB200_ERR_BAD_ARG;
+  // the ring is a whole number of lines (wg_waterf_size = wg_xpixels*wg_waterf_lines, wide_graph.c:1374)
+  if (c->wg_xpixels > 0 && a->wg_waterf_size % c->wg_xpixels) return LB200_ERR_BAD_ARG;
   if (k.wrows == 0) return LB200_OK;
   cudaSetDevice(plan->device);
   int nunits = 0;
@@ -130,11 +132,9 @@ extern "C" int lb200_fft1_waterfall_dev(lb200_plan* plan, const lb200_wg_config*
     const WgLines lg = wg_lines(k.counter0, k.avg1num, k.waterfall_avgnum, k.wrows);
     const int gx = (nunits + 255) / 256;
     bool fused = false;
-    const bool aligned = k.xpixels > 0 && k.waterf_size % k.xpixels == 0;
-    if (lg.nl > 0 && (mode == 2 || !aligned)) {
+    if (lg.nl > 0 && mode == 2) {
       // interpolation: the tail of a line reaches into the first pixels of the line written before it
-      // (fft1.c:190-205); a ring that is not a whole number of lines: lines overlap partially.  Either way the
-      // lines have to land in time order: one launch each
+      // (fft1.c:190-205), so the lines have to land in time order: one launch each
       for (int L = 0; L < lg.nl; L++) {
         waterfall_kernel<<<gx, 256, 0, plan->stream>>>(k, mode, nunits, 0, L, 1);
         LB_CUDA(cudaGetLastError());
@@ -224,6 +224,8 @@ extern "C" int lb200_fft1_waterfall(lb200_plan* plan, const lb200_wg_config* c, 
   int rc = wg_fill(plan, c, a, k);
   if (rc) return rc;
   if (!a->wg_waterf_sum || !a->wg_waterf_yfac || !a->wg_waterf || a->wg_waterf_size < c->wg_xpixels) return LB200_ERR_BAD_ARG;
+  // the ring is a whole number of lines (wg_waterf_size = wg_xpixels*wg_waterf_lines, wide_graph.c:1374)
+  if (c->wg_xpixels > 0 && a->wg_waterf_size % c->wg_xpixels) return LB200_ERR_BAD_ARG;
   if (k.wrows == 0) return LB200_OK;
   cudaSetDevice(plan->device);
   if ((rc = wg_stage_rows(plan, a, k.pwg0, k.wrows))) return rc;
