@@ -35,6 +35,23 @@ static int wg_fill(lb200_plan* plan, const lb200_wg_config* c, const lb200_wg_ar
   else k.fresh_recalc = 2;
   k.recalc0 = a->state->fft1_sumsq_recalc;
   k.change_flag0 = a->state->change_fft1_flag;
+  // the window recurrence stepped up to 24 rows before the end of the call (integers only)
+  k.tail_row = 0;
+  k.tail_recalc = k.recalc0;
+  if (a->nrows > 48) {
+    int recalc = k.recalc0;
+    bool change = k.change_flag0 != 0;
+    const int step = k.xpoints / k.fresh_recalc;
+    const int t0 = a->nrows - 24;
+    for (int r = 0; r < t0; r++) {
+      if (change) { change = false; continue; }
+      if (recalc == k.last_point) recalc = k.first_point;
+      recalc += step;
+      if (recalc > k.last_point) recalc = k.last_point;
+    }
+    k.tail_row = t0;
+    k.tail_recalc = recalc;
+  }
   k.wsum = a->wg_waterf_sum;
   k.yfac = a->wg_waterf_yfac;
   k.waterf = a->wg_waterf;

@@ -30,6 +30,8 @@ struct WgK {
   int wg_first_point, wg_last_point;
   int avg2num, xpoints, fresh_recalc;
   int recalc0, change_flag0;
+  int tail_row, tail_recalc;            // the recalculation window's state on entering row tail_row (host-stepped): the
+                                        // kernel scans only the last rows of a long call for a bin's last fresh value
   // waterfall
   float* wsum;
   const float* yfac;
@@ -62,11 +64,9 @@ __global__ void __launch_bounds__(256) slowsum_kernel(const WgK p)
   // the arithmetic from there: the value is the reference's, the work no longer grows with the rows of a call.
   const bool change0 = p.change_flag0 != 0;
   int last = -1;
-  {
-    int recalc = p.recalc0;
-    bool change = change0;
-    const int step = p.xpoints / p.fresh_recalc;
-    for (int r = 0; r < p.nrows; r++) {
+  const int step = p.xpoints / p.fresh_recalc;
+  auto scan = [&](int r_first, int recalc, bool change) {
+    for (int r = r_first; r < p.nrows; r++) {
       if (change) {
         change = false;
         if (i >= p.wg_first_point && i <= p.wg_last_point) last = r;
@@ -78,7 +78,11 @@ __global__ void __launch_bounds__(256) slowsum_kernel(const WgK p)
       if (recalc > p.last_point) recalc = p.last_point;
       if (i >= ia && i <= recalc) last = r;
     }
-  }
+  };
+  // every in-band bin is recalculated every fresh_recalc (2..8) rows, so the last rows of the call decide; the whole
+  // call is scanned only if they do not (they always do for in-band bins when the tail is longer than a sweep)
+  if (p.tail_row > 0) scan(p.tail_row, p.tail_recalc, false);
+  if (last < 0) scan(0, p.recalc0, change0);
   const bool inband = i >= p.first_point && i <= p.last_point;
   if (last < 0 && !inband) return;                       // untouched by this call
   float s;
