@@ -7,6 +7,10 @@ using namespace lb;
 #ifndef LB_MIX1_LE_MID
 #define LB_MIX1_LE_MID 3
 #endif
+// ... and for mix1.size 2048 .. 8192
+#ifndef LB_MIX1_LE_BIG
+#define LB_MIX1_LE_BIG 4
+#endif
 
 // transforms side by side in one CTA, at most 8: about 512 threads for small mix1.size, 256 from
 // 1024 points up (measured: two half-size CTAs per SM overlap each other's barrier phases better
@@ -53,7 +57,7 @@ typedef cudaError_t (*mix1_launch_t)(const Mix1K&, int grid, cudaStream_t);
 mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem, int* par)
 {
   LB_MCASE(3, 3) LB_MCASE(4, 3) LB_MCASE(5, 3) LB_MCASE(6, 3) LB_MCASE(7, 3) LB_MCASE(8, 3) LB_MCASE(9, LB_MIX1_LE_MID)
-  LB_MCASE(10, LB_MIX1_LE_MID) LB_MCASE(11, 4) LB_MCASE(12, 4)
+  LB_MCASE(10, LB_MIX1_LE_MID) LB_MCASE(11, LB_MIX1_LE_BIG) LB_MCASE(12, LB_MIX1_LE_BIG)
   if (log2m == 13 && nch == 1) LB_MCASE1(13, 4, 1)
   return nullptr;
 }
