@@ -238,7 +238,7 @@ def _random_pipe_case(seed):
     return kw, nblocks, chunk, first
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("LB200_PIPE_SEEDS", "24"))))     # more seeds for a one-off sweep
 def test_pipe_equals_legacy_random(seed):
     """seeded sweep over formats, sizes, windows, direction, display range, averaging, call chunking and ring position:
     the persistent kernel against the two-kernel path (which the parity tests pin on the compiled reference)"""
@@ -249,9 +249,22 @@ def test_pipe_equals_legacy_random(seed):
         f0, p0 = _run(s, rawb, nblocks, chunk=chunk, first=first)
     with _Env():
         f1, p1 = _run(s, rawb, nblocks, chunk=chunk, first=first)
-    e = rel_rms(f1, f0)
-    assert e <= 4e-6, (e, kw, nblocks, chunk)     # two float32 transforms of different structure; with direction < 0 and a limited range
-                                                  # the post kernel adds its own rounding steps (measured up to 2.3e-6)
+    # Bins outside the display range keep the raw fft1_b scale (no filter correction), orders of magnitude above the
+    # scaled ones, and may hold nothing but noise: like tests/test_parity_gpu.py, the scaled bins are judged against
+    # their own energy and the raw ones against the energy of the whole raw spectrum (two float32 transforms of
+    # different structure differ by a few ulps of the STRONGEST line in every bin: measured 3e-5 of a tone-free
+    # region's own energy in a 300-seed sweep, 3e-7 of the spectrum's).
+    N, lo, hi = s.fft1_size, s.fft1_first_point, s.fft1_last_point
+    C = s.rf_channels
+    g3, r3 = f1.reshape(nblocks, N, 2 * C).astype(np.float64), f0.reshape(nblocks, N, 2 * C).astype(np.float64)
+    e = rel_rms(g3[:, lo:hi + 1], r3[:, lo:hi + 1])
+    assert e <= 4e-6, (e, kw, nblocks, chunk)     # (with direction < 0 and a limited range the post kernel adds rounding steps: up to 2.3e-6)
+    if lo > 0 or hi < N - 1:
+        gain = float(s.filtercorr[2 * C * (N // 2)])
+        out_err = ((g3[:, :lo] - r3[:, :lo]) ** 2).sum() + ((g3[:, hi + 1:] - r3[:, hi + 1:]) ** 2).sum()
+        raw_energy = (r3[:, :lo] ** 2).sum() + (r3[:, hi + 1:] ** 2).sum() + (r3[:, lo:hi + 1] ** 2).sum() / gain ** 2
+        eo = float(np.sqrt(out_err / max(raw_energy, 1e-300)))
+        assert eo <= 4e-6, (eo, kw, nblocks, chunk)
     assert np.isfinite(f1).all()
     assert np.array_equal(p1 == 0, p0 == 0)
     if p0.size:

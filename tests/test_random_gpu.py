@@ -2,6 +2,8 @@
 direction, display range, averaging, mixer reduction, selections, call chunking, and the rarely
 used fft1_b options), each case checked against the compiled reference exactly like the
 hand-picked parity cases.  The cases are fixed by their seeds, so a failure is reproducible."""
+import os
+
 import numpy as np
 import pytest
 
@@ -63,7 +65,7 @@ def _case(seed):
     return kw, nblocks, sel, chunk, over, ext, M
 
 
-@pytest.mark.parametrize("seed", range(96))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("LB200_RANDOM_SEEDS", "96"))))     # more seeds for a one-off sweep
 def test_random_configuration(seed):
     kw, nblocks, sel, chunk, over, ext, M = _case(seed)
     # same bound as the hand-picked cases (no extra slack): the per-bin allowance, or 1.25 x the distance of
