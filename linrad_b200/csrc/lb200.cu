@@ -22,9 +22,9 @@ using namespace lb;
 // ------------------------------------------------------------------------------------------
 // kernel launchers (explicit instantiation lives in kernels_*.cu so they compile in parallel)
 typedef cudaError_t (*fft1_small_launch_t)(const Fft1K&, int grid, cudaStream_t);
-typedef cudaError_t (*mix1_launch_t)(const Mix1K&, int grid, cudaStream_t);
+typedef cudaError_t (*mix1_launch_t)(const Mix1K&, int grid, int stage, cudaStream_t);
 fft1_small_launch_t lb_get_fft1_small(int log2n, int fmt, int variant, int* threads, size_t* smem);
-mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem, int* par);
+mix1_launch_t lb_get_mix1(int log2m, int nch, int* threads, size_t* smem, int* par, int* split);
 fft1_small_launch_t lb_get_fft1_fused(int log2n, int fmt, int fc, int* threads, size_t* smem);
 cudaError_t lb_launch_fft1_large(lb200_plan* plan, const Fft1K& k);
 cudaError_t lb_launch_fft1_real(lb200_plan* plan, const Fft1K& k);
@@ -263,7 +263,7 @@ extern "C" int lb200_create(const lb200_config* cfg, lb200_plan** out)
 
   // ---- mix1 (buf.c:1297-1300, prepare_mixer buf.c:55-111)
   if (cfg->mix1_n > 0) {
-    if (cfg->mix1_n < 3 || cfg->mix1_n > (plan->nch == 2 ? 12 : 13) || cfg->mix1_n > cfg->fft1_n) return fail(LB200_ERR_UNSUPPORTED);
+    if (cfg->mix1_n < 3 || cfg->mix1_n > (plan->nch == 2 ? 13 : 14) || cfg->mix1_n > cfg->fft1_n) return fail(LB200_ERR_UNSUPPORTED);
     plan->M = 1 << cfg->mix1_n;
     if (!cfg->mix1_fqwin) return fail(LB200_ERR_BAD_CONFIG);
     std::vector<float2> w;
@@ -307,7 +307,7 @@ extern "C" void lb200_destroy(lb200_plan* plan)
   void* ptrs[] = {plan->d_foldcorr, plan->d_window, plan->d_Wn, plan->d_filtercorr, plan->d_Wm, plan->d_fqwin, plan->d_mixwin,
                   plan->d_cos2win, plan->d_sin2win, plan->d_scratch, plan->d_Wn1, plan->d_Wn2,
                   plan->d_wsign, plan->d_wsign_g, plan->d_edge, plan->d_tab1, plan->d_scratch2, plan->d_zbuf, plan->d_Wre, plan->d_powtmp,
-                  plan->d_wT, plan->d_pipe_y, plan->d_pipe_sync, plan->d_invwin, plan->d_timf2_tmp,
+                  plan->d_wT, plan->d_pipe_y, plan->d_pipe_sync, plan->d_invwin, plan->d_timf2_tmp, plan->d_mix_y,
                   (plan->d_tab1_any != plan->d_tab1) ? (void*)plan->d_tab1_any : nullptr};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < lb200_plan::kJobSlots; i++) {
@@ -931,8 +931,31 @@ static int launch_mix1(lb200_plan* plan, const lb200_mix1_args* a, const float* 
   k.mode = mix1_mode(plan);
   int threads = 0, par = 1;
   size_t smem = 0;
-  mix1_launch_t fn = lb_get_mix1(plan->cfg.mix1_n, plan->nch, &threads, &smem, &par);
+  int split = 0;
+  mix1_launch_t fn = lb_get_mix1(plan->cfg.mix1_n, plan->nch, &threads, &smem, &par, &split);
   if (!fn) return LB200_ERR_UNSUPPORTED;
+  if (split) {
+    // mix1.size 16384 (8192 with two channels): two launches, every transform its own work item, the
+    // back-transformed blocks pass through a scratch buffer
+    const size_t ybytes = (size_t)K * B * plan->nch * plan->M * sizeof(float2);
+    if (plan->mix_y_bytes < ybytes) {
+      if (plan->d_mix_y) cudaFree(plan->d_mix_y);
+      plan->d_mix_y = nullptr;
+      plan->mix_y_bytes = 0;
+      LB_CUDA(cudaMalloc(&plan->d_mix_y, ybytes));
+      plan->mix_y_bytes = ybytes;
+    }
+    k.ybuf_g = (float2*)plan->d_mix_y;
+    k.runlen = 1;
+    int grid = K * B;
+    const int cap2 = plan->sm_count * 8;
+    if (grid > cap2) grid = cap2;
+    LB_CUDA(fn(k, grid, 1, plan->stream));
+    LB_CUDA(fn(k, grid, 2, plan->stream));
+    LB_CUDA(cudaEventRecord(plan->mixjobs_done[slot], plan->stream));
+    plan->launches += 2;
+    return LB200_OK;
+  }
   // run length: a whole number of PAR-wide chunks (the first chunk of a run spends one lane on
   // the rebuilt predecessor), long enough to amortise that lane, short enough to fill the GPU
   int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -963,7 +986,7 @@ static int launch_mix1(lb200_plan* plan, const lb200_mix1_args* a, const float* 
   int grid = nruns;
   const int cap = target * 4;
   if (grid > cap) grid = cap;
-  LB_CUDA(fn(k, grid, plan->stream));
+  LB_CUDA(fn(k, grid, 0, plan->stream));
   LB_CUDA(cudaEventRecord(plan->mixjobs_done[slot], plan->stream));
   plan->launches++;
   return LB200_OK;

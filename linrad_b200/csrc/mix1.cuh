@@ -43,6 +43,7 @@ struct Mix1K {
   int first_point, last_point;
   int Mi, Mn, cross;      // mix1.interleave_points, new_points, crossover_points
   int mode;               // 0 none, 1 sin^2 (Mi==Mn), 2 crossover
+  float2* ybuf_g;         // two-launch form (STAGE 1 / 2): back-transformed blocks [nsel][nblocks][NCH][M]
 };
 
 // sin/cos of a mixer phase (the reference takes sin()/cos() in double of the float phase,
@@ -85,8 +86,13 @@ LB_D float mix1_taper(const float* fqwin, int i, int M)
 }
 
 // Threads per CTA: PAR transforms side by side, each by NCH*T threads.
-template <int LOG2M, int LOG2E, int NCH, int PAR>
-__global__ void __launch_bounds__((PAR * NCH) << (LOG2M - LOG2E), (((PAR * NCH) << (LOG2M - LOG2E)) <= 512 ? 2 : 1))
+// STAGE 0: everything in one kernel (runs of consecutive transforms, the predecessor's tail found in shared
+// memory).  mix1.size 16384 (8192 with two channels) does not leave room for that: there the two halves are two
+// launches with every transform its own work item -- STAGE 1 = gather + taper + back transform into ybuf_g,
+// STAGE 2 = phase rotation and overlap from ybuf_g into timf3.  (For the sizes that fit, the two-launch form was
+// measured slower than STAGE 0: configs[3] pass 0.234 vs 0.231 ms, profiles/r2_notes.txt.)
+template <int LOG2M, int LOG2E, int NCH, int PAR, int STAGE>
+__global__ void __launch_bounds__((PAR * NCH) << (LOG2M - LOG2E), (((PAR * NCH) << (LOG2M - LOG2E)) <= 512 && LOG2M < 13 + (NCH == 1) ? 2 : 1))
 mix1_kernel(const Mix1K p)
 {
   using P = Plan<LOG2M, LOG2E>;
@@ -109,7 +115,7 @@ mix1_kernel(const Mix1K p)
   float* ph_t = reinterpret_cast<float*>(xch_all + lane * NCH * XCH);
   float* ph_r = ph_t + M;
   Twiddles<P> tw;
-  load_twiddles<P>(tw, p.Wm, t);
+  if (STAGE != 2) load_twiddles<P>(tw, p.Wm, t);
 
   const int runs_per_sel = (p.nblocks + p.runlen - 1) / p.runlen;
   const int nruns = runs_per_sel * p.nsel;
@@ -127,10 +133,10 @@ mix1_kernel(const Mix1K p)
     const Mix1Job* jobs = p.jobs + (size_t)ss * p.nblocks;
     float* t3 = p.timf3 + (size_t)ss * p.sel_stride;
     // ystart = bfirst-1 rebuilds the predecessor's tail when this run does not start the call
-    const int ystart = (bfirst > 0 && carry_len > 0) ? bfirst - 1 : bfirst;
+    const int ystart = (STAGE == 0 && bfirst > 0 && carry_len > 0) ? bfirst - 1 : bfirst;
     // the spectra this run will gather (fft1_float has long left L2 when the batch is large): one thread
     // per transform asks for its M bins now, so that only the first gather of the run waits for DRAM
-    if (tid < blast - ystart && tid < 32) {
+    if (STAGE != 2 && tid < blast - ystart && tid < 32) {
       const Mix1Job pj = jobs[ystart + tid];
       if (pj.point >= 0) {
         int lo = pj.point - M / 2, hi = pj.point + M / 2;
@@ -149,7 +155,9 @@ mix1_kernel(const Mix1K p)
       Mix1Job job;
       job.point = -1;
       if (active) job = jobs[b];
-      float2* ybuf = ybuf_all + (((b - ystart) % SLOTS) * NCH + ch) * M;
+      float2* ybuf = STAGE == 0 ? ybuf_all + (((b - ystart) % SLOTS) * NCH + ch) * M
+                                : p.ybuf_g + (((size_t)ss * p.nblocks + (active ? b : 0)) * NCH + ch) * M;
+      if (STAGE != 2) {
       // ---- gather + taper (mix1.c:1015-1030, 113-135); idle lanes run the transform on zeros
       float2 v[E];
       if (job.point >= 0) {
@@ -173,6 +181,11 @@ mix1_kernel(const Mix1K p)
 #pragma unroll
         for (int e = 0; e < E; e++) ybuf[t + T * e] = v[e];
       }
+      }
+      if (STAGE == 1) {
+        __syncthreads();                       // the exchange buffer is free for the next chunk
+        continue;
+      }
       // ---- exact float phase chains for this transform (mix1.c:143-153,164-186)
       if (emit && job.point >= 0) {
         // one closed-form jump per 16 samples (it costs ~300 instructions), then plain float adds
@@ -195,8 +208,10 @@ mix1_kernel(const Mix1K p)
       }
       __syncthreads();
       if (emit) {
-        const float2* yb = ybuf_all + (((b - ystart) % SLOTS) * NCH) * M;          // [NCH][M]
-        const float2* cb = ybuf_all + (((b - 1 - ystart + SLOTS) % SLOTS) * NCH) * M;   // predecessor
+        const float2* yb = STAGE == 0 ? ybuf_all + (((b - ystart) % SLOTS) * NCH) * M          // [NCH][M]
+                                      : p.ybuf_g + (((size_t)ss * p.nblocks + b) * NCH) * M;
+        const float2* cb = STAGE == 0 ? ybuf_all + (((b - 1 - ystart + SLOTS) % SLOTS) * NCH) * M   // predecessor
+                                      : p.ybuf_g + (((size_t)ss * p.nblocks + (b > 0 ? b - 1 : 0)) * NCH) * M;
         const bool from_ring = (b == 0);      // first transform of the call: tail is in timf3
         if (job.point < 0) {
           // mix1_clear: zero timf3_block floats
@@ -263,6 +278,13 @@ template <int LOG2M, int NCH, int PAR>
 constexpr size_t mix1_smem()
 {
   return sizeof(float2) * (size_t)(PAR * NCH * ((1 << LOG2M) + (1 << LOG2M) / 32 + 32) + (PAR + 1) * NCH * (1 << LOG2M));
+}
+
+// the two-launch form keeps only the exchange slices (STAGE 2: the phase chains) in shared memory
+template <int LOG2M, int NCH, int PAR>
+constexpr size_t mix1_smem_split()
+{
+  return sizeof(float2) * (size_t)(PAR * NCH * ((1 << LOG2M) + (1 << LOG2M) / 32 + 32));
 }
 
 }  // namespace lb

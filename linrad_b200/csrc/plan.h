@@ -80,6 +80,8 @@ struct lb200_plan {
   float4* d_tab1_any = nullptr;     // pass-1 twiddles of the 32-points-per-thread plan (any input kind)
   float2* d_timf2_tmp = nullptr;    // timf2_tmp of a whole call
   size_t timf2_tmp_elems = 0;
+  void* d_mix_y = nullptr;          // mix1.size 16384 / 8192 (two channels): back-transformed blocks between the two launches
+  size_t mix_y_bytes = 0;
   HostMirror m_t2_fft1, m_t2_ring, m_t2_pwr, m_t2_lim;
   // mix1 per-call staging: a small ring of pinned/device job tables so that consecutive
   // calls never wait for each other on the host

@@ -24,9 +24,9 @@ def _code(fn):
 
 
 def test_create_rejects_what_is_not_built():
-    # mix1.size above what one CTA can hold (documented limit: 8192 one channel, 4096 two)
-    assert _code(lambda: api.Plan(_setup(fft1_n=16, mix1_red_n=2))) == UNSUPPORTED
-    assert _code(lambda: api.Plan(_setup(input_mode=IQ_DATA | TWO_CHANNELS, rf_channels=2, fft1_n=15, mix1_red_n=2))) == UNSUPPORTED
+    # mix1.size above what is built (documented limit: 16384 one channel, 8192 two; the reference allows 32768)
+    assert _code(lambda: api.Plan(_setup(fft1_n=17, mix1_red_n=2))) == UNSUPPORTED
+    assert _code(lambda: api.Plan(_setup(input_mode=IQ_DATA | TWO_CHANNELS, rf_channels=2, fft1_n=16, mix1_red_n=2))) == UNSUPPORTED
     # IQ-only options on real input / one channel
     fold = np.zeros(2 * 2048, np.float32)
     assert _code(lambda: api.Plan(_setup(input_mode=0), foldcorr=fold)) == UNSUPPORTED

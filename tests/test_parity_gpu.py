@@ -280,6 +280,23 @@ def test_large_iq16_vs_float_reference(n, version):
     _compare(kw, 7, [0.3663 * N + 0.37, 0.61 * N], chunk=4)
 
 
+@pytest.mark.parametrize("sinpow", [2, 3, 0])
+def test_mix1_size_16384_one_channel(sinpow):
+    """mix1.size 16384 does not fit the one-kernel mixer (predecessor tail on chip): two launches through a scratch
+    buffer.  All three overlap schemes, a cleared selection, calls of uneven size."""
+    n = 16
+    kw = dict(input_mode=IQ_DATA, rf_channels=1, ad_speed=2400000, fft1_n=n, mix1_red_n=2, version=7)
+    N = 1 << n
+    _compare(kw, 7, [0.3663 * N + 0.37, -1, 0.61 * N], chunk=3, sinpow=sinpow)
+
+
+def test_mix1_size_8192_two_channels():
+    n = 15
+    kw = dict(input_mode=IQ_DATA | TWO_CHANNELS, rf_channels=2, ad_speed=2400000, fft1_n=n, mix1_red_n=2, version=7)
+    N = 1 << n
+    _compare(kw, 6, [0.41 * N + 0.2, 0.7 * N], chunk=4)
+
+
 @pytest.mark.parametrize("n,mode", [(17, IQ_DATA | TWO_CHANNELS), (18, IQ_DATA | TWO_CHANNELS | DWORD_INPUT)])
 def test_large_two_channel_vs_double_reference(n, mode):
     """above 65536 points the reference only has its double precision version 20 (2 channels)"""
