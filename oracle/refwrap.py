@@ -37,6 +37,35 @@ def cufft_available():
     return os.path.exists(CUFFT_SO)
 
 
+# the reference's own 18-bit codec, assembled from getiq64.s through oracle/nasm2gas.py (oracle/Makefile)
+GETIQ_BIN = os.path.join(_HERE, "_ref", "getiq_check")
+
+
+def getiq_available():
+    return os.path.exists(GETIQ_BIN)
+
+
+def _getiq(mode, nwords, payload):
+    import subprocess
+    r = subprocess.run([GETIQ_BIN, mode, str(nwords)], input=payload, capture_output=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"getiq_check {mode} failed rc={r.returncode}")
+    return r.stdout
+
+
+def ref_expand_rawdat(packed):
+    """expand_rawdat (getiq64.s:158-220) itself: 9 packed bytes -> 4 int32 words"""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    nwords = packed.size // 9 * 4
+    return np.frombuffer(_getiq("expand", nwords, packed.tobytes()), np.int32).copy()
+
+
+def ref_compress_rawdat(words, net=False):
+    """compress_rawdat_disk / _net (getiq64.s:39-156) themselves: 4 int32 words -> 9 bytes"""
+    words = np.ascontiguousarray(words, np.int32)
+    return np.frombuffer(_getiq("compress_net" if net else "compress", words.size, words.tobytes()), np.uint8).copy()
+
+
 class RefOracle:
     """One instance at a time (the reference keeps its state in globals)."""
 

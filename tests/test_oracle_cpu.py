@@ -206,6 +206,28 @@ int main(void){
     assert got[:5] == sizes and got[5:10] == wg and got[10:] == offs
 
 
+def test_18bit_codec_port_equals_the_assembled_reference():
+    """getiq64.s is NASM source and NASM is not in the image; oracle/nasm2gas.py rewrites it mechanically into GNU
+    assembler syntax and gcc assembles it (oracle/_ref/getiq_check).  The C / numpy restatements that the GPU kernel is
+    checked against must be that code bit for bit: expand_rawdat and both compress_rawdat variants, random data,
+    group counts around the kernel's tile size."""
+    from oracle import refwrap
+    if not refwrap.getiq_available():
+        pytest.skip("oracle/_ref/getiq_check not built")
+    rng = np.random.default_rng(18)
+    for groups in (1, 2, 255, 256, 257, 4099):
+        packed = rng.integers(0, 256, 9 * groups, dtype=np.uint8)
+        want = refwrap.ref_expand_rawdat(packed)
+        assert np.array_equal(port.expand_rawdat(packed, 16 * groups), want)
+        assert np.array_equal(port.expand_rawdat_numpy(packed, 16 * groups), want)
+        words = rng.integers(-2**31, 2**31, 4 * groups, dtype=np.int64).astype(np.int32)
+        assert np.array_equal(port.compress_rawdat(words), refwrap.ref_compress_rawdat(words))
+        assert np.array_equal(port.compress_rawdat(words), refwrap.ref_compress_rawdat(words, net=True))
+    # extreme words
+    words = np.array([0x7fffffff, -0x80000000, -1, 0, 0x00003fff, 0x00004000, -0x4000, 0x12345678], np.int32)
+    assert np.array_equal(port.compress_rawdat(words), refwrap.ref_compress_rawdat(words))
+
+
 def test_prebuilt_shim_harness_was_compiled_against_the_current_header():
     """oracle/_ref/libref_shim.so travels prebuilt to the GPU box (the reference's sources do not): a header change without
     `make -C oracle` would leave its shim object with stale argument structures"""
