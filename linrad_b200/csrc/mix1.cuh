@@ -101,7 +101,8 @@ mix1_kernel(const Mix1K p)
   constexpr int SLOTS = PAR + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: xch[PAR][NCH][M+M/32+32] | ybuf[SLOTS][NCH][M]; after its transform a lane reuses
-  // its first exchange slice for the two phase chains (ph_t[M] | ph_r[M/2] floats)
+  // its first exchange slice for the two phase chains (ph_t | ph_r, one pad float per 16: a thread fills 16
+  // consecutive phases, so the pad puts the threads of a warp 17 floats apart = on 32 different banks)
   float2* xch_all = reinterpret_cast<float2*>(smem_raw);
   constexpr int XCH = M + M / 32 + 32;
   float2* ybuf_all = xch_all + PAR * NCH * XCH;
@@ -113,7 +114,8 @@ mix1_kernel(const Mix1K p)
   const int t = lt - ch * T;
   float2* xch = xch_all + (lane * NCH + ch) * XCH;
   float* ph_t = reinterpret_cast<float*>(xch_all + lane * NCH * XCH);
-  float* ph_r = ph_t + M;
+  float* ph_r = ph_t + M + M / 16;
+  auto pp = [](int i) { return i + (i >> 4); };
   Twiddles<P> tw;
   if (STAGE != 2) load_twiddles<P>(tw, p.Wm, t);
 
@@ -195,7 +197,7 @@ mix1_kernel(const Mix1K p)
         if (i0 < nt) {
           float x = lb_phase_advance(job.t1, job.t2, i0);
           int i1 = i0 + chunk_t; if (i1 > nt) i1 = nt;
-          for (int i = i0; i < i1; i++) { ph_t[i] = x; x = lb_float_add(x, job.t2); }
+          for (int i = i0; i < i1; i++) { ph_t[pp(i)] = x; x = lb_float_add(x, job.t2); }
         }
         int chunk_r = (nr + LANE_THREADS - 1) / LANE_THREADS;
         if (chunk_r < 16 && nr > 0) chunk_r = 16;
@@ -203,7 +205,7 @@ mix1_kernel(const Mix1K p)
         if (chunk_r > 0 && i0 < nr) {
           float x = lb_phase_advance(job.r1, job.r2, i0);
           int i1 = i0 + chunk_r; if (i1 > nr) i1 = nr;
-          for (int i = i0; i < i1; i++) { ph_r[i] = x; x = lb_float_add(x, job.r2); }
+          for (int i = i0; i < i1; i++) { ph_r[pp(i)] = x; x = lb_float_add(x, job.r2); }
         }
       }
       __syncthreads();
@@ -219,9 +221,9 @@ mix1_kernel(const Mix1K p)
         } else {
           for (int s = lt; s < nt; s += LANE_THREADS) {
             float st, ct;
-            mix1_sincos(ph_t[s], &st, &ct);
+            mix1_sincos(ph_t[pp(s)], &st, &ct);
             float sr = 0.f, cr = 1.f;
-            if (s < nr) mix1_sincos(ph_r[s], &sr, &cr);
+            if (s < nr) mix1_sincos(ph_r[pp(s)], &sr, &cr);
             const uint32_t o = (job.dst + (uint32_t)s * MM) & p.timf3_mask;
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
