@@ -201,7 +201,9 @@ mix1_kernel(const Mix1K p)
         }
         int chunk_r = (nr + LANE_THREADS - 1) / LANE_THREADS;
         if (chunk_r < 16 && nr > 0) chunk_r = 16;
-        i0 = lt * chunk_r;
+        // the second chain is dealt from the other end of the lane: with 16 samples per thread each chain keeps
+        // only part of the threads busy, and this way they are different threads
+        i0 = (LANE_THREADS - 1 - lt) * chunk_r;
         if (chunk_r > 0 && i0 < nr) {
           float x = lb_phase_advance(job.r1, job.r2, i0);
           int i1 = i0 + chunk_r; if (i1 > nr) i1 = nr;
