@@ -1,6 +1,7 @@
 /* linrad_b200.h -- C ABI of liblinrad_b200.so, the B200 (sm_100a) replacement for Linrad's
  * wideband DSP hot path:  timf1 -> (unpack, window) -> fft1 -> fft1_float -> |X|^2 ->
- * fft1_sumsq -> mix1 -> timf3.
+ * fft1_sumsq -> mix1 -> timf3, with the wide-graph consumers of fft1_sumsq (slowsum, waterfall), the input codecs
+ * of recorded files, and the front ends of the second and third FFT (make_timf2, the transforms of make_fft3_all).
  *
  * The reference (fventuri/linrad) has no FFI for this path: its boundary is a set of C
  * functions working on global ring buffers.  Every entry point
